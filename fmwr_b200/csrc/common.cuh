@@ -1,0 +1,237 @@
+// fmwr_b200 internal header: error plumbing, device buffers, handle structs, warp helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#include "../../include/fmwr_b200.h"
+
+namespace fmwr {
+
+// ---- errors ---------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define FMWR_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      char _b[512];                                                                              \
+      snprintf(_b, sizeof _b, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__,   \
+               __LINE__, #expr);                                                                 \
+      throw ::fmwr::Error(_e == cudaErrorMemoryAllocation ? FMWR_ERR_NOMEM : FMWR_ERR_CUDA, _b); \
+    }                                                                                            \
+  } while (0)
+
+#define FMWR_REQUIRE(cond, code, msg)              \
+  do {                                             \
+    if (!(cond)) throw ::fmwr::Error((code), (msg)); \
+  } while (0)
+
+// wraps the body of every extern "C" entry point: nothing throws across the ABI
+template <class F>
+static inline int guarded(F&& f) noexcept
+{
+  try {
+    f();
+    return FMWR_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return FMWR_ERR_ARG;
+  } catch (...) {
+    set_last_error("unknown failure");
+    return FMWR_ERR_ARG;
+  }
+}
+
+// ---- device buffer ----------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() {}
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count)
+  {
+    if (count == n && p) return;
+    release();
+    if (count == 0) count = 1;
+    FMWR_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void zero(cudaStream_t s) { if (p) FMWR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// pinned host staging buffer
+template <class T>
+struct HBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~HBuf() { if (p) cudaFreeHost(p); }
+  void ensure(size_t count)
+  {
+    if (count <= n) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    FMWR_CUDA(cudaMallocHost((void**)&p, count * sizeof(T)));
+    n = count;
+  }
+};
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace fmwr
+
+// ---- handles (C structs named in the public header) ------------------------------------------------
+struct fmwr_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t copy_stream = nullptr;  // H2D / D2H staging
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
+  int64_t launches = 0;
+  fmwr::DBuf<double> pn_table;   // fast_pnorm Y table   (2862 f64)
+  fmwr::DBuf<double> dp_table;   // fast_dpnorm Y table  (40002 f64)
+  fmwr::DBuf<char> flush_buf;    // L2 flush scratch
+  fmwr::DBuf<double> red_scratch;  // reductions
+  fmwr::HBuf<double> h_scalar;
+};
+
+struct fmwr_data {
+  fmwr_ctx* ctx = nullptr;
+  int64_t n = 0, p = 0, nnz = 0;
+  bool has_labels = false;
+  // CSR
+  fmwr::DBuf<uint32_t> rowptr;   // [n+1]
+  fmwr::DBuf<uint32_t> col;      // [nnz]
+  fmwr::DBuf<float> val;         // [nnz]
+  fmwr::DBuf<float> y;           // [n]
+  // CSC twin (rows ascending inside each column)
+  bool has_csc = false;
+  fmwr::DBuf<uint32_t> colptr;   // [p+1]
+  fmwr::DBuf<uint32_t> crow;     // [nnz]
+  fmwr::DBuf<float> cval;        // [nnz]
+  // coordinate-pass phases: consecutive feature ranges whose members never share a row
+  bool has_phases = false;
+  std::vector<uint32_t> phase_begin;   // [n_phases+1]
+  // per-batch CSC (minibatch mode): entries sorted by (batch, col, row)
+  int64_t mb_batch = 0;          // rows per batch the structure was built for (0: none)
+  int64_t mb_row0 = 0;           // first row covered
+  fmwr::DBuf<uint32_t> mb_seg_ptr;   // [n_seg+1] entry offsets
+  fmwr::DBuf<uint32_t> mb_seg_col;   // [n_seg]
+  fmwr::DBuf<uint32_t> mb_ent_row;   // [nnz'] global row index
+  fmwr::DBuf<float> mb_ent_val;      // [nnz']
+  std::vector<int64_t> mb_batch_seg;  // [n_batches+1] segment offsets per batch (host)
+  // last forward result
+  int pred_prec = FMWR_F32;
+  fmwr::DBuf<float> pred32;      // [n]
+  fmwr::DBuf<double> pred64;     // [n]
+  double min_y = 0, max_y = 0;
+};
+
+struct fmwr_model {
+  fmwr_ctx* ctx = nullptr;
+  fmwr_model_cfg cfg;
+  int64_t p = 0;
+  int prec = FMWR_F32;
+  int k = 0;    // logical factors
+  int kp = 0;   // padded row stride (elements): multiple of the 16-byte vector width, power-of-two lanes
+  // parameters: w0 is element 0 of `scal`; see layout notes in DESIGN.md
+  fmwr::DBuf<char> scal;     // small scalar block: [0]=w0, optimizer scalars follow (f64 each)
+  fmwr::DBuf<char> w;        // [p] real
+  fmwr::DBuf<char> v;        // [p][kp] real
+  // optimizer state, allocated by the trainer on demand (n_state arrays shaped like w / v)
+  int n_state = 0;
+  fmwr::DBuf<char> sw[5];    // per-solver state for w
+  fmwr::DBuf<char> sv[5];    // per-solver state for V
+  size_t esz() const { return prec == FMWR_F64 ? 8 : 4; }
+};
+
+namespace fmwr {
+
+// ---- device helpers ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <class T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 16-byte vector views of the parameter rows
+template <class T> struct Vec;
+template <> struct Vec<float> { typedef float4 type; enum { N = 4 }; };
+template <> struct Vec<double> { typedef double2 type; enum { N = 2 }; };
+
+__device__ __forceinline__ void vec_to_arr(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+__device__ __forceinline__ void vec_to_arr(const double2& v, double* a) { a[0] = v.x; a[1] = v.y; }
+__device__ __forceinline__ float4 arr_to_vec(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ double2 arr_to_vec(const double* a) { return make_double2(a[0], a[1]); }
+
+// splitmix64: the counter hash behind the synthetic data and the native RNG
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+#endif
+
+// kernel-launch bookkeeping: every launch of OUR kernels goes through this so gpu_launches is a count, not a guess
+#define FMWR_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+  do {                                                                                    \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+    (ctx)->launches++;                                                                    \
+    FMWR_CUDA(cudaGetLastError());                                                        \
+  } while (0)
+
+// padded factor stride: k rounded up so a row is LPR 16-byte vectors with LPR a power of two (<= 32 per chunk)
+int padded_k(int k, int prec);
+
+// module entry points (implemented across the .cu files)
+void build_link_tables(fmwr_ctx* ctx);
+void forward_launch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, int link, double lo, double hi);
+void transpose_build(fmwr_data* d);
+void phases_build(fmwr_data* d);
+void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch);
+void train_exact(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);
+void train_minibatch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);
+void train_als_mcmc(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);
+double evaluate_dev(fmwr_ctx* ctx, fmwr_data* d, int task, int metric);
+void model_alloc_state(fmwr_model* m, int n_state);
+void model_get_host(fmwr_model* m, double* w0, double* w, double* v);
+void model_set_host(fmwr_model* m, double w0, const double* w, const double* v);
+double model_get_w0(fmwr_model* m);
+void data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double* mean, double* sd);
+void data_normalize(fmwr_data* d, const double* mean, const double* sd);
+void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
+                int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
+void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);
+void link_table_eval(fmwr_ctx* ctx, int which, int64_t n, const double* x, double* out);
+
+}  // namespace fmwr

@@ -1,0 +1,81 @@
+// Per-coordinate optimizer steps shared by the exact (batch=1) and minibatch kernels.
+//
+// Every function takes the coordinate's gradient g (for the exact mode g is one sample's
+// gradient, for the minibatch mode the sum over the batch rows that touch the coordinate),
+// the current parameter value and its optimizer state, and returns the new value.
+//   SGD   reference src/solver/SGD_Learner.h:106-138 (+ apply_penalty :195-204)
+//   FTRL  reference src/solver/FTRL_Learner.h:80-113 (state) and :177-199 (closed-form refresh)
+//   TDAP  reference src/solver/TDAP_Learner.h:96-143 (state) and :203-231 (refresh)
+#pragma once
+#include "common.cuh"
+
+namespace fmwr {
+
+template <class T>
+struct SolverParams {
+  int solver;        // FMWR_SGD / FMWR_FTRL / FMWR_TDAP
+  int l1;            // SGD: cumulative-penalty L1 active
+  T lr;              // SGD
+  T reg_w, reg_v;    // SGD: L2 rate (or L1 rate when l1)
+  T reg_w0;          // SGD: L2.w0
+  T alpha_w, alpha_v, beta_w, beta_v;   // FTRL / TDAP
+  T l1_w, l1_v, l2_w, l2_v;             // FTRL / TDAP refresh
+  T egamma;          // TDAP exp(-gamma)
+};
+
+// cumulative-penalty clip (Tsuruoka et al.), reference src/solver/SGD_Learner.h:195-204
+template <class T>
+__device__ __forceinline__ void sgd_apply_penalty(T& theta, T u, T& q)
+{
+  const T old = theta;
+  if (theta > T(0)) theta = fmax(T(0), old - (u + q));
+  else if (theta < T(0)) theta = fmin(T(0), old + (u - q));
+  q += theta - old;
+}
+
+// SGD step for one coordinate.  g excludes the learning rate.  q is touched only when l1.
+template <class T>
+__device__ __forceinline__ T sgd_step(T theta, T g, T lr, T reg, int l1, T u, T& q)
+{
+  theta -= lr * g;
+  if (l1) sgd_apply_penalty(theta, u, q);
+  else theta -= lr * reg * theta;
+  return theta;
+}
+
+// FTRL-Proximal: state (z, n) in/out, returns refreshed theta
+template <class T>
+__device__ __forceinline__ T ftrl_step(T theta, T g, T& z, T& n, T alpha, T beta, T l1, T l2)
+{
+  const T n_old = n;
+  n = n_old + g * g;
+  const T sq = sqrt(n);
+  const T sigma = (sq - sqrt(n_old)) / alpha;
+  z += g - sigma * theta;
+  if (fabs(z) <= l1) return T(0);
+  const T sign = z < T(0) ? T(-1) : T(1);
+  return -(z - sign * l1) / ((beta + sq) / alpha + l2);
+}
+
+// TDAP state update: (u, nu, delta, h) in/out; returns z = nu - h
+template <class T>
+__device__ __forceinline__ T tdap_state(T theta, T g, T& u, T& nu, T& delta, T& h, T alpha, T egamma)
+{
+  const T u_old = u;
+  u = u_old + g * g;
+  nu += g;
+  const T sigma = (sqrt(u) - sqrt(u_old)) / alpha;
+  delta = egamma * (delta + sigma);
+  h = egamma * (h + sigma * theta);
+  return nu - h;
+}
+
+template <class T>
+__device__ __forceinline__ T tdap_refresh(T z, T delta, T l1, T l2)
+{
+  if (fabs(z) <= l1) return T(0);
+  const T sign = z < T(0) ? T(-1) : T(1);
+  return -(z - sign * l1) / (delta + l2);
+}
+
+}  // namespace fmwr

@@ -1,0 +1,677 @@
+// Device-resident sparse data: CSR ingest, CSR->CSC twin, coordinate phases, per-batch CSC,
+// z-score normalisation and the synthetic generators.
+//
+// Replaces SMatrix<float>::assign / transpose / scales / normalize (reference
+// src/util/Smatrix.h:44-61, :155-185, :98-153) and Data::add_data/add_target (src/core/Data.h:48-86).
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cmath>
+
+namespace fmwr {
+
+// ------------------------------------------------------------------------------------------ scan
+// exclusive prefix sum of u32 (reduce-then-scan, 3 phases, recursive on the block sums)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void scan_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums)
+{
+  __shared__ uint32_t red[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  uint32_t s = 0;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS) {
+    const int64_t j = base + i;
+    if (j < n) s += in[j];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) t += red[i];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// out[j] = offset[tile] + exclusive scan within tile; out may alias in
+__global__ void scan_tile_apply(const uint32_t* __restrict__ in, int64_t n, const uint32_t* __restrict__ tile_off,
+                                uint32_t* __restrict__ out)
+{
+  __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t x[SCAN_ITEMS];
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t j = base + i;
+    x[i] = j < n ? in[j] : 0u;
+    t += x[i];
+  }
+  // inclusive scan of per-thread totals across the block
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int i = 0; i < wid; ++i) woff += warp_tot[i];
+  uint32_t run = tile_off[blockIdx.x] + woff + inc - t;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t j = base + i;
+    if (j < n) out[j] = run;
+    run += x[i];
+  }
+}
+
+// exclusive scan of in[0..n) into out[0..n); returns nothing (total = out[n-1] + in[n-1])
+static void exclusive_scan_u32(fmwr_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n)
+{
+  if (n <= 0) return;
+  const int64_t tiles = ceil_div64(n, SCAN_TILE);
+  DBuf<uint32_t> sums;
+  sums.alloc(tiles);
+  FMWR_LAUNCH(ctx, scan_tile_sums, (int)tiles, SCAN_THREADS, 0, in, n, sums.p);
+  if (tiles > 1) exclusive_scan_u32(ctx, sums.p, sums.p, tiles);
+  else FMWR_CUDA(cudaMemsetAsync(sums.p, 0, sizeof(uint32_t), ctx->stream));
+  FMWR_LAUNCH(ctx, scan_tile_apply, (int)tiles, SCAN_THREADS, 0, in, n, sums.p, out);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));   // sums is freed on return
+}
+
+// ------------------------------------------------------------------------------------------ ingest
+__global__ void f64_to_f32(const double* __restrict__ in, float* __restrict__ out, int64_t n)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// flags[0] |= 1 if any col >= p; flags[0] |= 2 if a row is not strictly ascending
+__global__ void validate_csr(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t n,
+                             uint32_t p, uint32_t nnz, int* __restrict__ flags)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t b = rowptr[r], e = rowptr[r + 1];
+  if (e < b || e > nnz) { atomicOr(flags, 4); return; }
+  int bad = 0;
+  uint32_t prev = 0;
+  for (uint32_t j = b; j < e; ++j) {
+    const uint32_t c = col[j];
+    if (c >= p) bad |= 1;
+    if (j > b && c <= prev) bad |= 2;
+    prev = c;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+static void finish_create(fmwr_data* d)
+{
+  fmwr_ctx* ctx = d->ctx;
+  if (d->n == 0) return;
+  DBuf<int> flags;
+  flags.alloc(1);
+  flags.zero(ctx->stream);
+  FMWR_LAUNCH(ctx, validate_csr, ceil_div(d->n, 256), 256, 0, d->rowptr.p, d->col.p, d->n, (uint32_t)d->p,
+              (uint32_t)d->nnz, flags.p);
+  int h = 0;
+  FMWR_CUDA(cudaMemcpyAsync(&h, flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  FMWR_REQUIRE(!(h & 4), FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
+  FMWR_REQUIRE(!(h & 1), FMWR_ERR_SHAPE, "col_idx out of range (>= number of features)");
+  FMWR_REQUIRE(!(h & 2), FMWR_ERR_SHAPE, "col_idx must be strictly ascending within each row");
+}
+
+static void set_labels(fmwr_data* d, const float* y)
+{
+  d->has_labels = true;
+  d->y.alloc(d->n);
+  FMWR_CUDA(cudaMemcpyAsync(d->y.p, y, sizeof(float) * d->n, cudaMemcpyHostToDevice, d->ctx->stream));
+  // Data::add_target min/max (reference src/core/Data.h:80-84)
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = 0; i < d->n; ++i) { mn = std::min(mn, y[i]); mx = std::max(mx, y[i]); }
+  d->min_y = mn; d->max_y = mx;
+  FMWR_CUDA(cudaStreamSynchronize(d->ctx->stream));
+}
+
+fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, const int32_t* row_size,
+                           const int32_t* col_idx, const double* value, const double* labels)
+{
+  FMWR_REQUIRE(n >= 0 && p >= 0 && nnz >= 0, FMWR_ERR_ARG, "negative dimension");
+  FMWR_REQUIRE(nnz < (int64_t)0xffffffffll && n < (int64_t)0xffffffffll && p < (int64_t)0xffffffffll, FMWR_ERR_UNSUPPORTED,
+               "dimensions must fit 32-bit indices per device shard");
+  fmwr_data* d = new fmwr_data();
+  try {
+    d->ctx = ctx; d->n = n; d->p = p; d->nnz = nnz;
+    d->rowptr.alloc(n + 1);
+    d->col.alloc(nnz);
+    d->val.alloc(nnz);
+    // rowptr: prefix sum of row_size on the device (reference src/util/Smatrix.h:55-60)
+    FMWR_CUDA(cudaMemsetAsync(d->rowptr.p, 0, sizeof(uint32_t) * (n + 1), ctx->stream));
+    if (n > 0) {
+      DBuf<uint32_t> rs;
+      rs.alloc(n + 1);
+      FMWR_CUDA(cudaMemsetAsync(rs.p, 0, sizeof(uint32_t) * (n + 1), ctx->stream));
+      FMWR_CUDA(cudaMemcpyAsync(rs.p, row_size, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+      exclusive_scan_u32(ctx, rs.p, d->rowptr.p, n + 1);
+      uint32_t total = 0;
+      FMWR_CUDA(cudaMemcpy(&total, d->rowptr.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      FMWR_REQUIRE((int64_t)total == nnz, FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
+    }
+    if (nnz > 0) {
+      FMWR_CUDA(cudaMemcpyAsync(d->col.p, col_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+      // f64 -> f32 narrowing on the device, chunked so the f64 staging buffer stays small
+      const int64_t chunk = 32ll << 20;
+      DBuf<double> stage;
+      stage.alloc(std::min(chunk, nnz));
+      for (int64_t off = 0; off < nnz; off += chunk) {
+        const int64_t m = std::min(chunk, nnz - off);
+        FMWR_CUDA(cudaMemcpyAsync(stage.p, value + off, sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
+        FMWR_LAUNCH(ctx, f64_to_f32, ceil_div(m, 256), 256, 0, stage.p, d->val.p + off, m);
+      }
+      FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (labels) {
+      std::vector<float> y(n);
+      for (int64_t i = 0; i < n; ++i) y[i] = (float)labels[i];
+      set_labels(d, y.data());
+    }
+    finish_create(d);
+  } catch (...) { delete d; throw; }
+  return d;
+}
+
+fmwr_data* data_create_csr32(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, const uint32_t* rowptr,
+                             const uint32_t* col_idx, const float* value, const float* labels)
+{
+  FMWR_REQUIRE(n >= 0 && p >= 0 && nnz >= 0, FMWR_ERR_ARG, "negative dimension");
+  FMWR_REQUIRE(nnz < (int64_t)0xffffffffll && n < (int64_t)0xffffffffll && p < (int64_t)0xffffffffll, FMWR_ERR_UNSUPPORTED,
+               "dimensions must fit 32-bit indices per device shard");
+  fmwr_data* d = new fmwr_data();
+  try {
+    d->ctx = ctx; d->n = n; d->p = p; d->nnz = nnz;
+    d->rowptr.alloc(n + 1); d->col.alloc(nnz); d->val.alloc(nnz);
+    FMWR_CUDA(cudaMemcpyAsync(d->rowptr.p, rowptr, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz > 0) {
+      FMWR_CUDA(cudaMemcpyAsync(d->col.p, col_idx, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+      FMWR_CUDA(cudaMemcpyAsync(d->val.p, value, sizeof(float) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    FMWR_REQUIRE(rowptr[n] == (uint32_t)nnz && rowptr[0] == 0, FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
+    if (labels) set_labels(d, labels);
+    finish_create(d);
+  } catch (...) { delete d; throw; }
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ CSR -> CSC
+__global__ void expand_rows(const uint32_t* __restrict__ rowptr, int64_t n, uint32_t* __restrict__ erow)
+{
+  // one warp per row writes the row id over the row's entry range
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const uint32_t b = rowptr[row], e = rowptr[row + 1];
+  for (uint32_t j = b + (threadIdx.x & 31); j < e; j += 32) erow[j] = (uint32_t)row;
+}
+
+__global__ void iota_u32(uint32_t* __restrict__ a, int64_t n)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (uint32_t)i;
+}
+
+__global__ void gather_csc(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ erow, const float* __restrict__ val,
+                           int64_t nnz, uint32_t* __restrict__ crow, float* __restrict__ cval)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const uint32_t e = perm[i];
+  crow[i] = erow[e];
+  cval[i] = val[e];
+}
+
+// ptr[c] = first index i with keys[i] >= c  (keys sorted ascending), c in [0, p]
+__global__ void segment_ptr_from_sorted(const uint32_t* __restrict__ keys, int64_t nnz, int64_t p, uint32_t* __restrict__ ptr)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nnz) return;
+  const int64_t lo = (i == 0) ? 0 : (int64_t)keys[i - 1] + 1;
+  const int64_t hi = (i == nnz) ? p : (int64_t)keys[i];
+  for (int64_t c = lo; c <= hi; ++c) ptr[c] = (uint32_t)i;
+}
+
+static int bits_for(uint64_t maxval)
+{
+  int b = 1;
+  while (b < 64 && (maxval >> b) != 0) ++b;
+  return b;
+}
+
+// stable sort of entry ids by column: radix sort keeps equal keys in input (== row-ascending) order
+void transpose_build(fmwr_data* d)
+{
+  if (d->has_csc) return;
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t nnz = d->nnz, n = d->n, p = d->p;
+  d->colptr.alloc(p + 1);
+  d->crow.alloc(nnz);
+  d->cval.alloc(nnz);
+  if (nnz == 0) {
+    FMWR_CUDA(cudaMemsetAsync(d->colptr.p, 0, sizeof(uint32_t) * (p + 1), ctx->stream));
+    d->has_csc = true;
+    return;
+  }
+  DBuf<uint32_t> erow, keys_out, idx_in, idx_out;
+  erow.alloc(nnz); keys_out.alloc(nnz); idx_in.alloc(nnz); idx_out.alloc(nnz);
+  FMWR_LAUNCH(ctx, expand_rows, ceil_div(n * 32, 256), 256, 0, d->rowptr.p, n, erow.p);
+  FMWR_LAUNCH(ctx, iota_u32, ceil_div(nnz, 256), 256, 0, idx_in.p, nnz);
+  size_t tmp_bytes = 0;
+  const int end_bit = bits_for((uint64_t)(p > 0 ? p - 1 : 0));
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d->col.p, keys_out.p, idx_in.p, idx_out.p, (int)nnz, 0,
+                                            end_bit, ctx->stream));
+  DBuf<char> tmp;
+  tmp.alloc(tmp_bytes);
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d->col.p, keys_out.p, idx_in.p, idx_out.p, (int)nnz, 0,
+                                            end_bit, ctx->stream));
+  ctx->launches += 1;
+  FMWR_LAUNCH(ctx, gather_csc, ceil_div(nnz, 256), 256, 0, idx_out.p, erow.p, d->val.p, nnz, d->crow.p, d->cval.p);
+  FMWR_LAUNCH(ctx, segment_ptr_from_sorted, ceil_div(nnz + 1, 256), 256, 0, keys_out.p, nnz, p, d->colptr.p);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  d->has_csc = true;
+}
+
+// ------------------------------------------------------------------------------------------ phases
+// prev[c] = max over rows containing c of the column that precedes c in that row (+1; 0 = none).
+__global__ void phase_prev(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t n,
+                           uint32_t* __restrict__ prev)
+{
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const uint32_t b = rowptr[row], e = rowptr[row + 1];
+  for (uint32_t j = b + 1 + (threadIdx.x & 31); j < e; j += 32) atomicMax(prev + col[j], col[j - 1] + 1u);
+}
+
+// Greedy split of the feature axis into consecutive ranges whose members never co-occur in a row.
+// Updating all features of such a range concurrently equals the reference's sequential Gauss-Seidel
+// sweep (src/solver/MCMC_ALS_Learner.h:211-255, :303-351 at nthreads=1) because their column
+// supports -- the only entries of e and q they touch -- are disjoint.
+void phases_build(fmwr_data* d)
+{
+  if (d->has_phases) return;
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t p = d->p, n = d->n;
+  DBuf<uint32_t> prev;
+  prev.alloc(p);
+  prev.zero(ctx->stream);
+  if (n > 0) FMWR_LAUNCH(ctx, phase_prev, ceil_div(n * 32, 256), 256, 0, d->rowptr.p, d->col.p, n, prev.p);
+  std::vector<uint32_t> h(p);
+  FMWR_CUDA(cudaMemcpyAsync(h.data(), prev.p, sizeof(uint32_t) * p, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  d->phase_begin.clear();
+  d->phase_begin.push_back(0);
+  uint32_t a = 0;
+  for (int64_t c = 0; c < p; ++c) {
+    if (h[c] > a) {            // some row holds c together with a feature >= a of the current range
+      a = (uint32_t)c;
+      d->phase_begin.push_back(a);
+    }
+  }
+  d->phase_begin.push_back((uint32_t)p);
+  d->has_phases = true;
+}
+
+// ------------------------------------------------------------------------------------------ per-batch CSC
+__global__ void mb_keys(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t row0, int64_t n,
+                        uint32_t batch, int colbits, uint64_t* __restrict__ keys, uint32_t* __restrict__ erow)
+{
+  const int64_t row = row0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (row >= n) return;
+  const uint32_t b = rowptr[row], e = rowptr[row + 1], e0 = rowptr[row0];
+  const uint64_t bid = (uint64_t)((row - row0) / batch);
+  for (uint32_t j = b + (threadIdx.x & 31); j < e; j += 32) {
+    keys[j - e0] = (bid << colbits) | (uint64_t)col[j];
+    erow[j - e0] = (uint32_t)row;
+  }
+}
+
+// head[i] = 1 where a new (batch, col) segment starts
+__global__ void mb_heads(const uint64_t* __restrict__ keys, int64_t m, uint32_t* __restrict__ head)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void mb_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ segid,
+                        const uint32_t* __restrict__ perm, const uint32_t* __restrict__ erow, const float* __restrict__ val,
+                        uint32_t e0, int64_t m, int colbits, uint32_t* __restrict__ seg_ptr, uint32_t* __restrict__ seg_col,
+                        uint32_t* __restrict__ ent_row, float* __restrict__ ent_val, uint32_t n_seg)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t e = perm[i];
+  ent_row[i] = erow[e];
+  ent_val[i] = val[e0 + e];
+  if (head[i]) {
+    const uint32_t s = segid[i];
+    seg_ptr[s] = (uint32_t)i;
+    seg_col[s] = (uint32_t)(keys[i] & ((1ull << colbits) - 1ull));
+  }
+  if (i == m - 1) seg_ptr[n_seg] = (uint32_t)m;
+}
+
+// first segment of each batch: batch_seg[b] = #segments with batch id < b
+__global__ void mb_batch_bounds(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head,
+                                const uint32_t* __restrict__ segid, int64_t m, int colbits, int64_t n_batches,
+                                uint32_t n_seg, uint32_t* __restrict__ batch_seg)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  if (!head[i]) return;
+  const uint64_t bid = keys[i] >> colbits;
+  const uint64_t pb = (i == 0) ? (uint64_t)-1 : (keys[i - 1] >> colbits);
+  if (i == 0 || pb != bid) {
+    // batches (pb, bid] start at this segment (empty batches in between share the offset)
+    const uint64_t from = (i == 0) ? 0 : pb + 1;
+    for (uint64_t b = from; b <= bid; ++b) batch_seg[b] = segid[i];
+  }
+  (void)n_batches; (void)n_seg;
+}
+
+// Entries of rows [row0, n) regrouped by (batch, feature, row): the "sorted-key segmented
+// reduction" layout of the minibatch update kernels (one segment = one touched coordinate).
+void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
+{
+  if (d->mb_batch == batch && d->mb_row0 == row0) return;
+  fmwr_ctx* ctx = d->ctx;
+  FMWR_REQUIRE(batch > 0, FMWR_ERR_ARG, "batch_size must be positive");
+  const int64_t rows = d->n - row0;
+  const int64_t n_batches = rows > 0 ? ceil_div64(rows, batch) : 0;
+  d->mb_batch_seg.assign(n_batches + 1, 0);
+  if (rows <= 0) { d->mb_batch = batch; d->mb_row0 = row0; return; }
+  uint32_t e0 = 0, e1 = 0;
+  FMWR_CUDA(cudaMemcpy(&e0, d->rowptr.p + row0, 4, cudaMemcpyDeviceToHost));
+  FMWR_CUDA(cudaMemcpy(&e1, d->rowptr.p + d->n, 4, cudaMemcpyDeviceToHost));
+  const int64_t m = (int64_t)e1 - e0;
+  const int colbits = bits_for((uint64_t)(d->p > 0 ? d->p - 1 : 0));
+  const int batchbits = bits_for((uint64_t)(n_batches > 0 ? n_batches - 1 : 0));
+  d->mb_ent_row.alloc(m); d->mb_ent_val.alloc(m);
+  if (m == 0) {
+    d->mb_seg_ptr.alloc(1); d->mb_seg_col.alloc(1);
+    FMWR_CUDA(cudaMemsetAsync(d->mb_seg_ptr.p, 0, 4, ctx->stream));
+    d->mb_batch = batch; d->mb_row0 = row0;
+    return;
+  }
+  DBuf<uint64_t> keys_in, keys_out;
+  DBuf<uint32_t> erow, idx_in, idx_out, head, segid;
+  keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); idx_in.alloc(m); idx_out.alloc(m); head.alloc(m); segid.alloc(m);
+  FMWR_LAUNCH(ctx, mb_keys, ceil_div(rows * 32, 256), 256, 0, d->rowptr.p, d->col.p, row0, d->n, (uint32_t)batch, colbits,
+              keys_in.p, erow.p);
+  FMWR_LAUNCH(ctx, iota_u32, ceil_div(m, 256), 256, 0, idx_in.p, m);
+  size_t tmp_bytes = 0;
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, idx_out.p, (int)m, 0,
+                                            colbits + batchbits, ctx->stream));
+  DBuf<char> tmp;
+  tmp.alloc(tmp_bytes);
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, idx_out.p, (int)m, 0,
+                                            colbits + batchbits, ctx->stream));
+  ctx->launches += 1;
+  FMWR_LAUNCH(ctx, mb_heads, ceil_div(m, 256), 256, 0, keys_out.p, m, head.p);
+  exclusive_scan_u32(ctx, head.p, segid.p, m);
+  uint32_t last_id = 0, last_head = 0;
+  FMWR_CUDA(cudaMemcpy(&last_id, segid.p + (m - 1), 4, cudaMemcpyDeviceToHost));
+  FMWR_CUDA(cudaMemcpy(&last_head, head.p + (m - 1), 4, cudaMemcpyDeviceToHost));
+  const uint32_t n_seg = last_id + last_head;
+  d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_col.alloc(n_seg);
+  FMWR_LAUNCH(ctx, mb_emit, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, idx_out.p, erow.p, d->val.p, e0, m,
+              colbits, d->mb_seg_ptr.p, d->mb_seg_col.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
+  DBuf<uint32_t> bseg;
+  bseg.alloc(n_batches + 1);
+  // default every batch offset to n_seg (covers trailing empty batches), then fill real starts
+  std::vector<uint32_t> fill(n_batches + 1, n_seg);
+  FMWR_CUDA(cudaMemcpyAsync(bseg.p, fill.data(), 4 * (n_batches + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_LAUNCH(ctx, mb_batch_bounds, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, m, colbits, n_batches, n_seg,
+              bseg.p);
+  std::vector<uint32_t> hb(n_batches + 1);
+  FMWR_CUDA(cudaMemcpyAsync(hb.data(), bseg.p, 4 * (n_batches + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  // empty batches in the middle were filled by the next non-empty one; trailing ones keep n_seg
+  for (int64_t b = 0; b <= n_batches; ++b) d->mb_batch_seg[b] = hb[b];
+  d->mb_batch_seg[n_batches] = n_seg;
+  for (int64_t b = n_batches - 1; b >= 0; --b) if (d->mb_batch_seg[b] > d->mb_batch_seg[b + 1]) d->mb_batch_seg[b] = d->mb_batch_seg[b + 1];
+  d->mb_batch = batch; d->mb_row0 = row0;
+}
+
+// ------------------------------------------------------------------------------------------ scales / normalize
+__global__ void col_moments(const uint32_t* __restrict__ col, const float* __restrict__ val, int64_t nnz,
+                            double* __restrict__ sum, double* __restrict__ sumsq)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const double x = val[i];
+  atomicAdd(sum + col[i], x);
+  atomicAdd(sumsq + col[i], x * x);
+}
+
+__global__ void col_rescale(const uint32_t* __restrict__ col, float* __restrict__ val, int64_t nnz,
+                            const double* __restrict__ mean, const double* __restrict__ sd, int mode)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const uint32_t c = col[i];
+  if (mode == 0) {
+    // SMatrix::scales in-place step: float -= double; float /= (double + 1e-30)  (src/util/Smatrix.h:121-125)
+    float x = val[i];
+    x = (float)((double)x - mean[c]);
+    x = (float)((double)x / (sd[c] + 1e-30));
+    val[i] = x;
+  } else {
+    // SMatrix::normalize (src/util/Smatrix.h:144-150): skipped when std == 0
+    if (sd[c] != 0) val[i] = (float)(((double)val[i] - mean[c]) / sd[c]);
+  }
+}
+
+void data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double* mean, double* sd)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t p = d->p, n = d->n;
+  DBuf<double> s, q;
+  s.alloc(p); q.alloc(p);
+  s.zero(ctx->stream); q.zero(ctx->stream);
+  if (d->nnz > 0) FMWR_LAUNCH(ctx, col_moments, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->val.p, d->nnz, s.p, q.p);
+  std::vector<double> hs(p), hq(p);
+  FMWR_CUDA(cudaMemcpyAsync(hs.data(), s.p, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaMemcpyAsync(hq.data(), q.p, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  // per-column statistics exactly as src/util/Smatrix.h:111-119 (unlisted columns: mean 0, std 1)
+  const double mult_dim = (double)n * ((double)n - 1);
+  int64_t i = 0;
+  for (int64_t c = 0; c < p; ++c) {
+    if (i < n_norm && c == (int64_t)norm_cols[i]) {
+      sd[c] = std::sqrt(hq[c] / (double)(uint32_t)(n - 1) - hs[c] * hs[c] / mult_dim);
+      mean[c] = hs[c] / (double)n;
+      ++i;
+    } else { sd[c] = 1.0; mean[c] = 0.0; }
+  }
+  FMWR_CUDA(cudaMemcpyAsync(s.p, mean, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_CUDA(cudaMemcpyAsync(q.p, sd, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+  if (d->nnz > 0) FMWR_LAUNCH(ctx, col_rescale, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->val.p, d->nnz, s.p, q.p, 0);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  d->has_csc = false; d->mb_batch = 0;   // derived layouts hold stale values
+}
+
+void data_normalize(fmwr_data* d, const double* mean, const double* sd)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t p = d->p;
+  DBuf<double> s, q;
+  s.alloc(p); q.alloc(p);
+  FMWR_CUDA(cudaMemcpyAsync(s.p, mean, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_CUDA(cudaMemcpyAsync(q.p, sd, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+  if (d->nnz > 0) FMWR_LAUNCH(ctx, col_rescale, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->val.p, d->nnz, s.p, q.p, 1);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  d->has_csc = false; d->mb_batch = 0;
+}
+
+// ------------------------------------------------------------------------------------------ synthetic data
+// id(row, field) = offset_f + skewed(h(seed, row*F + field)) mod size_f          
+// h = splitmix64(seed ^ (row*F + field)); integer-only so the numpy twin (fmwr_b200/synth.py) is bit-identical.
+__device__ __host__ __forceinline__ uint64_t synth_id(uint64_t h, uint64_t size, int skew)
+{
+  if (!skew) return h % size;
+  // power-law skew: u^3 in 32.32 fixed point, then scaled to [0, size)
+  const uint64_t u = h >> 32;                       // 32-bit uniform
+  const uint64_t u2 = (u * u) >> 32;
+  const uint64_t u3 = (u2 * u) >> 32;
+  return (u3 * size) >> 32;
+}
+
+__device__ __host__ __forceinline__ float synth_value(uint64_t h, int value_mode)
+{
+  if (!value_mode) return 1.0f;
+  // second hash word -> 24-bit mantissa, exactly representable: x in [0.5, 1.5)
+  const uint64_t h2 = splitmix64(h ^ 0xD1B54A32D192ED03ull);
+  return 0.5f + (float)(h2 >> 40) * (1.0f / 16777216.0f);
+}
+
+struct SynthFields {
+  uint64_t offset[64];
+  uint64_t size[64];
+  int skew[64];
+};
+
+__global__ void synth_fill(int64_t n, int F, SynthFields f, int value_mode, uint64_t seed, uint32_t* __restrict__ rowptr,
+                           uint32_t* __restrict__ col, float* __restrict__ val)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // entry index
+  if (i <= n) { if (i * F <= 0xffffffffll) rowptr[i] = (uint32_t)(i * F); }
+  if (i >= n * F) return;
+  const int64_t row = i / F;
+  const int fld = (int)(i - row * F);
+  const uint64_t h = splitmix64(seed ^ (uint64_t)i);
+  col[i] = (uint32_t)(f.offset[fld] + synth_id(h, f.size[fld], f.skew[fld]));
+  val[i] = synth_value(h, value_mode);
+}
+
+// standard normal from two hash words (Box-Muller), double precision
+__device__ __forceinline__ double hash_normal(uint64_t key)
+{
+  const uint64_t a = splitmix64(key), b = splitmix64(key ^ 0xA0761D6478BD642Full);
+  const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+template <class T>
+__global__ void fill_normal(T* __restrict__ a, int64_t n, int k, int kp, double mean, double sd, uint64_t seed)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into the padded [p][kp] array
+  if (i >= n) return;
+  const int f = (int)(i % kp);
+  const int64_t j = i / kp;
+  a[i] = (f < k) ? T(mean + sd * hash_normal(seed ^ (uint64_t)(j * k + f))) : T(0);
+}
+
+template <class T>
+__global__ void synth_labels(const T* __restrict__ score, int64_t n, int label_mode, double noise, uint64_t seed,
+                             float* __restrict__ y)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = (double)score[i];
+  if (label_mode == 1) {
+    const double u = ((double)(splitmix64(seed ^ (uint64_t)i) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    y[i] = (u < 1.0 / (1.0 + exp(-s))) ? 1.0f : -1.0f;
+  } else if (label_mode == 2) {
+    y[i] = (float)(s + noise * hash_normal(seed ^ (uint64_t)i));
+  } else {
+    double t = 3.5 + s + noise * hash_normal(seed ^ (uint64_t)i);
+    t = t < 0.5 ? 0.5 : (t > 5.0 ? 5.0 : t);
+    y[i] = (float)t;
+  }
+}
+
+__global__ void minmax_f32(const float* __restrict__ y, int64_t n, float* __restrict__ out /*[2]: -min, max as ordered ints*/)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float mn = INFINITY, mx = -INFINITY;
+  if (i < n) { mn = y[i]; mx = y[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // float atomic min/max through the sign-aware int trick
+    int* o = (int*)out;
+    if (mn >= 0) atomicMin(o, __float_as_int(mn)); else atomicMax((unsigned*)o, __float_as_uint(mn));
+    if (mx >= 0) atomicMax(o + 1, __float_as_int(mx)); else atomicMin((unsigned*)(o + 1), __float_as_uint(mx));
+  }
+}
+
+void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed)
+{
+  fmwr_ctx* ctx = m->ctx;
+  const int64_t tot = m->p * m->kp;
+  FMWR_CUDA(cudaMemsetAsync(m->scal.p, 0, m->scal.bytes(), ctx->stream));
+  FMWR_CUDA(cudaMemsetAsync(m->w.p, 0, m->w.bytes(), ctx->stream));
+  if (m->prec == FMWR_F64) FMWR_LAUNCH(ctx, fill_normal<double>, ceil_div(tot, 256), 256, 0, (double*)m->v.p, tot, m->k, m->kp, mean, sd, seed);
+  else FMWR_LAUNCH(ctx, fill_normal<float>, ceil_div(tot, 256), 256, 0, (float*)m->v.p, tot, m->k, m->kp, mean, sd, seed);
+}
+
+void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
+                int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out)
+{
+  FMWR_REQUIRE(n_fields > 0 && n_fields <= 64, FMWR_ERR_ARG, "n_fields must be in [1, 64]");
+  SynthFields sf;
+  uint64_t off = 0;
+  for (int f = 0; f < n_fields; ++f) {
+    FMWR_REQUIRE(field_size[f] > 0, FMWR_ERR_ARG, "field_size must be positive");
+    sf.offset[f] = off; sf.size[f] = (uint64_t)field_size[f]; sf.skew[f] = skew ? skew[f] : 0;
+    off += (uint64_t)field_size[f];
+  }
+  const int64_t p = (int64_t)off, nnz = n * n_fields;
+  FMWR_REQUIRE(nnz < (int64_t)0xffffffffll && p < (int64_t)0xffffffffll, FMWR_ERR_UNSUPPORTED,
+               "dimensions must fit 32-bit indices per device shard");
+  fmwr_data* d = new fmwr_data();
+  try {
+    d->ctx = ctx; d->n = n; d->p = p; d->nnz = nnz;
+    d->rowptr.alloc(n + 1); d->col.alloc(nnz); d->val.alloc(nnz);
+    const int64_t threads = std::max(nnz, n + 1);
+    FMWR_LAUNCH(ctx, synth_fill, ceil_div(threads, 256), 256, 0, n, n_fields, sf, value_mode, seed, d->rowptr.p, d->col.p, d->val.p);
+    if (label_mode != 0) {
+      // planted FM (k* = 8, w*, V* ~ N(0, 0.1^2)) scored with the engine's own forward kernel
+      fmwr_model_cfg mc; memset(&mc, 0, sizeof mc);
+      mc.task = FMWR_REGRESSION; mc.keep_w0 = 1; mc.keep_w1 = 1; mc.k = 8;
+      fmwr_model* pm = nullptr;
+      FMWR_REQUIRE(fmwr_model_create(ctx, &mc, p, FMWR_F32, &pm) == 0, FMWR_ERR_CUDA, fmwr_last_error());
+      try {
+        model_init_random(pm, 0.0, 0.1, seed + 1);
+        const int64_t pw = p;
+        FMWR_LAUNCH(ctx, fill_normal<float>, ceil_div(pw, 256), 256, 0, (float*)pm->w.p, pw, 1, 1, 0.0, 0.1, seed + 2);
+        forward_launch(ctx, pm, d, FMWR_LINK_NONE, 0, 0);
+        d->y.alloc(n); d->has_labels = true;
+        FMWR_LAUNCH(ctx, synth_labels<float>, ceil_div(n, 256), 256, 0, d->pred32.p, n, label_mode, noise, seed + 3, d->y.p);
+        DBuf<float> mm; mm.alloc(2);
+        const float init[2] = {INFINITY, -INFINITY};
+        FMWR_CUDA(cudaMemcpyAsync(mm.p, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMWR_LAUNCH(ctx, minmax_f32, ceil_div(n, 256), 256, 0, d->y.p, n, mm.p);
+        float h[2];
+        FMWR_CUDA(cudaMemcpyAsync(h, mm.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+        d->min_y = h[0]; d->max_y = h[1];
+      } catch (...) { fmwr_model_destroy(pm); throw; }
+      fmwr_model_destroy(pm);
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) { delete d; throw; }
+  *out = d;
+}
+
+}  // namespace fmwr

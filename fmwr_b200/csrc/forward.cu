@@ -1,0 +1,55 @@
+// predict.FM / error-cache forward pass: replaces Model::predict_batch + predict_prob + the
+// regression clamp (reference src/core/Model.h:106-180, src/FM.cpp:197-211).
+#include "forward.cuh"
+
+namespace fmwr {
+
+template <class T, int LPR, int CH>
+__global__ void __launch_bounds__(256)
+forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
+               const T* __restrict__ w, const T* __restrict__ v, const double* __restrict__ scal, int kp, int k0, int k1,
+               int64_t n, int link, double lo, double hi, const double* __restrict__ pnY, T* __restrict__ out)
+{
+  constexpr int U = (LPR >= 16) ? 8 : 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const T w0 = T(scal[0]);
+  for (int64_t row = warp0; row < n; row += nwarps) {
+    const uint32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    T S[CH][Vec<T>::N];
+    const T score = row_forward<T, LPR, CH, U>(col, val, b, e, w, v, kp, w0, k0, k1, S);
+    if (lane == 0) out[row] = T(apply_link(link, (double)score, lo, hi, pnY));
+  }
+}
+
+struct FwdLaunch {
+  fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; int link; double lo, hi;
+  template <class T, int LPR, int CH>
+  void run()
+  {
+    const int block = 256, wpb = block / 32;
+    int64_t want = ceil_div64(d->n, wpb);
+    int64_t cap = (int64_t)ctx->sm_count * 8 * 4;   // 4 waves of 8 resident CTAs per SM, grid-stride beyond that
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    T* out;
+    if (sizeof(T) == 8) { d->pred64.ensure(d->n); out = (T*)d->pred64.p; d->pred_prec = FMWR_F64; }
+    else { d->pred32.ensure(d->n); out = (T*)d->pred32.p; d->pred_prec = FMWR_F32; }
+    FMWR_LAUNCH(ctx, (forward_kernel<T, LPR, CH>), grid, block, 0,
+                d->rowptr.p, d->col.p, d->val.p, (const T*)m->w.p, (const T*)m->v.p, (const double*)m->scal.p,
+                m->kp, m->cfg.keep_w0, m->cfg.keep_w1, d->n, link, lo, hi, ctx->pn_table.p, out);
+  }
+};
+
+void forward_launch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, int link, double lo, double hi)
+{
+  // shape checks of Model::predict_batch (reference src/core/Model.h:112-113)
+  FMWR_REQUIRE(d->p == m->p, FMWR_ERR_SHAPE, "number of input's features is not correct...");
+  if (d->n == 0) return;
+  FwdLaunch f{ctx, m, d, link, lo, hi};
+  if (m->prec == FMWR_F64) dispatch_layout<double>(m->kp, f);
+  else dispatch_layout<float>(m->kp, f);
+}
+
+}  // namespace fmwr

@@ -11,6 +11,18 @@ namespace fmwr {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
+cudaEvent_t prof_begin(fmwr_ctx* ctx, const char* tag)
+{
+  cudaEvent_t e[2];
+  for (int i = 0; i < 2; ++i) {
+    if (!ctx->prof_pool.empty()) { e[i] = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else if (cudaEventCreate(&e[i]) != cudaSuccess) return nullptr;
+  }
+  cudaEventRecord(e[0], ctx->stream);
+  ctx->prof_recs.push_back({tag, e[0], e[1]});
+  return e[1];
+}
+
 int padded_k(int k, int prec)
 {
   const int vn = prec == FMWR_F64 ? 2 : 4;
@@ -259,6 +271,8 @@ int fmwr_ctx_destroy(fmwr_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]); }
+    for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -290,6 +304,53 @@ int fmwr_timer_stop_ms(fmwr_ctx* ctx, double* ms)
 int fmwr_ctx_launch_count(fmwr_ctx* ctx, int64_t* n)
 {
   return guarded([&] { FMWR_REQUIRE(ctx && n, FMWR_ERR_ARG, "null argument"); *n = ctx->launches; });
+}
+
+int fmwr_profile_enable(fmwr_ctx* ctx, int on)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx, FMWR_ERR_ARG, "null ctx");
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof_recs) { ctx->prof_pool.push_back(r.e0); ctx->prof_pool.push_back(r.e1); }
+    ctx->prof_recs.clear();
+    ctx->profile = on != 0;
+  });
+}
+
+int fmwr_profile_read(fmwr_ctx* ctx, char* buf, int64_t buf_len)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx && buf && buf_len > 0, FMWR_ERR_ARG, "null argument");
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    struct Agg { const char* tag; double ms; int64_t n; };
+    std::vector<Agg> agg;
+    for (auto& r : ctx->prof_recs) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+      size_t i = 0;
+      for (; i < agg.size(); ++i) if (agg[i].tag == r.tag || strcmp(agg[i].tag, r.tag) == 0) break;
+      if (i == agg.size()) agg.push_back({r.tag, 0.0, 0});
+      agg[i].ms += ms; agg[i].n += 1;
+    }
+    std::string out;
+    for (auto& a : agg) {
+      char line[512];
+      snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", a.tag, (long long)a.n, a.ms);
+      out += line;
+    }
+    FMWR_REQUIRE((int64_t)out.size() + 1 <= buf_len, FMWR_ERR_ARG, "profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+  });
+}
+
+int fmwr_host_pin(void* ptr, int64_t bytes)
+{
+  return guarded([&] { FMWR_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault)); });
+}
+
+int fmwr_host_unpin(void* ptr)
+{
+  return guarded([&] { FMWR_CUDA(cudaHostUnregister(ptr)); });
 }
 
 int fmwr_flush_l2(fmwr_ctx* ctx)

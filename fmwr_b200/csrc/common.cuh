@@ -113,6 +113,11 @@ struct fmwr_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
   int64_t launches = 0;
+  // per-kernel CUDA-event profile (bench.py: roofline.achieved is measured live, on this stream)
+  bool profile = false;
+  struct ProfRec { const char* tag; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
   fmwr::DBuf<double> pn_table;   // fast_pnorm Y table   (2862 f64)
   fmwr::DBuf<double> dp_table;   // fast_dpnorm Y table  (40002 f64)
   fmwr::DBuf<char> flush_buf;    // L2 flush scratch
@@ -205,10 +210,15 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 // kernel-launch bookkeeping: every launch of OUR kernels goes through this so gpu_launches is a count, not a guess
 #define FMWR_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
   do {                                                                                    \
+    cudaEvent_t _pe1 = nullptr;                                                           \
+    if ((ctx)->profile) _pe1 = ::fmwr::prof_begin((ctx), #kernel);                        \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+    if (_pe1) cudaEventRecord(_pe1, (ctx)->stream);                                       \
     (ctx)->launches++;                                                                    \
     FMWR_CUDA(cudaGetLastError());                                                        \
   } while (0)
+
+cudaEvent_t prof_begin(fmwr_ctx* ctx, const char* tag);   // records the start event, returns the stop event
 
 // padded factor stride: k rounded up so a row is LPR 16-byte vectors with LPR a power of two (<= 32 per chunk)
 int padded_k(int k, int prec);

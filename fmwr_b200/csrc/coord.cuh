@@ -23,6 +23,14 @@ struct SolverParams {
   T egamma;          // TDAP exp(-gamma)
 };
 
+// d/dv_f of the pairwise term for one non-zero: S_f x - v x^2, with the reference's operation order and
+// NO fused multiply-add (reference src/solver/SGD_Learner.h:129: `sum * x - v * x * x`).  On a row whose
+// only non-zero is this feature S_f == v*x, so the expression is exactly 0 in the reference; a contracted
+// FMA would leave a rounding residue of random sign, and TDAP (no beta in its denominator) turns the sign of
+// an infinitesimal gradient into a +-alpha jump of the parameter.
+__device__ __forceinline__ float fm_grad(float S, float v, float x) { return __fsub_rn(__fmul_rn(S, x), __fmul_rn(__fmul_rn(v, x), x)); }
+__device__ __forceinline__ double fm_grad(double S, double v, double x) { return __dsub_rn(__dmul_rn(S, x), __dmul_rn(__dmul_rn(v, x), x)); }
+
 // cumulative-penalty clip (Tsuruoka et al.), reference src/solver/SGD_Learner.h:195-204
 template <class T>
 __device__ __forceinline__ void sgd_apply_penalty(T& theta, T u, T& q)

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
             if (sp.l1) vec_to_arr(qr[vi], q);
 #pragma unroll
             for (int i = 0; i < VN; ++i) {
-              const T grad = Sf[ch][i] * x - th[i] * x * x;
+              const T grad = fm_grad(Sf[ch][i], th[i], x);
               T qq = sp.l1 ? q[i] : T(0);
               th[i] = sgd_step(th[i], mult * grad, sp.lr, sp.reg_v, sp.l1, u_v, qq);
               if (sp.l1) q[i] = qq;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
             vec_to_arr(zr[vi], z); vec_to_arr(nr[vi], nn);
 #pragma unroll
             for (int i = 0; i < VN; ++i) {
-              const T g = mult * (Sf[ch][i] * x - th[i] * x * x);
+              const T g = mult * fm_grad(Sf[ch][i], th[i], x);
               th[i] = ftrl_step(th[i], g, z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
             }
             zr[vi] = arr_to_vec(z); nr[vi] = arr_to_vec(nn);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
             vec_to_arr(ur[vi], u); vec_to_arr(nur[vi], nu); vec_to_arr(dr[vi], dl); vec_to_arr(hr[vi], h);
 #pragma unroll
             for (int i = 0; i < VN; ++i) {
-              const T g = mult * (Sf[ch][i] * x - th[i] * x * x);
+              const T g = mult * fm_grad(Sf[ch][i], th[i], x);
               const T z = tdap_state(th[i], g, u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
               th[i] = tdap_refresh(z, dl[i], sp.l1_v, sp.l2_v);
             }
@@ -288,6 +288,8 @@ static SolverParams<T> make_params(const fmwr_model* m, const fmwr_solver_cfg* s
   }
   return sp;
 }
+
+SolverParams<double> make_params_f64(const fmwr_model* m, const fmwr_solver_cfg* s) { return make_params<double>(m, s); }
 
 int solver_state_count(const SolverParams<double>& sp)
 {

@@ -1,8 +1,319 @@
-// placeholder: filled in below in this round
-#include "common.cuh"
+// Throughput (minibatch) mode of SGD / FTRL-Proximal / TDAP.
+//
+// The reference has no minibatch semantics (every solver is batch = 1, reference
+// src/solver/*_Learner.h); this mode is DEFINED here and reduces to the exact mode at batch = 1:
+//
+//   for each batch of B consecutive rows (in the reference's scan order):
+//     K1  row-parallel forward with frozen parameters: mult_r and S_r[f] for every row of the batch
+//     K2  coordinate-parallel update: every touched coordinate c receives ONE optimizer step with the
+//         summed gradient  G_c = sum_{r in batch, x_rc != 0} g_rc   (g_rc exactly as in the exact mode),
+//         FTRL: n += G^2, z += G - sigma*theta; TDAP likewise; SGD: theta -= lr*G then the L2 / L1 step.
+//         w0: FTRL/TDAP use the summed gradient; SGD uses the batch MEAN (a summed dense gradient
+//         diverges for B*lr*0.25 > 2); identical at B = 1.
+//
+// K2 does not use atomics: the batch's non-zeros are pre-sorted by (batch, feature, row)
+// (data.cu: minibatch_build), so one lane group owns one (batch, feature) segment, reduces its rows'
+// gradients in registers and writes the coordinate once -- deterministic and contention-free.
+#include "forward.cuh"
+#include "coord.cuh"
+
+#include <cmath>
+
 namespace fmwr {
-void train_minibatch(fmwr_ctx*, fmwr_model*, fmwr_data*, const fmwr_solver_cfg*, fmwr_trace*)
+
+int solver_state_count(const SolverParams<double>& sp);
+double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s);
+void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
+
+// ---- K1: forward + multiplier + S cache --------------------------------------------------------
+template <class T, int LPR, int CH>
+__global__ void __launch_bounds__(256)
+mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
+                  const float* __restrict__ y, const T* __restrict__ w, const T* __restrict__ v,
+                  const double* __restrict__ scal, int kp, int k0, int k1, int task, T lo, T hi,
+                  int64_t row_begin, int rows, T* __restrict__ mult, T* __restrict__ Scache)
 {
-  throw Error(FMWR_ERR_UNSUPPORTED, "minibatch mode not built yet");
+  typedef typename Vec<T>::type V16;
+  constexpr int U = (LPR >= 16) ? 8 : 4;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t row = row_begin + r;
+  const uint32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+  T S[CH][Vec<T>::N];
+  const T score = row_forward<T, LPR, CH, U>(col, val, b, e, w, v, kp, T(scal[0]), k0, k1, S);
+  if (lane == 0) mult[r] = grad_mult<T>(task, score, T(__ldg(y + row)), lo, hi);
+  if (lane < LPR) {
+    V16* dst = reinterpret_cast<V16*>(Scache + (size_t)r * kp);
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + lane] = arr_to_vec(S[ch]);
+  }
 }
+
+// ---- K2: one lane group per (batch, feature) segment --------------------------------------------
+template <class T>
+struct MbUpdArgs {
+  const uint32_t* seg_ptr; const uint32_t* seg_col; const uint32_t* ent_row; const float* ent_val;
+  uint32_t seg_begin, seg_end;
+  int64_t row_begin; int rows;          // rows of this batch that take part (row filter for a truncated last batch)
+  const T* mult; const T* Scache;
+  T* w; T* v; double* scal;
+  T* sw[4]; T* sv[4];
+  int kp, k0, k1;
+  SolverParams<T> sp;
+  T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
+};
+
+template <class T, int LPR, int CH, int SOLVER>
+__global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
+{
+  typedef typename Vec<T>::type V16;
+  constexpr int VN = Vec<T>::N;
+  constexpr int G = 32 / LPR;
+  const SolverParams<T> sp = a.sp;
+
+  // last block: the intercept (dense coordinate) -- fixed-order reduction of the batch's multipliers
+  if (blockIdx.x == gridDim.x - 1) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < a.rows; r += blockDim.x) acc += (double)a.mult[r];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double gsum = 0;
+      for (int i = 0; i < 8; ++i) gsum += red[i];
+      double* sc = a.scal;
+      if (SOLVER == FMWR_SGD) {
+        if (a.k0) sc[0] -= (double)sp.lr * (gsum / (double)a.rows + (double)sp.reg_w0 * sc[0]);
+      } else if (SOLVER == FMWR_FTRL) {
+        if (a.k0) {
+          const double old = sc[2];
+          sc[2] += gsum * gsum;
+          const double delta = (sqrt(sc[2]) - sqrt(old)) / (double)sp.alpha_w;
+          sc[1] += gsum - delta * sc[0];
+        }
+        sc[0] = -sc[1] * (double)sp.alpha_w / ((double)sp.beta_w + sqrt(sc[2]));
+      } else {
+        if (a.k0) {
+          const double old = sc[1];
+          sc[1] += gsum * gsum; sc[2] += gsum;
+          const double sigma = (sqrt(sc[1]) - sqrt(old)) / (double)sp.alpha_w;
+          sc[3] = (double)sp.egamma * (sc[3] + sigma);
+          sc[4] = (double)sp.egamma * (sc[4] + sigma * sc[0]);
+          sc[5] = sc[2] - sc[4];
+        }
+        sc[0] = -sc[5] / sc[3];
+      }
+    }
+    return;
+  }
+
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const uint32_t seg = a.seg_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
+  if (seg >= a.seg_end) return;
+  const uint32_t c = a.seg_col[seg];
+  const uint32_t eb = a.seg_ptr[seg], ee = a.seg_ptr[seg + 1];
+  const int kp = a.kp;
+
+  V16* vr = reinterpret_cast<V16*>(a.v + (size_t)c * kp);
+  T th[CH][VN], Gv[CH][VN];
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    vec_to_arr(vr[ch * LPR + l], th[ch]);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) Gv[ch][i] = T(0);
+  }
+  T Gw = T(0);
+  int touched = 0;
+  for (uint32_t i = eb; i < ee; ++i) {
+    const int r = (int)((int64_t)a.ent_row[i] - a.row_begin);
+    if (r >= a.rows) break;                       // rows ascend inside a segment: the rest is filtered too
+    const T x = T(a.ent_val[i]);
+    const T mr = a.mult[r];
+    const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)r * kp);
+    touched = 1;
+    Gw += mr * x;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      T s[VN];
+      vec_to_arr(sr[ch * LPR + l], s);
+#pragma unroll
+      for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] += mr * fm_grad(s[k2], th[ch][k2], x);
+    }
+  }
+  if (!touched) return;
+
+  // ---- linear weight (lane 0 of the group)
+  if (a.k1 && l == 0) {
+    T tw = a.w[c];
+    if (SOLVER == FMWR_SGD) {
+      T q = sp.l1 ? a.sw[0][c] : T(0);
+      tw = sgd_step(tw, Gw, sp.lr, sp.reg_w, sp.l1, a.u_w, q);
+      if (sp.l1) a.sw[0][c] = q;
+    } else if (SOLVER == FMWR_FTRL) {
+      T z = a.sw[0][c], nn = a.sw[1][c];
+      tw = ftrl_step(tw, Gw, z, nn, sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
+      a.sw[0][c] = z; a.sw[1][c] = nn;
+    } else {
+      T u = a.sw[0][c], nu = a.sw[1][c], dl = a.sw[2][c], h = a.sw[3][c];
+      const T z = tdap_state(tw, Gw, u, nu, dl, h, sp.alpha_w, sp.egamma);
+      a.sw[0][c] = u; a.sw[1][c] = nu; a.sw[2][c] = dl; a.sw[3][c] = h;
+      tw = tdap_refresh(z, dl, sp.l1_w, sp.l2_w);
+    }
+    a.w[c] = tw;
+  }
+  // ---- factors
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    const int vi = ch * LPR + l;
+    if (SOLVER == FMWR_SGD) {
+      T q[VN];
+      V16* qr = sp.l1 ? reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp) : nullptr;
+      if (sp.l1) vec_to_arr(qr[vi], q);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        T qq = sp.l1 ? q[i] : T(0);
+        th[ch][i] = sgd_step(th[ch][i], Gv[ch][i], sp.lr, sp.reg_v, sp.l1, a.u_v, qq);
+        if (sp.l1) q[i] = qq;
+      }
+      if (sp.l1) qr[vi] = arr_to_vec(q);
+    } else if (SOLVER == FMWR_FTRL) {
+      V16* zr = reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp);
+      V16* nr = reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp);
+      T z[VN], nn[VN];
+      vec_to_arr(zr[vi], z); vec_to_arr(nr[vi], nn);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) th[ch][i] = ftrl_step(th[ch][i], Gv[ch][i], z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
+      zr[vi] = arr_to_vec(z); nr[vi] = arr_to_vec(nn);
+    } else {
+      V16* ur = reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp);
+      V16* nur = reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp);
+      V16* dr = reinterpret_cast<V16*>(a.sv[2] + (size_t)c * kp);
+      V16* hr = reinterpret_cast<V16*>(a.sv[3] + (size_t)c * kp);
+      T u[VN], nu[VN], dl[VN], h[VN];
+      vec_to_arr(ur[vi], u); vec_to_arr(nur[vi], nu); vec_to_arr(dr[vi], dl); vec_to_arr(hr[vi], h);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const T z = tdap_state(th[ch][i], Gv[ch][i], u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
+        th[ch][i] = tdap_refresh(z, dl[i], sp.l1_v, sp.l2_v);
+      }
+      ur[vi] = arr_to_vec(u); nur[vi] = arr_to_vec(nu); dr[vi] = arr_to_vec(dl); hr[vi] = arr_to_vec(h);
+    }
+    vr[vi] = arr_to_vec(th[ch]);
+  }
 }
+
+template <class T>
+struct MbLaunch {
+  fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; const fmwr_solver_cfg* s;
+  int64_t row_begin; int rows; T* mult; T* Scache; MbUpdArgs<T> ua; int phase;   // phase 0: K1, 1: K2
+  template <class TT, int LPR, int CH>
+  void run()
+  {
+    if (phase == 0) {
+      FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH>), ceil_div(rows, 8), 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
+                  (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
+                  m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache);
+    } else {
+      constexpr int G = 32 / LPR;
+      const uint32_t nseg = ua.seg_end - ua.seg_begin;
+      const int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
+      switch (s->solver) {
+        case FMWR_SGD: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD>), grid, 256, 0, ua); break;
+        case FMWR_FTRL: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_FTRL>), grid, 256, 0, ua); break;
+        default: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_TDAP>), grid, 256, 0, ua); break;
+      }
+    }
+  }
+};
+
+template <class T>
+static SolverParams<T> params_from(const SolverParams<double>& d)
+{
+  SolverParams<T> sp;
+  sp.solver = d.solver; sp.l1 = d.l1;
+  sp.lr = T(d.lr); sp.reg_w = T(d.reg_w); sp.reg_v = T(d.reg_v); sp.reg_w0 = T(d.reg_w0);
+  sp.alpha_w = T(d.alpha_w); sp.alpha_v = T(d.alpha_v); sp.beta_w = T(d.beta_w); sp.beta_v = T(d.beta_v);
+  sp.l1_w = T(d.l1_w); sp.l1_v = T(d.l1_v); sp.l2_w = T(d.l2_w); sp.l2_v = T(d.l2_v); sp.egamma = T(d.egamma);
+  return sp;
+}
+
+SolverParams<double> make_params_f64(const fmwr_model* m, const fmwr_solver_cfg* s);
+
+template <class T>
+static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
+{
+  FMWR_REQUIRE(s->batch_size > 0, FMWR_ERR_ARG, "batch_size must be positive in minibatch mode");
+  FMWR_REQUIRE(s->random_step <= 1 && !s->visit_order, FMWR_ERR_UNSUPPORTED,
+               "minibatch mode scans rows in storage order (random_step must be 1)");
+  const SolverParams<double> spd = make_params_f64(m, s);
+  model_alloc_state(m, solver_state_count(spd));
+  FMWR_CUDA(cudaMemsetAsync((double*)m->scal.p + 1, 0, 7 * sizeof(double), ctx->stream));
+
+  const int64_t row0 = (s->compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0;     // F5: the reference scan starts at row 1
+  const int64_t B = s->batch_size;
+  const int64_t epoch_rows = d->n - row0;
+  if (epoch_rows <= 0) { if (tr) tr->iters_done = 0; return; }
+  minibatch_build(d, row0, B);
+  const int64_t n_batches = ceil_div64(epoch_rows, B);
+
+  DBuf<T> mult, Scache;
+  mult.alloc(B);
+  Scache.alloc((size_t)B * m->kp);
+
+  MbLaunch<T> L;
+  L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = mult.p; L.Scache = Scache.p;
+  MbUpdArgs<T>& ua = L.ua;
+  memset(&ua, 0, sizeof ua);
+  ua.seg_ptr = d->mb_seg_ptr.p; ua.seg_col = d->mb_seg_col.p; ua.ent_row = d->mb_ent_row.p; ua.ent_val = d->mb_ent_val.p;
+  ua.mult = mult.p; ua.Scache = Scache.p;
+  ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
+  for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
+  ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1;
+  ua.sp = params_from<T>(spd);
+
+  const int64_t max_iter = s->max_iter;
+  const int step = s->step_size;
+  int64_t iter = 0, next_track = 0;
+  int n_rec = 0, conv_times = 0, convergent = 0;
+  double old_score = 0.0, u_w = 0.0, u_v = 0.0;
+  while (iter < max_iter && !convergent) {
+    for (int64_t b = 0; b < n_batches && iter < max_iter; ++b) {
+      const int64_t rb = row0 + b * B;
+      int64_t rows = std::min<int64_t>(B, d->n - rb);
+      rows = std::min<int64_t>(rows, max_iter - iter);
+      L.row_begin = rb; L.rows = (int)rows;
+      L.phase = 0;
+      dispatch_layout<T>(m->kp, L);
+      if (spd.solver == FMWR_SGD && spd.l1) { u_w += (double)rows * spd.lr * spd.reg_w; u_v += (double)rows * spd.lr * spd.reg_v; }
+      ua.seg_begin = (uint32_t)d->mb_batch_seg[b]; ua.seg_end = (uint32_t)d->mb_batch_seg[b + 1];
+      ua.row_begin = rb; ua.rows = (int)rows; ua.u_w = T(u_w); ua.u_v = T(u_v);
+      L.phase = 1;
+      dispatch_layout<T>(m->kp, L);
+      iter += rows;
+      if (step > 0 && (iter > next_track || iter >= max_iter)) {
+        // tracker at batch granularity: one record per step_size samples crossed (and at the end)
+        const double score = tracker_score(ctx, m, d, s);
+        if (n_rec > 1 && std::fabs((score - old_score) / (old_score + 1e-30)) <= s->convergence) conv_times++;
+        else conv_times = 0;
+        old_score = score;
+        tracker_snapshot(m, tr, n_rec, (int)(iter - 1), score);
+        n_rec++;
+        next_track = (iter / step + 1) * (int64_t)step;
+        if (conv_times >= 3) { convergent = 1; break; }
+      }
+    }
+  }
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (tr) { tr->n_rec = n_rec; tr->convergent = convergent; tr->iters_done = (int)iter; }
+}
+
+void train_minibatch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
+{
+  if (m->prec == FMWR_F64) train_minibatch_t<double>(ctx, m, d, s, tr);
+  else train_minibatch_t<float>(ctx, m, d, s, tr);
+}
+
+}  // namespace fmwr

@@ -118,6 +118,12 @@ int fmwr_timer_start(fmwr_ctx* ctx);
 int fmwr_timer_stop_ms(fmwr_ctx* ctx, double* ms);
 int fmwr_ctx_launch_count(fmwr_ctx* ctx, int64_t* n_launches);   /* kernels launched by this library so far */
 int fmwr_flush_l2(fmwr_ctx* ctx);                                 /* writes a 256 MiB scratch buffer */
+/* per-kernel CUDA-event profile on the engine's stream: enable, run, then read "tag\tlaunches\ttotal_ms\n" lines */
+int fmwr_profile_enable(fmwr_ctx* ctx, int on);
+int fmwr_profile_read(fmwr_ctx* ctx, char* buf, int64_t buf_len);
+/* page-lock / unlock a caller buffer so the one-shot entry points copy at full PCIe speed */
+int fmwr_host_pin(void* ptr, int64_t bytes);
+int fmwr_host_unpin(void* ptr);
 
 /* ---- data: replaces SMatrix<float>::assign(List) + Data::add_data/add_target
  *      (reference src/util/Smatrix.h:44-61, src/FM.cpp:31-44, src/core/Data.h:48-86) ---- */

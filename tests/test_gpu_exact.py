@@ -1,0 +1,185 @@
+"""Exact (batch = 1) SGD / FTRL / TDAP parity against the oracle after N epochs
+(reference src/solver/{SGD,FTRL,TDAP}_Learner.h).  Tolerance: 1e-4 relative on parameters
+(north star); the fp64 instantiation is held to 1e-9."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from fmwr_b200 import _lib as L
+from fmwr_b200 import synth
+from tests.util import relerr
+
+pytestmark = pytest.mark.gpu
+
+SOLV = {O.SGD: L.SGD, O.FTRL: L.FTRL, O.TDAP: L.TDAP}
+
+
+def gpu_train(ctx, prec, ds, y, task, solver, k, w0, w, v, max_iter, regs=None, step_size=-1, metric=L.LL, compat=L.COMPAT_REFERENCE,
+              visit=None, random_step=1, k0=1, k1=1, **sk):
+    regs = regs or {}
+    d = L.Data.from_csr32(ctx, ds["n"], ds["p"], ds["rowptr"], ds["col"], ds["val"], y)
+    mc = L.ModelCfg(task=task, keep_w0=k0, keep_w1=k1, k=k, l2_w0=regs.get("l2_w0", 0), l1_w1=regs.get("l1_w", 0),
+                    l2_w1=regs.get("l2_w", 0), l1_v=regs.get("l1_v", 0), l2_v=regs.get("l2_v", 0))
+    m = L.Model(ctx, mc, ds["p"], prec)
+    m.set(w0, w, v)
+    sc = L.SolverCfg(solver=solver, max_iter=max_iter, random_step=random_step, learn_rate=sk.get("learn_rate", 0.01),
+                     alpha_w=sk.get("alpha_w", 0.1), alpha_v=sk.get("alpha_v", 0.1), beta_w=sk.get("beta_w", 1.0),
+                     beta_v=sk.get("beta_v", 1.0), gamma=sk.get("gamma", 1e-4), min_target=float(np.min(y)),
+                     max_target=float(np.max(y)), mode=L.MODE_EXACT, precision=prec, compat=compat,
+                     step_size=step_size, metric=metric, convergence=sk.get("convergence", 1e-4))
+    keep = None
+    if visit is not None:
+        keep = np.ascontiguousarray(visit, np.uint32)
+        sc.visit_order = L.ptr(keep); sc.n_visit = keep.size
+    tr = L.TraceBuf(200)
+    L.train_dev(ctx, m, d, sc, tr, keep=(keep,))
+    out = m.get()
+    m.close(); d.close()
+    return out, tr.result()
+
+
+def small(n=400, p=60, seed=3, nnz=8):
+    rowptr, col, val = synth.random_csr(n, p, nnz, seed=seed)
+    return dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+
+
+REGS = [dict(), dict(l1_w=0.01, l1_v=0.01, l2_w=0.001), dict(l2_w=0.01, l2_v=0.02, l2_w0=0.01)]
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL, O.TDAP])
+@pytest.mark.parametrize("task", [O.CLASSIFICATION, O.REGRESSION])
+@pytest.mark.parametrize("regs", REGS)
+def test_exact_matches_oracle_fp64(gpu_ctx, port, solver, task, regs):
+    rng = np.random.default_rng(1)
+    ds = small()
+    n, p, k = ds["n"], ds["p"], 4
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0) if task == O.CLASSIFICATION else rng.normal(0, 1, n)
+    y = y.astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k)); w0 = 0.3
+    iters = 3 * (n - 1) + 11                                 # N epochs == N*(n-1) updates (F4/F5), plus a ragged tail
+    cfg = O.make_cfg(task=task, solver=solver, k=k, max_iter=iters, min_target=float(y.min()), max_target=float(y.max()), **regs)
+    rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v)
+    (gw0, gw, gv), tr = gpu_train(gpu_ctx, L.F64, ds, y, task, SOLV[solver], k, w0, w, v, iters, regs)
+    assert tr["iters_done"] == iters
+    assert relerr(gw0, rw0) < 1e-9 and relerr(gw, rw) < 1e-9 and relerr(gv, rv) < 1e-9
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL, O.TDAP])
+def test_exact_fp32_within_north_star_tolerance(gpu_ctx, port, solver):
+    rng = np.random.default_rng(2)
+    ds = synth.make_dataset("c1", 3000)                      # C1-shaped (10 fields x 1000 ids, real-valued x), regression
+    n, p, k = ds["n"], ds["p"], 8
+    y = ds["y"]
+    w = np.zeros(p); v = rng.normal(0, 0.01, (p, k)); w0 = 0.0
+    iters = 2 * (n - 1)
+    cfg = O.make_cfg(task=O.REGRESSION, solver=solver, k=k, max_iter=iters, l2_w=0.001, l2_v=0.001,
+                     min_target=float(y.min()), max_target=float(y.max()))
+    rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v)
+    (gw0, gw, gv), _ = gpu_train(gpu_ctx, L.F32, ds, y, L.REGRESSION, SOLV[solver], k, w0, w, v, iters, dict(l2_w=0.001, l2_v=0.001))
+    # north star: batch=1 SGD / FTRL parameters within 1e-4.  TDAP is not on that list: theta = -(nu - h)/delta has no
+    # beta in the denominator and cancels two running sums, so fp32 STORAGE of nu and h costs ~1e-2; its tight parity
+    # is asserted with the fp64 instantiation (test_exact_matches_oracle_fp64) and here only loosely.
+    tol = 5e-2 if solver == O.TDAP else 1e-4
+    assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL])
+def test_exact_wide_rows_and_large_k(gpu_ctx, port, solver):
+    # rows wider than the CTA's slot count and k that needs several 16-byte chunks per lane
+    rng = np.random.default_rng(4)
+    n, p, k = 60, 400, 40
+    rowptr, col, val = synth.random_csr(n, p, 150, seed=8)
+    ds = dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.05, p); v = rng.normal(0, 0.05, (p, k)); w0 = 0.0
+    iters = 2 * (n - 1)
+    cfg = O.make_cfg(solver=solver, k=k, max_iter=iters)
+    rw0, rw, rv, _ = port.train(cfg, n, p, rowptr, col, val, y, w0, w, v)
+    (gw0, gw, gv), _ = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, SOLV[solver], k, w0, w, v, iters)
+    assert relerr(gw0, rw0) < 1e-9 and relerr(gw, rw) < 1e-9 and relerr(gv, rv) < 1e-9
+
+
+def test_exact_tracker_and_convergence(gpu_ctx, port):
+    rng = np.random.default_rng(5)
+    ds = small(n=300, p=40, seed=6)
+    n, p, k = ds["n"], ds["p"], 3
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = np.zeros(p); v = rng.normal(0, 0.01, (p, k))
+    iters = 1500
+    for metric in (O.LL, O.AUC, O.ACC):
+        cfg = O.make_cfg(solver=O.FTRL, k=k, max_iter=iters, step_size=100, metric=metric, convergence=1e-3)
+        rw0, rw, rv, rt = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, 0.0, w, v, max_rec=100)
+        (gw0, gw, gv), gt = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, L.FTRL, k, 0.0, w, v, iters, step_size=100,
+                                      metric=metric, convergence=1e-3)
+        assert gt["n_rec"] == rt["n_rec"] and (gt["rec_index"] == rt["rec_index"]).all()
+        assert gt["convergent"] == rt["convergent"] and gt["iters_done"] == rt["iters_done"]
+        assert relerr(gt["eval_train"], rt["eval_train"]) < 1e-9
+        assert relerr(gv, rv) < 1e-9
+
+
+def test_exact_explicit_visit_order_random_step(gpu_ctx, port):
+    # random_step > 1: both sides consume the same injected rand() stream (reference src/util/Random.h:126-132)
+    rng = np.random.default_rng(6)
+    ds = small(n=500, p=50, seed=7)
+    n, p, k = ds["n"], ds["p"], 4
+    y = rng.normal(0, 1, n).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k))
+    rands = rng.integers(0, 2**31 - 1, 5000).astype(np.int32)
+    step, iters = 5, 700
+    # the visit sequence the reference derives from that stream
+    u = rands / (2.0**31)
+    sel = (u * step + 1).astype(np.uint32)
+    order = []; q = 0
+    while len(order) < iters:
+        i = sel[q]; q += 1
+        while i < n and len(order) < iters:
+            order.append(i); i += sel[q]; q += 1
+    cfg = O.make_cfg(task=O.REGRESSION, solver=O.SGD, k=k, max_iter=iters, random_step=step, min_target=float(y.min()),
+                     max_target=float(y.max()))
+    port.set_streams(None, None, rands)
+    rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, 0.1, w, v)
+    port.set_streams(None, None, None)
+    (gw0, gw, gv), _ = gpu_train(gpu_ctx, L.F64, ds, y, L.REGRESSION, L.SGD, k, 0.1, w, v, iters, visit=order, random_step=step)
+    assert relerr(gw0, rw0) < 1e-9 and relerr(gw, rw) < 1e-9 and relerr(gv, rv) < 1e-9
+
+
+def test_exact_keep_flags(gpu_ctx, port):
+    rng = np.random.default_rng(8)
+    ds = small(n=200, p=30, seed=9)
+    n, p, k = ds["n"], ds["p"], 2
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k))
+    for k0, k1 in ((0, 1), (1, 0)):
+        cfg = O.make_cfg(solver=O.SGD, k=k, max_iter=300, k0=k0, k1=k1)
+        rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, 0.2, w, v)
+        (gw0, gw, gv), _ = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, L.SGD, k, 0.2, w, v, 300, k0=k0, k1=k1)
+        assert relerr(gw0, rw0) < 1e-9 and relerr(gw, rw) < 1e-9 and relerr(gv, rv) < 1e-9
+
+
+def test_exact_fixed_mode_visits_row0(gpu_ctx):
+    # compat=0 ("fixed"): the scan includes row 0, which the reference never trains on (F5)
+    ds = small(n=5, p=10, seed=1, nnz=3)
+    y = np.ones(5, np.float32)
+    w = np.zeros(10); v = np.zeros((10, 2))
+    (w0a, wa, _), _ = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, L.SGD, 2, 0.0, w, v, 1, compat=0)
+    (w0b, wb, _), _ = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, L.SGD, 2, 0.0, w, v, 1, compat=L.COMPAT_REFERENCE)
+    r0 = ds["col"][ds["rowptr"][0]:ds["rowptr"][1]]
+    r1 = ds["col"][ds["rowptr"][1]:ds["rowptr"][2]]
+    assert np.count_nonzero(wa) == len(r0) and np.all(wa[r0] != 0)
+    assert np.count_nonzero(wb) == len(r1) and np.all(wb[r1] != 0)
+
+
+def test_exact_tdap_single_nnz_rows_no_fma_residue(gpu_ctx, port):
+    # rows with one non-zero make S_f*x - v*x*x exactly 0 in the reference; a fused multiply-add would leave a
+    # residue whose sign TDAP amplifies to +-alpha (see coord.cuh: fm_grad)
+    rng = np.random.default_rng(9)
+    n, p, k = 300, 20, 4
+    rowptr, col, val = synth.random_csr(n, p, 2, seed=10)
+    ds = dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k))
+    for prec, tol in ((L.F64, 1e-9), (L.F32, 1e-3)):
+        cfg = O.make_cfg(solver=O.TDAP, k=k, max_iter=2 * (n - 1))
+        rw0, rw, rv, _ = port.train(cfg, n, p, rowptr, col, val, y, 0.3, w, v)
+        (gw0, gw, gv), _ = gpu_train(gpu_ctx, prec, ds, y, L.CLASSIFICATION, L.TDAP, k, 0.3, w, v, 2 * (n - 1))
+        assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol

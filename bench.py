@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--features", type=int, default=1_000_000)
     ap.add_argument("--k", type=int, default=32)
-    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -146,7 +146,7 @@ struct fmwr_data {
   int64_t mb_batch = 0;          // rows per batch the structure was built for (0: none)
   int64_t mb_row0 = 0;           // first row covered
   fmwr::DBuf<uint32_t> mb_seg_ptr;   // [n_seg+1] entry offsets
-  fmwr::DBuf<uint32_t> mb_seg_col;   // [n_seg]
+  fmwr::DBuf<uint4> mb_seg_rec;      // [n_seg] {feature, length, first row, first value bits}
   fmwr::DBuf<uint32_t> mb_ent_row;   // [nnz'] global row index
   fmwr::DBuf<float> mb_ent_val;      // [nnz']
   std::vector<int64_t> mb_batch_seg;  // [n_batches+1] segment offsets per batch (host)

@@ -350,20 +350,30 @@ __global__ void mb_heads(const uint64_t* __restrict__ keys, int64_t m, uint32_t*
 
 __global__ void mb_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ segid,
                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ erow, const float* __restrict__ val,
-                        uint32_t e0, int64_t m, int colbits, uint32_t* __restrict__ seg_ptr, uint32_t* __restrict__ seg_col,
+                        uint32_t e0, int64_t m, int colbits, uint32_t* __restrict__ seg_ptr, uint4* __restrict__ seg_rec,
                         uint32_t* __restrict__ ent_row, float* __restrict__ ent_val, uint32_t n_seg)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const uint32_t e = perm[i];
-  ent_row[i] = erow[e];
-  ent_val[i] = val[e0 + e];
+  const uint32_t r = erow[e];
+  const float x = val[e0 + e];
+  ent_row[i] = r;
+  ent_val[i] = x;
   if (head[i]) {
+    // segment record: {feature, length (filled by mb_seg_len), first row, first value} -- one 16-byte load gives
+    // the update kernel everything it needs for the common single-entry segment
     const uint32_t s = segid[i];
     seg_ptr[s] = (uint32_t)i;
-    seg_col[s] = (uint32_t)(keys[i] & ((1ull << colbits) - 1ull));
+    seg_rec[s] = make_uint4((uint32_t)(keys[i] & ((1ull << colbits) - 1ull)), 0u, r, __float_as_uint(x));
   }
   if (i == m - 1) seg_ptr[n_seg] = (uint32_t)m;
+}
+
+__global__ void mb_seg_len(const uint32_t* __restrict__ seg_ptr, uint4* __restrict__ seg_rec, uint32_t n_seg)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_seg) seg_rec[s].y = seg_ptr[s + 1] - seg_ptr[s];
 }
 
 // first segment of each batch: batch_seg[b] = #segments with batch id < b
@@ -403,7 +413,7 @@ void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
   const int batchbits = bits_for((uint64_t)(n_batches > 0 ? n_batches - 1 : 0));
   d->mb_ent_row.alloc(m); d->mb_ent_val.alloc(m);
   if (m == 0) {
-    d->mb_seg_ptr.alloc(1); d->mb_seg_col.alloc(1);
+    d->mb_seg_ptr.alloc(1); d->mb_seg_rec.alloc(1);
     FMWR_CUDA(cudaMemsetAsync(d->mb_seg_ptr.p, 0, 4, ctx->stream));
     d->mb_batch = batch; d->mb_row0 = row0;
     return;
@@ -428,9 +438,10 @@ void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_CUDA(cudaMemcpy(&last_id, segid.p + (m - 1), 4, cudaMemcpyDeviceToHost));
   FMWR_CUDA(cudaMemcpy(&last_head, head.p + (m - 1), 4, cudaMemcpyDeviceToHost));
   const uint32_t n_seg = last_id + last_head;
-  d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_col.alloc(n_seg);
+  d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_rec.alloc(n_seg);
   FMWR_LAUNCH(ctx, mb_emit, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, idx_out.p, erow.p, d->val.p, e0, m,
-              colbits, d->mb_seg_ptr.p, d->mb_seg_col.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
+              colbits, d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
+  FMWR_LAUNCH(ctx, mb_seg_len, ceil_div(n_seg, 256), 256, 0, d->mb_seg_ptr.p, d->mb_seg_rec.p, n_seg);
   DBuf<uint32_t> bseg;
   bseg.alloc(n_batches + 1);
   // default every batch offset to n_seg (covers trailing empty batches), then fill real starts
@@ -657,7 +668,7 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field
         FMWR_LAUNCH(ctx, fill_normal<float>, ceil_div(pw, 256), 256, 0, (float*)pm->w.p, pw, 1, 1, 0.0, 0.1, seed + 2);
         forward_launch(ctx, pm, d, FMWR_LINK_NONE, 0, 0);
         d->y.alloc(n); d->has_labels = true;
-        FMWR_LAUNCH(ctx, synth_labels<float>, ceil_div(n, 256), 256, 0, d->pred32.p, n, label_mode, noise, seed + 3, d->y.p);
+        FMWR_LAUNCH(ctx, synth_labels<double>, ceil_div(n, 256), 256, 0, d->pred64.p, n, label_mode, noise, seed + 3, d->y.p);
         DBuf<float> mm; mm.alloc(2);
         const float init[2] = {INFINITY, -INFINITY};
         FMWR_CUDA(cudaMemcpyAsync(mm.p, init, 8, cudaMemcpyHostToDevice, ctx->stream));

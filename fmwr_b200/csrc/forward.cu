@@ -8,7 +8,7 @@ template <class T, int LPR, int CH>
 __global__ void __launch_bounds__(256)
 forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                const T* __restrict__ w, const T* __restrict__ v, const double* __restrict__ scal, int kp, int k0, int k1,
-               int64_t n, int link, double lo, double hi, const double* __restrict__ pnY, T* __restrict__ out)
+               int64_t n, int link, double lo, double hi, const double* __restrict__ pnY, double* __restrict__ out)
 {
   constexpr int U = (LPR >= 16) ? 8 : 4;
   const int lane = threadIdx.x & 31;
@@ -19,7 +19,7 @@ forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__
     const uint32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
     T S[CH][Vec<T>::N];
     const T score = row_forward<T, LPR, CH, U>(col, val, b, e, w, v, kp, w0, k0, k1, S);
-    if (lane == 0) out[row] = T(apply_link(link, (double)score, lo, hi, pnY));
+    if (lane == 0) out[row] = apply_link(link, (double)score, lo, hi, pnY);
   }
 }
 
@@ -33,9 +33,11 @@ struct FwdLaunch {
     int64_t cap = (int64_t)ctx->sm_count * 8 * 4;   // 4 waves of 8 resident CTAs per SM, grid-stride beyond that
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    T* out;
-    if (sizeof(T) == 8) { d->pred64.ensure(d->n); out = (T*)d->pred64.p; d->pred_prec = FMWR_F64; }
-    else { d->pred32.ensure(d->n); out = (T*)d->pred32.p; d->pred_prec = FMWR_F32; }
+    // predictions are always kept in fp64 (8 of ~5.5 KB per row): the R side wants a NumericVector and the
+    // reference's log-likelihood (src/core/Evaluation.h:80-89) is NaN for a probability rounded to exactly 1.0f
+    d->pred64.ensure(d->n);
+    double* out = d->pred64.p;
+    d->pred_prec = FMWR_F64;
     FMWR_LAUNCH(ctx, (forward_kernel<T, LPR, CH>), grid, block, 0,
                 d->rowptr.p, d->col.p, d->val.p, (const T*)m->w.p, (const T*)m->v.p, (const double*)m->scal.p,
                 m->kp, m->cfg.keep_w0, m->cfg.keep_w1, d->n, link, lo, hi, ctx->pn_table.p, out);

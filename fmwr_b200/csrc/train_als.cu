@@ -1,8 +1,556 @@
-// placeholder: filled in below in this round
-#include "common.cuh"
+// ALS / MCMC coordinate passes over the CSC twin.
+//
+// Replaces MCMC_ALS_Learner::{learn, update_all, calculate_error, update_alpha, update_w0, update_w,
+// update_v, update_w_lambda, update_w_mu, update_v_lambda, update_v_mu}
+// (reference src/solver/MCMC_ALS_Learner.h:91-562) at nthreads = 1, i.e. exact Gauss-Seidel in feature
+// order.  GPU width comes from the "phase" decomposition (data.cu: phases_build): consecutive feature
+// ranges whose members never share a row touch disjoint entries of the error vector e and of the
+// per-row factor sums q, so updating them concurrently IS the sequential result.  For field-structured
+// data (one-hot user/item/context, Criteo's 39 fields) a phase is a field.
+//
+// Per sweep (update_all order, :141-155): forward -> e (and q[r][f] = S_f of every row, which is what the
+// reference rebuilds per factor at :286-299) -> calculate_error -> alpha -> w0 -> lambda_w -> mu_w -> w
+// [-> lambda_v -> mu_v -> V when enable_v; the shipped code comments that block out, SURVEY F1].
+// Hyper-parameters are the ones MCMC_ALS_Learner::init forces (alpha_0 = gamma_0 = beta_0 = 1, mu_0 = 0,
+// alpha = 1, w0_mean_0 = 0), one attribute group (src/FM.cpp:75).
+#include "forward.cuh"
+
+#include <cmath>
+#include <random>
+
 namespace fmwr {
-void train_als_mcmc(fmwr_ctx*, fmwr_model*, fmwr_data*, const fmwr_solver_cfg*, fmwr_trace*)
+
+double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s);
+void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
+int tracker_step_size(int step_size, int max_iter);
+
+constexpr int ALS_LONG = 4096;      // columns at least this long get a whole CTA
+
+// ---- forward: e = raw score, q[r][:] = S_f -----------------------------------------------------------
+template <class T, int LPR, int CH>
+__global__ void __launch_bounds__(256)
+als_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
+                   const T* __restrict__ w, const T* __restrict__ v, const double* __restrict__ scal, int kp, int k0, int k1,
+                   int64_t n, T* __restrict__ e, T* __restrict__ q)
 {
-  throw Error(FMWR_ERR_UNSUPPORTED, "ALS/MCMC not built yet");
+  typedef typename Vec<T>::type V16;
+  constexpr int U = (LPR >= 16) ? 8 : 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const T w0 = T(scal[0]);
+  for (int64_t row = warp0; row < n; row += nwarps) {
+    const uint32_t b = __ldg(rowptr + row), en = __ldg(rowptr + row + 1);
+    T S[CH][Vec<T>::N];
+    const T score = row_forward<T, LPR, CH, U>(col, val, b, en, w, v, kp, w0, k0, k1, S);
+    if (lane == 0) e[row] = score;
+    if (q && lane < LPR) {
+      V16* dst = reinterpret_cast<V16*>(q + (size_t)row * kp);
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + lane] = arr_to_vec(S[ch]);
+    }
+  }
 }
+
+template <class T>
+struct AlsFwd {
+  fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; T* e; T* q;
+  template <class TT, int LPR, int CH>
+  void run()
+  {
+    int64_t want = ceil_div64(d->n, 8);
+    int64_t cap = (int64_t)ctx->sm_count * 32;
+    int grid = (int)std::max<int64_t>(1, std::min(want, cap));
+    FMWR_LAUNCH(ctx, (als_forward_kernel<TT, LPR, CH>), grid, 256, 0, d->rowptr.p, d->col.p, d->val.p, (const TT*)m->w.p,
+                (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1, d->n, e, q);
+  }
+};
+
+// ---- uniform / normal sources ----------------------------------------------------------------------------
+struct RandSrc {
+  const int32_t* rands; long long n_rands;   // injected glibc rand() ints (NULL: counter hash)
+  uint64_t seed;
+};
+
+__device__ __forceinline__ double hash_unif(uint64_t key)   // (0,1)
+{
+  return ((double)(splitmix64(key) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
+
+__device__ __forceinline__ double hash_norm(uint64_t key)
+{
+  const double u1 = hash_unif(key), u2 = hash_unif(key ^ 0xA0761D6478BD642Full);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// sequential uniform source: either the injected rand() stream (position in *pos) or a per-row counter hash
+struct UnifStream {
+  const int32_t* rands; long long n_rands; long long* pos; uint64_t key; uint32_t ctr;
+  __device__ double next()
+  {
+    if (rands) {
+      const long long i = (*pos)++;
+      const int r = i < n_rands ? rands[i] : 0;
+      return r / 2147483648.0;                                  // rand() / (RAND_MAX + 1), reference src/util/Random.h:20-24
+    }
+    return hash_unif(key + 0x9E3779B97F4A7C15ull * (++ctr));
+  }
+};
+
+// fast_rnorm (Leva), reference src/util/Random.h:31-48
+__device__ double leva_norm(UnifStream& s)
+{
+  double u, v, av, x, y, Q;
+  do {
+    do { u = s.next(); } while (u == 0.0);
+    v = 1.7156 * (s.next() - 0.5);
+    av = v < 0 ? -v : v;
+    x = u - 0.449871;
+    y = av + 0.386595;
+    Q = x * x + y * (0.19600 * y - 0.25472 * x);
+    if (Q < 0.27597) break;
+  } while ((Q > 0.27846) || ((v * v) > (-4.0 * u * u * log(u))));
+  return v / u;
+}
+
+// fast_trnorm_left(left) standard form, reference src/util/Random.h:51-76
+__device__ double trnorm_left_std(UnifStream& s, double left)
+{
+  if (left < 0.0) {
+    for (;;) { const double r = leva_norm(s); if (r >= left) return r; }
+  }
+  const double a = 0.5 * (left + sqrt(left * left + 4.0));
+  for (;;) {
+    const double z = -log(1 - s.next()) / a + left;
+    double dd = z - a;
+    dd = exp(-(dd * dd) / 2);
+    const double u = s.next();
+    if (u < dd) return z;
+  }
+}
+
+// ---- calculate_error (reference :520-562) ------------------------------------------------------------------
+// mode 0: regression e -= y; 1: ALS classification hazard table; 2: MCMC classification, truncated-normal draw
+template <class T>
+__global__ void als_error_kernel(T* __restrict__ e, const float* __restrict__ y, int64_t n, int mode,
+                                 const double* __restrict__ dpY, uint64_t seed, uint64_t sweep)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = (double)e[i];
+  const float yi = y[i];
+  if (mode == 0) {
+    e[i] = T(s - (double)yi);
+  } else if (mode == 1) {
+    e[i] = T(yi >= 0.0f ? -dev_fast_dpnorm(dpY, -s) : dev_fast_dpnorm(dpY, s));
+  } else {
+    UnifStream us{nullptr, 0, nullptr, splitmix64(seed ^ (sweep * 0xD6E8FEB86659FD93ull) ^ (uint64_t)i), 0};
+    // as shipped: N(0,1) truncated at the score (reference :536-539)
+    const double t = yi >= 0.0f ? trnorm_left_std(us, s) : -trnorm_left_std(us, -s);
+    e[i] = T(s - t);
+  }
+}
+
+// injected rand() stream: rows consume a variable number of draws in row order -> one thread, validation sizes only
+template <class T>
+__global__ void als_error_stream_kernel(T* __restrict__ e, const float* __restrict__ y, int64_t n,
+                                        const int32_t* __restrict__ rands, long long n_rands, long long* __restrict__ pos)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  UnifStream us{rands, n_rands, pos, 0, 0};
+  for (int64_t i = 0; i < n; ++i) {
+    const double s = (double)e[i];
+    const double t = y[i] >= 0.0f ? trnorm_left_std(us, s) : -trnorm_left_std(us, -s);
+    e[i] = T(s - t);
+  }
+}
+
+// ---- reductions ------------------------------------------------------------------------------------------
+// mode 0: sum x, 1: sum x^2, 2: sum (x - c)^2
+template <class T>
+__global__ void als_reduce_kernel(const T* __restrict__ x, int64_t n, int64_t stride, int mode, double c, double* __restrict__ part)
+{
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)x[i * stride];
+    acc += mode == 0 ? v : (mode == 1 ? v * v : (v - c) * (v - c));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    part[blockIdx.x] = s;
+  }
+}
+
+template <class T>
+static double reduce(fmwr_ctx* ctx, const T* x, int64_t n, int64_t stride, int mode, double c)
+{
+  if (n <= 0) return 0.0;
+  const int nblk = (int)std::min<int64_t>(1024, std::max<int64_t>(1, ceil_div64(n, 256)));
+  ctx->red_scratch.ensure(1024);
+  FMWR_LAUNCH(ctx, als_reduce_kernel<T>, nblk, 256, 0, x, n, stride, mode, c, ctx->red_scratch.p);
+  std::vector<double> h(nblk);
+  FMWR_CUDA(cudaMemcpyAsync(h.data(), ctx->red_scratch.p, 8 * nblk, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  double s = 0;
+  for (int i = 0; i < nblk; ++i) s += h[i];
+  return s;
+}
+
+template <class T>
+__global__ void als_shift_kernel(T* __restrict__ e, int64_t n, T d)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) e[i] -= d;
+}
+
+// ---- coordinate kernels --------------------------------------------------------------------------------
+template <class T>
+struct CoordArgs {
+  const uint32_t* colptr; const uint32_t* crow; const float* cval;
+  uint32_t c_begin, c_end;           // the phase's feature range
+  const uint32_t* long_cols; int n_long;
+  T* e; T* q; int kp; int f;         // q == nullptr for the w pass
+  T* theta; int64_t theta_stride;    // w (stride 1) or V + f (stride kp)
+  double alpha, lambda, mu;
+  int do_sample; int w_sd_is_var;    // F7: w drawn with the variance as s.d.
+  const double* normals; long long n_normals; long long normal_base;   // draw for column c: normals[normal_base + c]
+  uint64_t seed;
+};
+
+template <class T>
+__device__ __forceinline__ bool dev_bad(T x) { return isnan(x) || isinf(x); }
+
+// one feature; `part` = number of cooperating threads, `tid` = index inside the group; reduce() sums over the group
+template <class T, class Reduce>
+__device__ __forceinline__ void coord_update(const CoordArgs<T>& a, uint32_t c, int tid, int part, Reduce reduce)
+{
+  const uint32_t b = a.colptr[c], en = a.colptr[c + 1];
+  T* th = a.theta + (size_t)c * a.theta_stride;
+  const double old = (double)*th;
+  double A = 0.0, Bm = 0.0;
+  if (a.q == nullptr) {
+    // update_w statistics (reference :225-230): A = sum x^2, Bm = sum (e x - w x^2)
+    for (uint32_t j = b + tid; j < en; j += part) {
+      const double x = (double)a.cval[j];
+      Bm += (double)a.e[a.crow[j]] * x - old * x * x;
+      A += x * x;
+    }
+  } else {
+    // update_v statistics (reference :313-321): h = x q - x^2 v, A = sum h^2, Bm = sum h e
+    for (uint32_t j = b + tid; j < en; j += part) {
+      const float xf = a.cval[j];
+      const uint32_t r = a.crow[j];
+      const double h = (double)xf * (double)a.q[(size_t)r * a.kp + a.f] - (double)(xf * xf) * old;
+      Bm += h * (double)a.e[r];
+      A += h * h;
+    }
+  }
+  A = reduce(A);
+  Bm = reduce(Bm);
+  if (a.q != nullptr) Bm -= old * A;                                   // :322
+  const double var = 1.0 / (a.lambda + a.alpha * A);
+  const double mean = -var * (a.alpha * Bm - a.mu * a.lambda);
+  double nv;
+  bool upd = true;
+  if (dev_bad(var)) nv = 0.0;                                           // :235-236, :326-327
+  else if (a.do_sample) {
+    const long long di = a.normal_base + (long long)c;
+    const double z = a.normals ? (di < a.n_normals ? a.normals[di] : 0.0) : hash_norm(a.seed ^ (uint64_t)di * 0x9E3779B97F4A7C15ull);
+    const double sd = (a.q == nullptr && a.w_sd_is_var) ? var : sqrt(var);   // :239 (F7) vs :330
+    nv = mean + sd * z;
+  } else nv = mean;
+  if (dev_bad(nv)) { nv = old; upd = false; }                           // CHECK_PARAM
+  if (tid == 0) *th = T(nv);
+  if (!upd) return;
+  const double dlt = old - nv;
+  if (a.q == nullptr) {
+    for (uint32_t j = b + tid; j < en; j += part) {
+      const uint32_t r = a.crow[j];
+      a.e[r] = T((double)a.e[r] - (double)a.cval[j] * dlt);             // :251-253
+    }
+  } else {
+    for (uint32_t j = b + tid; j < en; j += part) {
+      const float xf = a.cval[j];
+      const uint32_t r = a.crow[j];
+      const size_t qi = (size_t)r * a.kp + a.f;
+      const double qv = (double)a.q[qi];
+      const double h = (double)xf * qv - (double)(xf * xf) * old;
+      a.q[qi] = T(qv - (double)xf * dlt);                               // :346
+      a.e[r] = T((double)a.e[r] - h * dlt);                             // :347
+    }
+  }
+}
+
+// warp per feature (short columns); long ones are left to the CTA kernel
+template <class T>
+__global__ void __launch_bounds__(256) coord_warp_kernel(CoordArgs<T> a)
+{
+  const uint32_t c = a.c_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (c >= a.c_end) return;
+  const uint32_t len = a.colptr[c + 1] - a.colptr[c];
+  if (len >= ALS_LONG) return;
+  coord_update<T>(a, c, threadIdx.x & 31, 32, [](double v) { return warp_sum(v); });
+}
+
+template <class T>
+__global__ void __launch_bounds__(512) coord_block_kernel(CoordArgs<T> a)
+{
+  __shared__ double red[16];
+  __shared__ double tot;
+  const uint32_t c = a.long_cols[blockIdx.x];
+  auto block_sum = [&](double v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0;
+      for (int i = 0; i < 16; ++i) s += red[i];
+      tot = s;
+    }
+    __syncthreads();
+    return tot;
+  };
+  coord_update<T>(a, c, threadIdx.x, 512, block_sum);
+}
+
+// ---- driver ----------------------------------------------------------------------------------------------
+struct PhaseInfo {
+  std::vector<uint32_t> begin;                 // [n_phases + 1]
+  std::vector<std::vector<uint32_t>> long_cols;
+  DBuf<uint32_t> long_dev;                     // concatenated
+  std::vector<size_t> long_off;
+};
+
+static void build_phase_info(fmwr_data* d, PhaseInfo& ph)
+{
+  fmwr_ctx* ctx = d->ctx;
+  phases_build(d);
+  ph.begin = d->phase_begin;
+  const int np = (int)ph.begin.size() - 1;
+  std::vector<uint32_t> cp(d->p + 1);
+  FMWR_CUDA(cudaMemcpyAsync(cp.data(), d->colptr.p, 4 * (d->p + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> all;
+  ph.long_off.assign(np + 1, 0);
+  for (int i = 0; i < np; ++i) {
+    ph.long_off[i] = all.size();
+    for (uint32_t c = ph.begin[i]; c < ph.begin[i + 1]; ++c)
+      if (cp[c + 1] - cp[c] >= (uint32_t)ALS_LONG) all.push_back(c);
+  }
+  ph.long_off[np] = all.size();
+  ph.long_dev.alloc(all.size());
+  if (!all.empty()) FMWR_CUDA(cudaMemcpyAsync(ph.long_dev.p, all.data(), 4 * all.size(), cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+template <class T>
+static void run_phases(fmwr_ctx* ctx, const PhaseInfo& ph, CoordArgs<T> a)
+{
+  const int np = (int)ph.begin.size() - 1;
+  for (int i = 0; i < np; ++i) {
+    a.c_begin = ph.begin[i]; a.c_end = ph.begin[i + 1];
+    const uint32_t nc = a.c_end - a.c_begin;
+    if (nc == 0) continue;
+    FMWR_LAUNCH(ctx, coord_warp_kernel<T>, ceil_div(nc, 8), 256, 0, a);
+    const int nl = (int)(ph.long_off[i + 1] - ph.long_off[i]);
+    if (nl > 0) {
+      a.long_cols = ph.long_dev.p + ph.long_off[i]; a.n_long = nl;
+      FMWR_LAUNCH(ctx, coord_block_kernel<T>, nl, 512, 0, a);
+    }
+  }
+}
+
+struct HostStreams {
+  const double* normals; long long n_normals, i_normal;
+  const double* gammas; long long n_gammas, i_gamma;
+  std::mt19937_64 rng;
+  bool injected;
+  double normal(double mean, double sd)
+  {
+    double z;
+    if (injected) { z = (normals && i_normal < n_normals) ? normals[i_normal] : 0.0; }
+    else { std::normal_distribution<double> nd(0.0, 1.0); z = nd(rng); }
+    i_normal++;
+    return mean + sd * z;
+  }
+  double gamma(double shape, double scale)
+  {
+    double g;
+    if (injected) { g = (gammas && i_gamma < n_gammas) ? gammas[i_gamma] : 1.0; }
+    else { std::gamma_distribution<double> gd(shape, 1.0); g = gd(rng); }
+    i_gamma++;
+    return scale * g;
+  }
+};
+
+static inline bool hbad(double x) { return std::isnan(x) || std::isinf(x); }
+
+template <class T>
+static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
+{
+  const int64_t n = d->n, p = d->p;
+  const int k = m->k, kp = m->kp;
+  const bool mcmc = s->solver == FMWR_MCMC;
+  const bool do_sample = mcmc, do_multilevel = mcmc;                     // reference :567-587
+  const bool cls = m->cfg.task == FMWR_CLASSIFICATION;
+  const bool enable_v = s->enable_v && k > 0;
+  FMWR_REQUIRE(n < (1ll << 31) && p < (1ll << 31), FMWR_ERR_UNSUPPORTED, "dimension too large");
+
+  transpose_build(d);                                                    // src/FM.cpp:148-152
+  PhaseInfo ph;
+  build_phase_info(d, ph);
+
+  DBuf<T> e, q;
+  e.alloc(n);
+  if (enable_v) q.alloc((size_t)n * kp);
+  DBuf<double> normals_dev;
+  DBuf<int32_t> rands_dev;
+  DBuf<long long> rand_pos;
+  const bool injected = s->normals || s->gammas || s->rands;
+  if (s->normals && s->n_normals > 0) {
+    normals_dev.alloc(s->n_normals);
+    FMWR_CUDA(cudaMemcpyAsync(normals_dev.p, s->normals, 8 * s->n_normals, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (s->rands && s->n_rands > 0) {
+    rands_dev.alloc(s->n_rands);
+    FMWR_CUDA(cudaMemcpyAsync(rands_dev.p, s->rands, 4 * s->n_rands, cudaMemcpyHostToDevice, ctx->stream));
+    rand_pos.alloc(1);
+    rand_pos.zero(ctx->stream);
+  }
+  HostStreams hs{s->normals, (long long)s->n_normals, 0, s->gammas, (long long)s->n_gammas, 0, std::mt19937_64(s->seed ^ 0x5DEECE66Dull), injected};
+
+  // MCMC_ALS_Learner::init (:59-89) -- constants forced regardless of the R-side values (F2)
+  const double alpha_0 = 1.0, gamma_0 = 1.0, beta_0 = 1.0, mu_0 = 0.0, w0_mean_0 = 0.0;
+  double alpha = 1.0, w_mu = 0.0, w_lambda = 0.0;
+  std::vector<double> v_mu(std::max(k, 1), 0.0), v_lambda(std::max(k, 1), 0.0);
+
+  T* wp = (T*)m->w.p;
+  T* vp = (T*)m->v.p;
+  double* scal = (double*)m->scal.p;
+  const int step = tracker_step_size(s->step_size, s->max_iter);
+  int ii = -1, n_rec = 0;
+  int sweep = 0;
+  for (; sweep < s->max_iter; ++sweep) {
+    // tracker (:101-124): train metric of the model at the start of the sweep
+    if (step > 0) {
+      ii++;
+      if (ii == step) ii = 0;
+      if (ii == 0 || sweep == s->max_iter - 1) {
+        const double score = tracker_score(ctx, m, d, s);
+        tracker_snapshot(m, tr, n_rec, sweep, score);
+        n_rec++;
+      }
+    }
+    // e <- predict_batch (:100), q[r][f] <- S_f
+    AlsFwd<T> fw{ctx, m, d, e.p, enable_v ? q.p : nullptr};
+    dispatch_layout<T>(kp, fw);
+    // calculate_error (:520-562)
+    if (!cls) {
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, d->y.p, n, 0, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+    } else if (!do_sample) {
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, d->y.p, n, 1, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+    } else if (s->rands) {
+      FMWR_LAUNCH(ctx, als_error_stream_kernel<T>, 1, 32, 0, e.p, d->y.p, n, rands_dev.p, (long long)s->n_rands, rand_pos.p);
+    } else {
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, d->y.p, n, 2, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+    }
+    // update_alpha (:360-380)
+    if (!do_multilevel) alpha = alpha_0;
+    else {
+      const double alpha_n = alpha_0 + (double)n;
+      const double gamma_n = gamma_0 + reduce<T>(ctx, e.p, n, 1, 1, 0.0);
+      const double a = hs.gamma(alpha_n / 2.0, 2.0 / gamma_n);
+      if (!hbad(a)) alpha = a;
+    }
+    // update_w0 (:162-188)
+    if (m->cfg.keep_w0) {
+      const double w0 = model_get_w0(m);
+      const double err = reduce<T>(ctx, e.p, n, 1, 0, 0.0) - (double)n * w0;
+      const double var = 1.0 / (m->cfg.l2_w0 + alpha * (double)n);
+      const double mean = -(alpha * err - w0_mean_0 * m->cfg.l2_w0) * var;
+      double nw = do_sample ? hs.normal(mean, std::sqrt(var)) : mean;
+      if (hbad(nw)) nw = w0;
+      FMWR_CUDA(cudaMemcpyAsync(scal, &nw, 8, cudaMemcpyHostToDevice, ctx->stream));
+      FMWR_LAUNCH(ctx, als_shift_kernel<T>, ceil_div(n, 256), 256, 0, e.p, n, T(w0 - nw));
+      FMWR_CUDA(cudaStreamSynchronize(ctx->stream));      // nw lives on this stack frame
+    }
+    if (m->cfg.keep_w1) {
+      // update_w_lambda (:415-445), update_w_mu (:383-412)
+      if (do_multilevel) {
+        double g = reduce<T>(ctx, wp, p, 1, 2, w_mu);
+        g += beta_0 * (w_mu - mu_0) * (w_mu - mu_0) + gamma_0;
+        const double la = alpha_0 + (double)p + 1;
+        const double nl = do_sample ? hs.gamma(la / 2.0, 2.0 / g) : la / g;
+        if (!hbad(nl)) w_lambda = nl;
+        double mm = reduce<T>(ctx, wp, p, 1, 0, 0.0);
+        mm = (mm + beta_0 * mu_0) / ((double)p + beta_0);
+        const double var = 1.0 / (((double)p + beta_0) * w_lambda);
+        const double nm = do_sample ? hs.normal(mm, std::sqrt(var)) : mm;
+        if (!hbad(nm)) w_mu = nm;
+      } else w_mu = mu_0;
+      // update_w (:190-270)
+      CoordArgs<T> a;
+      memset(&a, 0, sizeof a);
+      a.colptr = d->colptr.p; a.crow = d->crow.p; a.cval = d->cval.p;
+      a.e = e.p; a.q = nullptr; a.kp = kp; a.f = 0; a.theta = wp; a.theta_stride = 1;
+      a.alpha = alpha; a.lambda = w_lambda; a.mu = w_mu; a.do_sample = do_sample;
+      a.w_sd_is_var = (s->compat & FMWR_COMPAT_MCMC_W_SD) ? 1 : 0;
+      a.normals = injected ? normals_dev.p : nullptr; a.n_normals = s->n_normals; a.normal_base = hs.i_normal; a.seed = s->seed;
+      run_phases<T>(ctx, ph, a);
+      if (do_sample) hs.i_normal += p;
+    }
+    if (enable_v) {
+      // update_v_lambda (:486-517) for every factor, then update_v_mu (:448-483), then update_v (:272-354)
+      if (do_multilevel) {
+        for (int f = 0; f < k; ++f) {
+          double g = reduce<T>(ctx, vp + f, p, kp, 2, v_mu[f]);
+          g += beta_0 * (v_mu[f] - mu_0) * (v_mu[f] - mu_0) + gamma_0;
+          const double la = alpha_0 + (double)p + 1;
+          const double nl = do_sample ? hs.gamma(la / 2.0, 2.0 / g) : la / g;
+          if (!hbad(nl)) v_lambda[f] = nl;
+        }
+        for (int f = 0; f < k; ++f) {
+          double mm;
+          if (s->compat & FMWR_COMPAT_MCMC_VMU_IDX) {
+            // F7: the reference sums v(f, attr_group[i]) == v(f, 0), p times (:462)
+            T v0;
+            FMWR_CUDA(cudaMemcpyAsync(&v0, vp + f, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+            FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+            mm = 0.0;
+            for (int64_t i = 0; i < p; ++i) mm += (double)v0;
+          } else mm = reduce<T>(ctx, vp + f, p, kp, 0, 0.0);
+          mm = (mm + beta_0 * mu_0) / ((double)p + beta_0);
+          const double var = 1.0 / (((double)p + beta_0) * v_lambda[f]);
+          const double nm = do_sample ? hs.normal(mm, std::sqrt(var)) : mm;
+          if (!hbad(nm)) v_mu[f] = nm;
+        }
+      } else { for (int f = 0; f < k; ++f) v_mu[f] = mu_0; }
+      for (int f = 0; f < k; ++f) {
+        CoordArgs<T> a;
+        memset(&a, 0, sizeof a);
+        a.colptr = d->colptr.p; a.crow = d->crow.p; a.cval = d->cval.p;
+        a.e = e.p; a.q = q.p; a.kp = kp; a.f = f; a.theta = vp + f; a.theta_stride = kp;
+        a.alpha = alpha; a.lambda = v_lambda[f]; a.mu = v_mu[f]; a.do_sample = do_sample; a.w_sd_is_var = 0;
+        a.normals = injected ? normals_dev.p : nullptr; a.n_normals = s->n_normals; a.normal_base = hs.i_normal; a.seed = s->seed;
+        run_phases<T>(ctx, ph, a);
+        if (do_sample) hs.i_normal += p;
+      }
+    }
+  }
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (tr) { tr->n_rec = n_rec; tr->convergent = 0; tr->iters_done = sweep; }
+}
+
+void train_als_mcmc(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
+{
+  if (m->prec == FMWR_F64) train_als_t<double>(ctx, m, d, s, tr);
+  else train_als_t<float>(ctx, m, d, s, tr);
+}
+
+}  // namespace fmwr

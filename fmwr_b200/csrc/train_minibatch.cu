@@ -53,7 +53,7 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
 // ---- K2: one lane group per (batch, feature) segment --------------------------------------------
 template <class T>
 struct MbUpdArgs {
-  const uint32_t* seg_ptr; const uint32_t* seg_col; const uint32_t* ent_row; const float* ent_val;
+  const uint32_t* seg_ptr; const uint4* seg_rec; const uint32_t* ent_row; const float* ent_val;
   uint32_t seg_begin, seg_end;
   int64_t row_begin; int rows;          // rows of this batch that take part (row filter for a truncated last batch)
   const T* mult; const T* Scache;
@@ -113,54 +113,81 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
   const int g = lane / LPR, l = lane % LPR;
   const uint32_t seg = a.seg_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
   if (seg >= a.seg_end) return;
-  const uint32_t c = a.seg_col[seg];
-  const uint32_t eb = a.seg_ptr[seg], ee = a.seg_ptr[seg + 1];
+  // one 16-byte record: {feature, length, first row, first value}; everything below depends only on it, so the
+  // parameter row, its optimizer state and the first row's cache line are all requested in the same round trip
+  const uint4 rec = __ldg(a.seg_rec + seg);
+  const uint32_t c = rec.x, len = rec.y;
+  const int r0 = (int)((int64_t)rec.z - a.row_begin);
+  if (r0 >= a.rows) return;                       // rows ascend inside a segment: nothing of it is in the (truncated) batch
   const int kp = a.kp;
 
   V16* vr = reinterpret_cast<V16*>(a.v + (size_t)c * kp);
-  T th[CH][VN], Gv[CH][VN];
+  V16 raw_th[CH], raw_s0[CH], raw_st[4][CH];
+  constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+  const bool use_state = SOLVER != FMWR_SGD || sp.l1;
+  const V16* s0r = reinterpret_cast<const V16*>(a.Scache + (size_t)r0 * kp);
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
-    vec_to_arr(vr[ch * LPR + l], th[ch]);
+    raw_th[ch] = vr[ch * LPR + l];
+    raw_s0[ch] = s0r[ch * LPR + l];
+    if (use_state) {
 #pragma unroll
-    for (int i = 0; i < VN; ++i) Gv[ch][i] = T(0);
-  }
-  T Gw = T(0);
-  int touched = 0;
-  for (uint32_t i = eb; i < ee; ++i) {
-    const int r = (int)((int64_t)a.ent_row[i] - a.row_begin);
-    if (r >= a.rows) break;                       // rows ascend inside a segment: the rest is filtered too
-    const T x = T(a.ent_val[i]);
-    const T mr = a.mult[r];
-    const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)r * kp);
-    touched = 1;
-    Gw += mr * x;
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) {
-      T s[VN];
-      vec_to_arr(sr[ch * LPR + l], s);
-#pragma unroll
-      for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] += mr * fm_grad(s[k2], th[ch][k2], x);
+      for (int st = 0; st < NST; ++st) raw_st[st][ch] = reinterpret_cast<const V16*>(a.sv[st] + (size_t)c * kp)[ch * LPR + l];
     }
   }
-  if (!touched) return;
+  const T m0 = a.mult[r0];
+  T tw = T(0), stw[4] = {T(0), T(0), T(0), T(0)};
+  if (a.k1 && l == 0) {
+    tw = a.w[c];
+    if (use_state) {
+#pragma unroll
+      for (int st = 0; st < NST; ++st) stw[st] = a.sw[st][c];
+    }
+  }
+
+  T th[CH][VN], Gv[CH][VN];
+  const T x0 = T(__uint_as_float(rec.w));
+  T Gw = m0 * x0;
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    T s[VN];
+    vec_to_arr(raw_th[ch], th[ch]);
+    vec_to_arr(raw_s0[ch], s);
+#pragma unroll
+    for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = m0 * fm_grad(s[k2], th[ch][k2], x0);
+  }
+  if (len > 1) {
+    const uint32_t eb = a.seg_ptr[seg];
+    for (uint32_t i = eb + 1; i < eb + len; ++i) {
+      const int r = (int)((int64_t)a.ent_row[i] - a.row_begin);
+      if (r >= a.rows) break;
+      const T x = T(a.ent_val[i]);
+      const T mr = a.mult[r];
+      const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)r * kp);
+      Gw += mr * x;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        T s[VN];
+        vec_to_arr(sr[ch * LPR + l], s);
+#pragma unroll
+        for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] += mr * fm_grad(s[k2], th[ch][k2], x);
+      }
+    }
+  }
 
   // ---- linear weight (lane 0 of the group)
   if (a.k1 && l == 0) {
-    T tw = a.w[c];
     if (SOLVER == FMWR_SGD) {
-      T q = sp.l1 ? a.sw[0][c] : T(0);
+      T q = stw[0];
       tw = sgd_step(tw, Gw, sp.lr, sp.reg_w, sp.l1, a.u_w, q);
       if (sp.l1) a.sw[0][c] = q;
     } else if (SOLVER == FMWR_FTRL) {
-      T z = a.sw[0][c], nn = a.sw[1][c];
-      tw = ftrl_step(tw, Gw, z, nn, sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
-      a.sw[0][c] = z; a.sw[1][c] = nn;
+      tw = ftrl_step(tw, Gw, stw[0], stw[1], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
+      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1];
     } else {
-      T u = a.sw[0][c], nu = a.sw[1][c], dl = a.sw[2][c], h = a.sw[3][c];
-      const T z = tdap_state(tw, Gw, u, nu, dl, h, sp.alpha_w, sp.egamma);
-      a.sw[0][c] = u; a.sw[1][c] = nu; a.sw[2][c] = dl; a.sw[3][c] = h;
-      tw = tdap_refresh(z, dl, sp.l1_w, sp.l2_w);
+      const T z = tdap_state(tw, Gw, stw[0], stw[1], stw[2], stw[3], sp.alpha_w, sp.egamma);
+      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1]; a.sw[2][c] = stw[2]; a.sw[3][c] = stw[3];
+      tw = tdap_refresh(z, stw[2], sp.l1_w, sp.l2_w);
     }
     a.w[c] = tw;
   }
@@ -170,36 +197,33 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
     const int vi = ch * LPR + l;
     if (SOLVER == FMWR_SGD) {
       T q[VN];
-      V16* qr = sp.l1 ? reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp) : nullptr;
-      if (sp.l1) vec_to_arr(qr[vi], q);
+      if (sp.l1) vec_to_arr(raw_st[0][ch], q);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         T qq = sp.l1 ? q[i] : T(0);
         th[ch][i] = sgd_step(th[ch][i], Gv[ch][i], sp.lr, sp.reg_v, sp.l1, a.u_v, qq);
         if (sp.l1) q[i] = qq;
       }
-      if (sp.l1) qr[vi] = arr_to_vec(q);
+      if (sp.l1) reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(q);
     } else if (SOLVER == FMWR_FTRL) {
-      V16* zr = reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp);
-      V16* nr = reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp);
       T z[VN], nn[VN];
-      vec_to_arr(zr[vi], z); vec_to_arr(nr[vi], nn);
+      vec_to_arr(raw_st[0][ch], z); vec_to_arr(raw_st[1][ch], nn);
 #pragma unroll
       for (int i = 0; i < VN; ++i) th[ch][i] = ftrl_step(th[ch][i], Gv[ch][i], z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
-      zr[vi] = arr_to_vec(z); nr[vi] = arr_to_vec(nn);
+      reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(z);
+      reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp)[vi] = arr_to_vec(nn);
     } else {
-      V16* ur = reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp);
-      V16* nur = reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp);
-      V16* dr = reinterpret_cast<V16*>(a.sv[2] + (size_t)c * kp);
-      V16* hr = reinterpret_cast<V16*>(a.sv[3] + (size_t)c * kp);
       T u[VN], nu[VN], dl[VN], h[VN];
-      vec_to_arr(ur[vi], u); vec_to_arr(nur[vi], nu); vec_to_arr(dr[vi], dl); vec_to_arr(hr[vi], h);
+      vec_to_arr(raw_st[0][ch], u); vec_to_arr(raw_st[1][ch], nu); vec_to_arr(raw_st[2][ch], dl); vec_to_arr(raw_st[3][ch], h);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         const T z = tdap_state(th[ch][i], Gv[ch][i], u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
         th[ch][i] = tdap_refresh(z, dl[i], sp.l1_v, sp.l2_v);
       }
-      ur[vi] = arr_to_vec(u); nur[vi] = arr_to_vec(nu); dr[vi] = arr_to_vec(dl); hr[vi] = arr_to_vec(h);
+      reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(u);
+      reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp)[vi] = arr_to_vec(nu);
+      reinterpret_cast<V16*>(a.sv[2] + (size_t)c * kp)[vi] = arr_to_vec(dl);
+      reinterpret_cast<V16*>(a.sv[3] + (size_t)c * kp)[vi] = arr_to_vec(h);
     }
     vr[vi] = arr_to_vec(th[ch]);
   }
@@ -267,7 +291,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = mult.p; L.Scache = Scache.p;
   MbUpdArgs<T>& ua = L.ua;
   memset(&ua, 0, sizeof ua);
-  ua.seg_ptr = d->mb_seg_ptr.p; ua.seg_col = d->mb_seg_col.p; ua.ent_row = d->mb_ent_row.p; ua.ent_val = d->mb_ent_val.p;
+  ua.seg_ptr = d->mb_seg_ptr.p; ua.seg_rec = d->mb_seg_rec.p; ua.ent_row = d->mb_ent_row.p; ua.ent_val = d->mb_ent_val.p;
   ua.mult = mult.p; ua.Scache = Scache.p;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }

@@ -376,7 +376,113 @@ def run_reference(args):
 
 
 def run_engine_multi(args, rank, world, local):
-    raise SystemExit("multi-GPU bench path is implemented in bench_multi (see run_engine_multi)")
+    """N > 1 (torchrun, one rank per GPU): FTRL minibatch epoch FEATURE-parallel with one NCCL all-reduce per batch;
+    predict.FM row-sharded with no collective.  Strong scaling: the configs[1] problem is fixed, N grows."""
+    import torch
+    import torch.distributed as dist
+    from fmwr_b200 import _lib as L
+    from fmwr_b200 import multi
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # control plane only (id exchange, barriers, max-reduce)
+    lib = L.lib()
+    ctx = L.Context(local)
+    ctx.comm_init(multi.exchange_unique_id(dist, L.Context, rank), rank, world)
+    peak, peak_src = measured_peak()
+    n, F, k, B = args.rows, 39, args.k, args.batch
+    field = args.features // F
+    p = field * F
+    f0, f1, c0, c1 = multi.field_partition([field] * F, world)[rank]
+
+    full = L.Data.synth(ctx, n, [field] * F, None, 0, 1, 0.1, 20240601)
+    data = full.slice_columns(c0, c1)
+    full.close()
+    mcfg = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+    model = L.Model(ctx, mcfg, c1 - c0, L.F32)
+    model.init_random(0.0, 0.01, 20240603 + c0)
+    epoch = n - 1
+    sc = L.SolverCfg(solver=L.FTRL, max_iter=epoch, random_step=1, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0, min_target=-1.0,
+                     max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F32, compat=L.COMPAT_REFERENCE, step_size=-1)
+
+    def timed(fn, steps):
+        ctx.sync(); dist.barrier()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop_ms()
+        ctx.sync(); dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # device time, max over ranks
+        return float(t[0])
+
+    for _ in range(args.warmup):
+        L.train_dev(ctx, model, data, sc)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launches()
+    ms_train = timed(lambda: L.train_dev(ctx, model, data, sc), args.steps)
+    l1 = ctx.launches()
+    train_sps = epoch * args.steps / (ms_train * 1e-3)
+    # per-kernel events on rank 0's stream (second pass)
+    buf = C.create_string_buffer(1 << 16)
+    L.check(lib.fmwr_profile_enable(ctx.h, 1))
+    L.train_dev(ctx, model, data, sc)
+    L.check(lib.fmwr_profile_enable(ctx.h, 1))
+    ms_prof = timed(lambda: L.train_dev(ctx, model, data, sc), args.steps)
+    L.check(lib.fmwr_profile_read(ctx.h, buf, C.c_int64(len(buf))))
+    prof = parse_profile(buf.value.decode())
+    L.check(lib.fmwr_profile_enable(ctx.h, 0))
+    data.close(); model.close()
+
+    # predict.FM: rows sharded, full model replicated
+    r0, r1 = multi.row_partition(n, world)[rank]
+    pdata = L.Data.synth_rows(ctx, r0, r1 - r0, [field] * F, None, 0, 0, 0.1, 20240601)
+    pmodel = L.Model(ctx, mcfg, p, L.F32)
+    pmodel.init_random(0.0, 0.01, 20240603)
+    for _ in range(args.warmup):
+        L.predict_dev(ctx, pmodel, pdata, L.LINK_LOGISTIC)
+    ms_pred = timed(lambda: L.predict_dev(ctx, pmodel, pdata, L.LINK_LOGISTIC), args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    pred_rps = n * args.steps / (ms_pred * 1e-3)
+    pdata.close(); pmodel.close()
+
+    if rank == 0:
+        b_fwd, b_ftrl = ALG_BYTES["predict"](F, k), ALG_BYTES["ftrl"](F, k)
+        roof = None
+        if "mb_update_kernel" in prof and prof["mb_update_kernel"][1] > 0:
+            launches, ms = prof["mb_update_kernel"]
+            share = (f1 - f0) / F                                      # rank 0's share of every sample's coordinates
+            ach = epoch * args.steps * (b_ftrl - b_fwd) * share / (ms * 1e-3) / 1e9
+            roof = {"kernel": "mb_update_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "launches": launches, "avg_launch_ms": round(ms / launches, 5),
+                    "note": "rank 0 only: %d of %d fields" % (f1 - f0, F), "share_of_step": round(ms / ms_prof, 4)}
+        out = {
+            "metric": "samples/sec per epoch (fm.train FTRL.solver, L1+L2, minibatch throughput mode); predict rows/sec in `predict`",
+            "value": round(train_sps, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_train / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: Criteo-shaped %d rows x %d nnz, %d features, k=%d, FTRL L1+L2 binary logloss" % (n, F, p, k),
+                       "rows": n, "nnz_per_row": F, "features": p, "k": k, "batch_size": B, "mode": "minibatch",
+                       "parallelism": "feature-parallel x%d (fields split %s), one NCCL all-reduce of rows x (k+4) f32 per minibatch; predict row-sharded" % (
+                           world, [b - a for a, b, _, _ in multi.field_partition([field] * F, world)]),
+                       "l2_flush": "inputs larger than L2"},
+            "roofline": roof,
+            "step_roofline": {"alg_bytes_per_sample": b_ftrl, "achieved": round(train_sps * b_ftrl / 1e9, 1), "unit": "GB/s",
+                              "frac_of_n_gpus_peak": round(train_sps * b_ftrl / 1e9 / (peak * world), 4)},
+            "kernels": {name: {"launches": v[0], "ms": round(v[1], 3)} for name, v in prof.items()},
+            "predict": {"value": round(pred_rps, 1), "unit": "rows/s", "ms_per_step": round(ms_pred / args.steps, 3),
+                        "roofline": {"bound": "hbm", "achieved": round(pred_rps * b_fwd / 1e9, 1), "unit": "GB/s",
+                                     "frac_of_n_gpus_peak": round(pred_rps * b_fwd / 1e9 / (peak * world), 4)}},
+            "cpu_baseline": None,
+            "e2e": None,
+            "gpu_launches": int(l1 - l0),
+            "clocks": clk,
+        }
+        print(json.dumps(out), flush=True)
+    ctx.comm_destroy()
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

@@ -127,6 +127,20 @@ class Context:
     def flush_l2(self):
         check(lib().fmwr_flush_l2(self.h))
 
+    # -- multi-GPU communicator (NCCL) ----------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().fmwr_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, id128, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        check(lib().fmwr_comm_init(self.h, buf, C.c_int32(rank), C.c_int32(world)))
+
+    def comm_destroy(self):
+        check(lib().fmwr_comm_destroy(self.h))
+
     def link_table(self, which, x):
         x = np.ascontiguousarray(x, np.float64)
         out = np.zeros_like(x)
@@ -172,6 +186,20 @@ class Data:
         check(lib().fmwr_data_synth(ctx.h, C.c_int64(n), C.c_int32(fs.size), ptr(fs), ptr(sk), C.c_int32(value_mode),
                                     C.c_int32(label_mode), C.c_double(noise), C.c_uint64(seed), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def synth_rows(cls, ctx, row_begin, n_rows, field_size, skew=None, value_mode=0, label_mode=0, noise=0.1, seed=20240601):
+        fs = np.ascontiguousarray(field_size, np.int64)
+        sk = np.ascontiguousarray(skew if skew is not None else np.zeros(fs.size), np.int32)
+        h = C.c_void_p()
+        check(lib().fmwr_data_synth_rows(ctx.h, C.c_int64(row_begin), C.c_int64(n_rows), C.c_int32(fs.size), ptr(fs), ptr(sk),
+                                         C.c_int32(value_mode), C.c_int32(label_mode), C.c_double(noise), C.c_uint64(seed), C.byref(h)))
+        return cls(ctx, h)
+
+    def slice_columns(self, c0, c1):
+        h = C.c_void_p()
+        check(lib().fmwr_data_slice_columns(self.h, C.c_int64(c0), C.c_int64(c1), C.byref(h)))
+        return Data(self.ctx, h)
 
     def close(self):
         if self.h:

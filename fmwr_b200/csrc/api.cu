@@ -455,7 +455,26 @@ int fmwr_data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* f
   return guarded([&] {
     FMWR_REQUIRE(ctx && out && field_size, FMWR_ERR_ARG, "null argument");
     FMWR_CUDA(cudaSetDevice(ctx->device));
-    data_synth(ctx, n, n_fields, field_size, skew, value_mode, label_mode, noise, seed, out);
+    data_synth(ctx, n, 0, n_fields, field_size, skew, value_mode, label_mode, noise, seed, out);
+  });
+}
+
+int fmwr_data_synth_rows(fmwr_ctx* ctx, int64_t row_begin, int64_t n_rows, int32_t n_fields, const int64_t* field_size,
+                         const int32_t* skew, int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx && out && field_size && row_begin >= 0, FMWR_ERR_ARG, "bad argument");
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    data_synth(ctx, n_rows, row_begin, n_fields, field_size, skew, value_mode, label_mode, noise, seed, out);
+  });
+}
+
+int fmwr_data_slice_columns(fmwr_data* d, int64_t col_begin, int64_t col_end, fmwr_data** out)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(d && out, FMWR_ERR_ARG, "null argument");
+    FMWR_CUDA(cudaSetDevice(d->ctx->device));
+    *out = data_slice_columns(d, col_begin, col_end);
   });
 }
 

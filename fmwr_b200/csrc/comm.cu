@@ -1,0 +1,107 @@
+// NCCL plumbing for the feature-parallel minibatch path.  libnccl is resolved at run time
+// (dlopen) so the single-GPU library has no link-time dependency on it; in a torchrun process the copy torch
+// already loaded is reused.
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <mutex>
+
+namespace fmwr {
+
+typedef struct { char internal[128]; } NcclUniqueId;
+typedef int (*fn_get_unique_id)(NcclUniqueId*);
+typedef int (*fn_comm_init_rank)(void**, int, NcclUniqueId, int);
+typedef int (*fn_comm_destroy)(void*);
+typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*fn_error_string)(int);
+
+static struct {
+  void* handle = nullptr;
+  fn_get_unique_id get_unique_id = nullptr;
+  fn_comm_init_rank comm_init_rank = nullptr;
+  fn_comm_destroy comm_destroy = nullptr;
+  fn_all_reduce all_reduce = nullptr;
+  fn_error_string error_string = nullptr;
+} g_nccl;
+
+static void load_nccl()
+{
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (g_nccl.handle) return;
+  const char* names[] = {getenv("FMWR_NCCL_LIB"), "libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; i < 4 && !g_nccl.handle; ++i) {
+    if (!names[i]) continue;
+    g_nccl.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  }
+  FMWR_REQUIRE(g_nccl.handle, FMWR_ERR_COMM, "cannot load libnccl.so.2 (set FMWR_NCCL_LIB)");
+  g_nccl.get_unique_id = (fn_get_unique_id)dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.comm_init_rank = (fn_comm_init_rank)dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.comm_destroy = (fn_comm_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.all_reduce = (fn_all_reduce)dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.error_string = (fn_error_string)dlsym(g_nccl.handle, "ncclGetErrorString");
+  FMWR_REQUIRE(g_nccl.get_unique_id && g_nccl.comm_init_rank && g_nccl.comm_destroy && g_nccl.all_reduce, FMWR_ERR_COMM,
+               "libnccl lacks an expected symbol");
+}
+
+static void nccl_check(int rc, const char* what)
+{
+  if (rc != 0) {
+    std::string msg = std::string("NCCL error in ") + what + ": " + (g_nccl.error_string ? g_nccl.error_string(rc) : "?");
+    throw Error(FMWR_ERR_COMM, msg);
+  }
+}
+
+void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64)
+{
+  FMWR_REQUIRE(ctx->nccl_comm, FMWR_ERR_COMM, "no communicator");
+  nccl_check(g_nccl.all_reduce(buf, buf, count, f64 ? 8 /*ncclFloat64*/ : 7 /*ncclFloat32*/, 0 /*ncclSum*/, ctx->nccl_comm, ctx->stream),
+             "ncclAllReduce");
+  ctx->launches++;
+}
+
+}  // namespace fmwr
+
+using namespace fmwr;
+
+extern "C" {
+
+int fmwr_comm_unique_id(uint8_t* id128)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(id128, FMWR_ERR_ARG, "null argument");
+    load_nccl();
+    NcclUniqueId id;
+    nccl_check(g_nccl.get_unique_id(&id), "ncclGetUniqueId");
+    memcpy(id128, id.internal, 128);
+  });
+}
+
+int fmwr_comm_init(fmwr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx && id128 && world >= 1 && rank >= 0 && rank < world, FMWR_ERR_ARG, "bad argument");
+    FMWR_REQUIRE(!ctx->nccl_comm, FMWR_ERR_ARG, "communicator already initialised");
+    load_nccl();
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    NcclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    void* comm = nullptr;
+    nccl_check(g_nccl.comm_init_rank(&comm, world, id, rank), "ncclCommInitRank");
+    ctx->nccl_comm = comm; ctx->rank = rank; ctx->world = world;
+  });
+}
+
+int fmwr_comm_destroy(fmwr_ctx* ctx)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx, FMWR_ERR_ARG, "null ctx");
+    if (ctx->nccl_comm) {
+      cudaStreamSynchronize(ctx->stream);
+      g_nccl.comm_destroy(ctx->nccl_comm);
+      ctx->nccl_comm = nullptr; ctx->rank = 0; ctx->world = 1;
+    }
+  });
+}
+
+}  // extern "C"

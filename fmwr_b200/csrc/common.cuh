@@ -121,6 +121,9 @@ struct fmwr_ctx {
   fmwr::DBuf<double> pn_table;   // fast_pnorm Y table   (2862 f64)
   fmwr::DBuf<double> dp_table;   // fast_dpnorm Y table  (40002 f64)
   fmwr::DBuf<char> flush_buf;    // L2 flush scratch
+  // feature-parallel communicator (NCCL, resolved at run time; null on a single GPU)
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
   fmwr::DBuf<double> red_scratch;  // reductions
   fmwr::HBuf<double> h_scalar;
 };
@@ -239,9 +242,10 @@ void model_set_host(fmwr_model* m, double w0, const double* w, const double* v);
 double model_get_w0(fmwr_model* m);
 void data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double* mean, double* sd);
 void data_normalize(fmwr_data* d, const double* mean, const double* sd);
-void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
+void data_synth(fmwr_ctx* ctx, int64_t n, int64_t row_begin, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
                 int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
 void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);
+fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1);
 void link_table_eval(fmwr_ctx* ctx, int which, int64_t n, const double* x, double* out);
 
 }  // namespace fmwr

@@ -557,15 +557,15 @@ struct SynthFields {
   int skew[64];
 };
 
-__global__ void synth_fill(int64_t n, int F, SynthFields f, int value_mode, uint64_t seed, uint32_t* __restrict__ rowptr,
-                           uint32_t* __restrict__ col, float* __restrict__ val)
+__global__ void synth_fill(int64_t n, int64_t row_begin, int F, SynthFields f, int value_mode, uint64_t seed,
+                           uint32_t* __restrict__ rowptr, uint32_t* __restrict__ col, float* __restrict__ val)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // entry index
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // local entry index
   if (i <= n) { if (i * F <= 0xffffffffll) rowptr[i] = (uint32_t)(i * F); }
   if (i >= n * F) return;
   const int64_t row = i / F;
   const int fld = (int)(i - row * F);
-  const uint64_t h = splitmix64(seed ^ (uint64_t)i);
+  const uint64_t h = splitmix64(seed ^ (uint64_t)((row_begin + row) * F + fld));   // keyed by the GLOBAL entry index
   col[i] = (uint32_t)(f.offset[fld] + synth_id(h, f.size[fld], f.skew[fld]));
   val[i] = synth_value(h, value_mode);
 }
@@ -590,21 +590,22 @@ __global__ void fill_normal(T* __restrict__ a, int64_t n, int k, int kp, double 
 }
 
 template <class T>
-__global__ void synth_labels(const T* __restrict__ score, int64_t n, int label_mode, double noise, uint64_t seed,
+__global__ void synth_labels(const T* __restrict__ score, int64_t n, int64_t row_begin, int label_mode, double noise, uint64_t seed,
                              float* __restrict__ y)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double s = (double)score[i];
+  const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n) return;
+  const double s = (double)score[li];
+  const int64_t i = row_begin + li;      // noise keyed by the global row
   if (label_mode == 1) {
     const double u = ((double)(splitmix64(seed ^ (uint64_t)i) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    y[i] = (u < 1.0 / (1.0 + exp(-s))) ? 1.0f : -1.0f;
+    y[li] = (u < 1.0 / (1.0 + exp(-s))) ? 1.0f : -1.0f;
   } else if (label_mode == 2) {
-    y[i] = (float)(s + noise * hash_normal(seed ^ (uint64_t)i));
+    y[li] = (float)(s + noise * hash_normal(seed ^ (uint64_t)i));
   } else {
     double t = 3.5 + s + noise * hash_normal(seed ^ (uint64_t)i);
     t = t < 0.5 ? 0.5 : (t > 5.0 ? 5.0 : t);
-    y[i] = (float)t;
+    y[li] = (float)t;
   }
 }
 
@@ -636,7 +637,7 @@ void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed)
   else FMWR_LAUNCH(ctx, fill_normal<float>, ceil_div(tot, 256), 256, 0, (float*)m->v.p, tot, m->k, m->kp, mean, sd, seed);
 }
 
-void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
+void data_synth(fmwr_ctx* ctx, int64_t n, int64_t row_begin, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
                 int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out)
 {
   FMWR_REQUIRE(n_fields > 0 && n_fields <= 64, FMWR_ERR_ARG, "n_fields must be in [1, 64]");
@@ -655,7 +656,7 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field
     d->ctx = ctx; d->n = n; d->p = p; d->nnz = nnz;
     d->rowptr.alloc(n + 1); d->col.alloc(nnz); d->val.alloc(nnz);
     const int64_t threads = std::max(nnz, n + 1);
-    FMWR_LAUNCH(ctx, synth_fill, ceil_div(threads, 256), 256, 0, n, n_fields, sf, value_mode, seed, d->rowptr.p, d->col.p, d->val.p);
+    FMWR_LAUNCH(ctx, synth_fill, ceil_div(threads, 256), 256, 0, n, row_begin, n_fields, sf, value_mode, seed, d->rowptr.p, d->col.p, d->val.p);
     if (label_mode != 0) {
       // planted FM (k* = 8, w*, V* ~ N(0, 0.1^2)) scored with the engine's own forward kernel
       fmwr_model_cfg mc; memset(&mc, 0, sizeof mc);
@@ -668,7 +669,7 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field
         FMWR_LAUNCH(ctx, fill_normal<float>, ceil_div(pw, 256), 256, 0, (float*)pm->w.p, pw, 1, 1, 0.0, 0.1, seed + 2);
         forward_launch(ctx, pm, d, FMWR_LINK_NONE, 0, 0);
         d->y.alloc(n); d->has_labels = true;
-        FMWR_LAUNCH(ctx, synth_labels<double>, ceil_div(n, 256), 256, 0, d->pred64.p, n, label_mode, noise, seed + 3, d->y.p);
+        FMWR_LAUNCH(ctx, synth_labels<double>, ceil_div(n, 256), 256, 0, d->pred64.p, n, row_begin, label_mode, noise, seed + 3, d->y.p);
         DBuf<float> mm; mm.alloc(2);
         const float init[2] = {INFINITY, -INFINITY};
         FMWR_CUDA(cudaMemcpyAsync(mm.p, init, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -683,6 +684,60 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field
     FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   } catch (...) { delete d; throw; }
   *out = d;
+}
+
+// ------------------------------------------------------------------------------------------ column slice
+// rows keep only the entries with column in [c0, c1); ids are rebased to c - c0 (feature-parallel sharding)
+__global__ void slice_count(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t n, uint32_t c0,
+                            uint32_t c1, uint32_t* __restrict__ cnt, uint32_t* __restrict__ first)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t b = rowptr[r], e = rowptr[r + 1];
+  uint32_t lo = b, hi = e;                        // first entry with col >= c0 (columns ascend inside a row)
+  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (col[m] < c0) lo = m + 1; else hi = m; }
+  const uint32_t f = lo;
+  hi = e;
+  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (col[m] < c1) lo = m + 1; else hi = m; }
+  first[r] = f;
+  cnt[r] = lo - f;
+}
+
+__global__ void slice_copy(const uint32_t* __restrict__ first, const uint32_t* __restrict__ new_rowptr, const uint32_t* __restrict__ col,
+                           const float* __restrict__ val, int64_t n, uint32_t c0, uint32_t* __restrict__ ocol, float* __restrict__ oval)
+{
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const uint32_t ob = new_rowptr[r], cnt = new_rowptr[r + 1] - ob, f = first[r];
+  for (uint32_t j = threadIdx.x & 31; j < cnt; j += 32) { ocol[ob + j] = col[f + j] - c0; oval[ob + j] = val[f + j]; }
+}
+
+fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1)
+{
+  fmwr_ctx* ctx = src->ctx;
+  FMWR_REQUIRE(0 <= c0 && c0 <= c1 && c1 <= src->p, FMWR_ERR_ARG, "column range out of bounds");
+  const int64_t n = src->n;
+  fmwr_data* d = new fmwr_data();
+  try {
+    d->ctx = ctx; d->n = n; d->p = c1 - c0;
+    d->rowptr.alloc(n + 1);
+    DBuf<uint32_t> cnt, first;
+    cnt.alloc(n + 1); first.alloc(n + 1);
+    FMWR_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * (n + 1), ctx->stream));
+    if (n > 0) FMWR_LAUNCH(ctx, slice_count, ceil_div(n, 256), 256, 0, src->rowptr.p, src->col.p, n, (uint32_t)c0, (uint32_t)c1, cnt.p, first.p);
+    exclusive_scan_u32(ctx, cnt.p, d->rowptr.p, n + 1);
+    uint32_t total = 0;
+    FMWR_CUDA(cudaMemcpy(&total, d->rowptr.p + n, 4, cudaMemcpyDeviceToHost));
+    d->nnz = total;
+    d->col.alloc(total); d->val.alloc(total);
+    if (n > 0 && total > 0) FMWR_LAUNCH(ctx, slice_copy, ceil_div(n * 32, 256), 256, 0, first.p, d->rowptr.p, src->col.p, src->val.p, n, (uint32_t)c0, d->col.p, d->val.p);
+    if (src->has_labels) {
+      d->y.alloc(n); d->has_labels = true; d->min_y = src->min_y; d->max_y = src->max_y;
+      FMWR_CUDA(cudaMemcpyAsync(d->y.p, src->y.p, 4 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) { delete d; throw; }
+  return d;
 }
 
 }  // namespace fmwr

@@ -23,9 +23,9 @@ struct RowAcc {
 // LPR: lanes per V row (power of two), CH: 16-byte chunks per lane, U: non-zeros in flight per group.
 // On return S[ch][i] holds the complete S_f for factor (ch*LPR + l)*VN + i in EVERY group.
 template <class T, int LPR, int CH, int U>
-__device__ __forceinline__ T row_forward(const uint32_t* __restrict__ col, const float* __restrict__ val,
-                                         uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
-                                         int kp, T w0, int k0, int k1, T (&S)[CH][Vec<T>::N])
+__device__ __forceinline__ void row_gather(const uint32_t* __restrict__ col, const float* __restrict__ val,
+                                           uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
+                                           int kp, int k1, T (&S)[CH][Vec<T>::N], T& lin_out, T& q_out)
 {
   typedef typename Vec<T>::type V16;
   constexpr int VN = Vec<T>::N;
@@ -93,15 +93,46 @@ __device__ __forceinline__ T row_forward(const uint32_t* __restrict__ col, const
         S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
         Q[ch][i] += __shfl_xor_sync(0xffffffffu, Q[ch][i], o);
       }
-  T r = lin;
+  // lin lives in lane 0 of every group; sum Q over this group's factors (identical in every group after the combine)
+  T qs = T(0);
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+    for (int i = 0; i < VN; ++i) qs += Q[ch][i];
+  lin_out = lin;
+  q_out = (g == 0) ? qs : T(0);
+}
+
+template <class T, int LPR, int CH, int U>
+__device__ __forceinline__ T row_forward(const uint32_t* __restrict__ col, const float* __restrict__ val,
+                                         uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
+                                         int kp, T w0, int k0, int k1, T (&S)[CH][Vec<T>::N])
+{
+  constexpr int VN = Vec<T>::N;
+  const int g = (threadIdx.x & 31) / LPR;
+  T lin, qs;
+  row_gather<T, LPR, CH, U>(col, val, b, e, w, v, kp, k1, S, lin, qs);
+  T r = lin - T(0.5) * qs;
   if (g == 0) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-      for (int i = 0; i < VN; ++i) r += T(0.5) * S[ch][i] * S[ch][i] - T(0.5) * Q[ch][i];
+      for (int i = 0; i < VN; ++i) r += T(0.5) * S[ch][i] * S[ch][i];
   }
   r = warp_sum(r);
   return (k0 ? w0 : T(0)) + r;
+}
+
+// column-slice variant: S_f of the slice plus the ADDITIVE part of the score (linear term - 1/2 sum Q);
+// 1/2 sum_f S_f^2 is formed after the partial S_f have been summed over the shards
+template <class T, int LPR, int CH, int U>
+__device__ __forceinline__ void row_forward_partial(const uint32_t* __restrict__ col, const float* __restrict__ val,
+                                                    uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
+                                                    int kp, int k1, T (&S)[CH][Vec<T>::N], T& addend)
+{
+  T lin, qs;
+  row_gather<T, LPR, CH, U>(col, val, b, e, w, v, kp, k1, S, lin, qs);
+  addend = warp_sum(lin - T(0.5) * qs);
 }
 
 // table-exact fast_pnorm (reference src/util/Random.h:95-111; Y table regenerated, see link_tables.cu)

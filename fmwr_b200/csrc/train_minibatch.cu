@@ -24,6 +24,7 @@ namespace fmwr {
 int solver_state_count(const SolverParams<double>& sp);
 double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s);
 void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
+void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
 template <class T, int LPR, int CH>
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256)
 mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                   const float* __restrict__ y, const T* __restrict__ w, const T* __restrict__ v,
                   const double* __restrict__ scal, int kp, int k0, int k1, int task, T lo, T hi,
-                  int64_t row_begin, int rows, T* __restrict__ mult, T* __restrict__ Scache)
+                  int64_t row_begin, int rows, T* __restrict__ mult, T* __restrict__ Scache, int s_stride, int partial)
 {
   typedef typename Vec<T>::type V16;
   constexpr int U = (LPR >= 16) ? 8 : 4;
@@ -41,12 +42,39 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
   const int64_t row = row_begin + r;
   const uint32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
   T S[CH][Vec<T>::N];
-  const T score = row_forward<T, LPR, CH, U>(col, val, b, e, w, v, kp, T(scal[0]), k0, k1, S);
-  if (lane == 0) mult[r] = grad_mult<T>(task, score, T(__ldg(y + row)), lo, hi);
+  if (!partial) {
+    const T score = row_forward<T, LPR, CH, U>(col, val, b, e, w, v, kp, T(scal[0]), k0, k1, S);
+    if (lane == 0) mult[r] = grad_mult<T>(task, score, T(__ldg(y + row)), lo, hi);
+  } else {
+    // feature-parallel: this rank holds a column slice, so the row's score is not known yet.  Emit the partials
+    // [S_f (kp), lin - 1/2 sum Q + 1/2 sum S_f^2 is NOT additive] -> store S_f and the additive scalar (lin - 1/2 sum Q)
+    T addend;
+    row_forward_partial<T, LPR, CH, U>(col, val, b, e, w, v, kp, k1, S, addend);
+    if (lane == 0) Scache[(size_t)r * s_stride + kp] = addend;
+  }
   if (lane < LPR) {
-    V16* dst = reinterpret_cast<V16*>(Scache + (size_t)r * kp);
+    V16* dst = reinterpret_cast<V16*>(Scache + (size_t)r * s_stride);
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + lane] = arr_to_vec(S[ch]);
+  }
+}
+
+// after the all-reduce: score = w0 + addend + 1/2 sum_f S_f^2 ; one warp per row
+template <class T>
+__global__ void __launch_bounds__(256)
+mb_finalize_kernel(const float* __restrict__ y, const double* __restrict__ scal, int kp, int k0, int task, T lo, T hi,
+                   int64_t row_begin, int rows, const T* __restrict__ Scache, int s_stride, T* __restrict__ mult)
+{
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const T* row = Scache + (size_t)r * s_stride;
+  T acc = T(0);
+  for (int f = lane; f < kp; f += 32) { const T s = row[f]; acc += T(0.5) * s * s; }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const T score = (k0 ? T(scal[0]) : T(0)) + row[kp] + acc;
+    mult[r] = grad_mult<T>(task, score, T(__ldg(y + row_begin + r)), lo, hi);
   }
 }
 
@@ -59,7 +87,7 @@ struct MbUpdArgs {
   const T* mult; const T* Scache;
   T* w; T* v; double* scal;
   T* sw[4]; T* sv[4];
-  int kp, k0, k1;
+  int kp, k0, k1, s_stride;
   SolverParams<T> sp;
   T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
 };
@@ -125,7 +153,7 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
   V16 raw_th[CH], raw_s0[CH], raw_st[4][CH];
   constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
   const bool use_state = SOLVER != FMWR_SGD || sp.l1;
-  const V16* s0r = reinterpret_cast<const V16*>(a.Scache + (size_t)r0 * kp);
+  const V16* s0r = reinterpret_cast<const V16*>(a.Scache + (size_t)r0 * a.s_stride);
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
     raw_th[ch] = vr[ch * LPR + l];
@@ -163,7 +191,7 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       if (r >= a.rows) break;
       const T x = T(a.ent_val[i]);
       const T mr = a.mult[r];
-      const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)r * kp);
+      const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)r * a.s_stride);
       Gw += mr * x;
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
@@ -233,13 +261,14 @@ template <class T>
 struct MbLaunch {
   fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; const fmwr_solver_cfg* s;
   int64_t row_begin; int rows; T* mult; T* Scache; MbUpdArgs<T> ua; int phase;   // phase 0: K1, 1: K2
+  int s_stride; int partial;
   template <class TT, int LPR, int CH>
   void run()
   {
     if (phase == 0) {
       FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH>), ceil_div(rows, 8), 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
                   (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
-                  m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache);
+                  m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial);
     } else {
       constexpr int G = 32 / LPR;
       const uint32_t nseg = ua.seg_end - ua.seg_begin;
@@ -283,19 +312,24 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   minibatch_build(d, row0, B);
   const int64_t n_batches = ceil_div64(epoch_rows, B);
 
+  // single GPU: S cache rows are kp wide.  Feature-parallel: kp + 4 (S_f, the additive scalar, padding to keep 16-byte rows)
+  const bool multi = ctx->nccl_comm != nullptr && ctx->world > 1;
+  FMWR_REQUIRE(!(multi && s->step_size > 0), FMWR_ERR_UNSUPPORTED, "the tracker is not available on a feature-sharded model (score the gathered model instead)");
+  const int s_stride = multi ? m->kp + 4 : m->kp;
   DBuf<T> mult, Scache;
   mult.alloc(B);
-  Scache.alloc((size_t)B * m->kp);
+  Scache.alloc((size_t)B * s_stride);
+  if (multi) FMWR_CUDA(cudaMemsetAsync(Scache.p, 0, Scache.bytes(), ctx->stream));
 
   MbLaunch<T> L;
-  L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = mult.p; L.Scache = Scache.p;
+  L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = mult.p; L.Scache = Scache.p; L.s_stride = s_stride; L.partial = multi ? 1 : 0;
   MbUpdArgs<T>& ua = L.ua;
   memset(&ua, 0, sizeof ua);
   ua.seg_ptr = d->mb_seg_ptr.p; ua.seg_rec = d->mb_seg_rec.p; ua.ent_row = d->mb_ent_row.p; ua.ent_val = d->mb_ent_val.p;
   ua.mult = mult.p; ua.Scache = Scache.p;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
-  ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1;
+  ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1; ua.s_stride = s_stride;
   ua.sp = params_from<T>(spd);
 
   const int64_t max_iter = s->max_iter;
@@ -311,6 +345,12 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
       L.row_begin = rb; L.rows = (int)rows;
       L.phase = 0;
       dispatch_layout<T>(m->kp, L);
+      if (multi) {
+        // one exchange per minibatch: sum the per-row partials over the feature shards (NCCL over NVLink / NVSwitch)
+        comm_allreduce_sum(ctx, Scache.p, (size_t)rows * s_stride, sizeof(T) == 8);
+        FMWR_LAUNCH(ctx, mb_finalize_kernel<T>, ceil_div(rows, 8), 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
+                    m->cfg.task, T(s->min_target), T(s->max_target), rb, (int)rows, Scache.p, s_stride, mult.p);
+      }
       if (spd.solver == FMWR_SGD && spd.l1) { u_w += (double)rows * spd.lr * spd.reg_w; u_v += (double)rows * spd.lr * spd.reg_v; }
       ua.seg_begin = (uint32_t)d->mb_batch_seg[b]; ua.seg_end = (uint32_t)d->mb_batch_seg[b + 1];
       ua.row_begin = rb; ua.rows = (int)rows; ua.u_w = T(u_w); ua.u_v = T(u_v);

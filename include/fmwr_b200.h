@@ -151,6 +151,21 @@ int fmwr_data_normalize(fmwr_data* d, const double* mean /*[p]*/, const double* 
 int fmwr_data_synth(fmwr_ctx* ctx, int64_t n, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
                     int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
 
+/* rows [row_begin, row_begin + n_rows) of the same synthetic matrix (row-sharded predict on several GPUs) */
+int fmwr_data_synth_rows(fmwr_ctx* ctx, int64_t row_begin, int64_t n_rows, int32_t n_fields, const int64_t* field_size,
+                         const int32_t* skew, int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
+/* column slice [col_begin, col_end) of a dataset, ids rebased to 0 (feature-parallel sharding; labels are shared) */
+int fmwr_data_slice_columns(fmwr_data* d, int64_t col_begin, int64_t col_end, fmwr_data** out);
+
+/* ---- multi-GPU (one process per GPU): feature-parallel minibatch training, SURVEY section 8e ----
+ * Rank 0 calls fmwr_comm_unique_id and ships the 128 bytes to the other ranks with whatever the host has
+ * (bench.py: torch.distributed); every rank then calls fmwr_comm_init.  Afterwards fmwr_train_dev in
+ * minibatch mode treats the data handle as this rank's COLUMN SLICE of the matrix (all rows, own features)
+ * and all-reduces the per-row partials (S_f, linear term, sum Q) of every batch with NCCL over NVLink. */
+int fmwr_comm_unique_id(uint8_t* id128);
+int fmwr_comm_init(fmwr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
+int fmwr_comm_destroy(fmwr_ctx* ctx);
+
 /* ---- model ---- */
 int fmwr_model_create(fmwr_ctx* ctx, const fmwr_model_cfg* cfg, int64_t p, int32_t precision, fmwr_model** out);
 int fmwr_model_destroy(fmwr_model* m);

@@ -3,13 +3,79 @@
 // (reference src/FM.cpp:7, :177, :218).
 #include "forward.cuh"
 
+#include <chrono>
 #include <cmath>
+#include <map>
 #include <mutex>
 
 namespace fmwr {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+// ---- caching device allocator -------------------------------------------------------------------------------
+static std::mutex g_mem_mu;
+static std::map<std::pair<int, size_t>, std::vector<void*>> g_mem_cache;   // (device, rounded bytes) -> free blocks
+
+static size_t round_bytes(size_t b)
+{
+  const size_t g = b >= (8u << 20) ? (2u << 20) : 512u;      // 2 MiB granules for big blocks, 512 B for small ones
+  return (b + g - 1) / g * g;
+}
+
+void dev_trim()
+{
+  std::lock_guard<std::mutex> lk(g_mem_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_mem_cache) {
+    if (kv.second.empty()) continue;
+    cudaSetDevice(kv.first.first);
+    for (void* p : kv.second) cudaFree(p);
+    kv.second.clear();
+  }
+  cudaSetDevice(cur);
+}
+
+void* dev_alloc(size_t bytes)
+{
+  const size_t rb = round_bytes(bytes);
+  int dev = 0;
+  FMWR_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    auto it = g_mem_cache.find({dev, rb});
+    if (it != g_mem_cache.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, rb);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    dev_trim();
+    e = cudaMalloc(&p, rb);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char b[160];
+    snprintf(b, sizeof b, "CUDA error %s allocating %zu bytes", cudaGetErrorString(e), rb);
+    throw Error(e == cudaErrorMemoryAllocation ? FMWR_ERR_NOMEM : FMWR_ERR_CUDA, b);
+  }
+  return p;
+}
+
+void dev_free(void* p, size_t bytes)
+{
+  if (!p) return;
+  int dev = 0;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) dev = attr.device; else { cudaGetLastError(); cudaGetDevice(&dev); }
+  std::lock_guard<std::mutex> lk(g_mem_mu);
+  g_mem_cache[{dev, round_bytes(bytes)}].push_back(p);
+}
 
 cudaEvent_t prof_begin(fmwr_ctx* ctx, const char* tag)
 {
@@ -343,6 +409,11 @@ int fmwr_profile_read(fmwr_ctx* ctx, char* buf, int64_t buf_len)
   });
 }
 
+int fmwr_mem_trim(void)
+{
+  return guarded([&] { dev_trim(); });
+}
+
 int fmwr_host_pin(void* ptr, int64_t bytes)
 {
   return guarded([&] { FMWR_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault)); });
@@ -587,6 +658,20 @@ static fmwr_ctx* default_ctx()
   return ctx;
 }
 
+// FMWR_TRACE=1: wall-clock of the phases of the one-shot entry points (stderr)
+struct PhaseTimer {
+  bool on; std::chrono::steady_clock::time_point t;
+  PhaseTimer() : on(getenv("FMWR_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* what)
+  {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[fmwr trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 struct DataGuard { fmwr_data* d = nullptr; ~DataGuard() { if (d) fmwr_data_destroy(d); } };
 struct ModelGuard { fmwr_model* m = nullptr; ~ModelGuard() { if (m) fmwr_model_destroy(m); } };
 
@@ -614,11 +699,20 @@ int fmwr_train(const fmwr_model_cfg* cfg, const fmwr_solver_cfg* s, int64_t n, i
     FMWR_REQUIRE(cfg && s && w0 && labels, FMWR_ERR_ARG, "null argument");
     fmwr_ctx* ctx = default_ctx();
     DataGuard dg; ModelGuard mg;
+    PhaseTimer pt;
     if (fmwr_data_create(ctx, n, p, nnz, row_size, col_idx, value, labels, &dg.d)) throw Error(FMWR_ERR_ARG, g_last_error);
+    pt.lap("data_create (H2D + narrow)");
     if (fmwr_model_create(ctx, cfg, p, s->precision, &mg.m)) throw Error(FMWR_ERR_ARG, g_last_error);
     model_set_host(mg.m, *w0, w, v);
+    pt.lap("model create + set");
+    if (s->mode == FMWR_MODE_MINIBATCH && s->solver >= FMWR_SGD) {
+      minibatch_build(dg.d, (s->compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0, s->batch_size);
+      pt.lap("per-batch CSC build");
+    }
     train_dispatch(ctx, mg.m, dg.d, s, trace);
+    pt.lap("train");
     model_get_host(mg.m, w0, w, v);
+    pt.lap("model get (D2H)");
   });
 }
 

@@ -56,6 +56,14 @@ static inline int guarded(F&& f) noexcept
 }
 
 // ---- device buffer ----------------------------------------------------------------------------
+// Device memory comes from a per-device caching allocator (api.cu): cudaMalloc / cudaFree of multi-GB blocks cost
+// tens of ms each and would dominate the one-shot entry points (fmwr_train, fmwr_predict), which build and drop
+// several such blocks per call.  Freed blocks are reused by later requests of the same rounded size; fmwr_mem_trim()
+// (also run automatically when cudaMalloc fails) returns them to the driver.
+void* dev_alloc(size_t bytes);
+void dev_free(void* p, size_t bytes);
+void dev_trim();
+
 template <class T>
 struct DBuf {
   T* p = nullptr;
@@ -66,7 +74,7 @@ struct DBuf {
   ~DBuf() { release(); }
   void release()
   {
-    if (p) cudaFree(p);
+    if (p) dev_free(p, n * sizeof(T));
     p = nullptr;
     n = 0;
   }
@@ -75,7 +83,7 @@ struct DBuf {
     if (count == n && p) return;
     release();
     if (count == 0) count = 1;
-    FMWR_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    p = (T*)dev_alloc(count * sizeof(T));
     n = count;
   }
   void ensure(size_t count) { if (count > n) alloc(count); }

@@ -337,8 +337,27 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   int64_t iter = 0, next_track = 0;
   int n_rec = 0, conv_times = 0, convergent = 0;
   double old_score = 0.0, u_w = 0.0, u_v = 0.0;
+  // The per-batch launches are recorded into CUDA graphs (chunks of GRAPH_CHUNK batches) and replayed by the device,
+  // so the epoch does not depend on host launch latency / host jitter.  Per-kernel profiling, the tracker and the
+  // NCCL path use plain launches.
+  const bool use_graph = !ctx->profile && step <= 0 && !multi && getenv("FMWR_NO_GRAPH") == nullptr;
+  constexpr int GRAPH_CHUNK = 2048;
+  std::vector<cudaGraphExec_t> execs;
+  std::vector<cudaGraph_t> graphs;
+  int captured = 0;
+  auto flush_graph = [&]() {
+    if (!use_graph || captured == 0) return;
+    cudaGraph_t g = nullptr;
+    FMWR_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    FMWR_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    graphs.push_back(g); execs.push_back(ge);
+    FMWR_CUDA(cudaGraphLaunch(ge, ctx->stream));
+    captured = 0;
+  };
   while (iter < max_iter && !convergent) {
     for (int64_t b = 0; b < n_batches && iter < max_iter; ++b) {
+      if (use_graph && captured == 0) FMWR_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
       const int64_t rb = row0 + b * B;
       int64_t rows = std::min<int64_t>(B, d->n - rb);
       rows = std::min<int64_t>(rows, max_iter - iter);
@@ -357,6 +376,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
       L.phase = 1;
       dispatch_layout<T>(m->kp, L);
       iter += rows;
+      if (use_graph && ++captured >= GRAPH_CHUNK) flush_graph();
       if (step > 0 && (iter > next_track || iter >= max_iter)) {
         // tracker at batch granularity: one record per step_size samples crossed (and at the end)
         const double score = tracker_score(ctx, m, d, s);
@@ -370,7 +390,10 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
       }
     }
   }
+  flush_graph();
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto ge : execs) cudaGraphExecDestroy(ge);
+  for (auto g : graphs) cudaGraphDestroy(g);
   if (tr) { tr->n_rec = n_rec; tr->convergent = convergent; tr->iters_done = (int)iter; }
 }
 

@@ -124,6 +124,8 @@ int fmwr_profile_read(fmwr_ctx* ctx, char* buf, int64_t buf_len);
 /* page-lock / unlock a caller buffer so the one-shot entry points copy at full PCIe speed */
 int fmwr_host_pin(void* ptr, int64_t bytes);
 int fmwr_host_unpin(void* ptr);
+/* return the library's cached (freed-but-retained) device blocks to the driver */
+int fmwr_mem_trim(void);
 
 /* ---- data: replaces SMatrix<float>::assign(List) + Data::add_data/add_target
  *      (reference src/util/Smatrix.h:44-61, src/FM.cpp:31-44, src/core/Data.h:48-86) ---- */

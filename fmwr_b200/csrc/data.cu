@@ -327,28 +327,31 @@ void phases_build(fmwr_data* d)
 }
 
 // ------------------------------------------------------------------------------------------ per-batch CSC
+template <class K>
 __global__ void mb_keys(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t row0, int64_t n,
-                        uint32_t batch, int colbits, uint64_t* __restrict__ keys, uint32_t* __restrict__ erow)
+                        uint32_t batch, int colbits, K* __restrict__ keys, uint32_t* __restrict__ erow)
 {
   const int64_t row = row0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (row >= n) return;
   const uint32_t b = rowptr[row], e = rowptr[row + 1], e0 = rowptr[row0];
   const uint64_t bid = (uint64_t)((row - row0) / batch);
   for (uint32_t j = b + (threadIdx.x & 31); j < e; j += 32) {
-    keys[j - e0] = (bid << colbits) | (uint64_t)col[j];
+    keys[j - e0] = (K)((bid << colbits) | (uint64_t)col[j]);
     erow[j - e0] = (uint32_t)row;
   }
 }
 
 // head[i] = 1 where a new (batch, col) segment starts
-__global__ void mb_heads(const uint64_t* __restrict__ keys, int64_t m, uint32_t* __restrict__ head)
+template <class K>
+__global__ void mb_heads(const K* __restrict__ keys, int64_t m, uint32_t* __restrict__ head)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
 }
 
-__global__ void mb_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ segid,
+template <class K>
+__global__ void mb_emit(const K* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ segid,
                         const uint32_t* __restrict__ perm, const uint32_t* __restrict__ erow, const float* __restrict__ val,
                         uint32_t e0, int64_t m, int colbits, uint32_t* __restrict__ seg_ptr, uint4* __restrict__ seg_rec,
                         uint32_t* __restrict__ ent_row, float* __restrict__ ent_val, uint32_t n_seg)
@@ -365,7 +368,7 @@ __global__ void mb_emit(const uint64_t* __restrict__ keys, const uint32_t* __res
     // the update kernel everything it needs for the common single-entry segment
     const uint32_t s = segid[i];
     seg_ptr[s] = (uint32_t)i;
-    seg_rec[s] = make_uint4((uint32_t)(keys[i] & ((1ull << colbits) - 1ull)), 0u, r, __float_as_uint(x));
+    seg_rec[s] = make_uint4((uint32_t)((uint64_t)keys[i] & ((1ull << colbits) - 1ull)), 0u, r, __float_as_uint(x));
   }
   if (i == m - 1) seg_ptr[n_seg] = (uint32_t)m;
 }
@@ -377,15 +380,16 @@ __global__ void mb_seg_len(const uint32_t* __restrict__ seg_ptr, uint4* __restri
 }
 
 // first segment of each batch: batch_seg[b] = #segments with batch id < b
-__global__ void mb_batch_bounds(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head,
+template <class K>
+__global__ void mb_batch_bounds(const K* __restrict__ keys, const uint32_t* __restrict__ head,
                                 const uint32_t* __restrict__ segid, int64_t m, int colbits, int64_t n_batches,
                                 uint32_t n_seg, uint32_t* __restrict__ batch_seg)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   if (!head[i]) return;
-  const uint64_t bid = keys[i] >> colbits;
-  const uint64_t pb = (i == 0) ? (uint64_t)-1 : (keys[i - 1] >> colbits);
+  const uint64_t bid = (uint64_t)keys[i] >> colbits;
+  const uint64_t pb = (i == 0) ? (uint64_t)-1 : ((uint64_t)keys[i - 1] >> colbits);
   if (i == 0 || pb != bid) {
     // batches (pb, bid] start at this segment (empty batches in between share the offset)
     const uint64_t from = (i == 0) ? 0 : pb + 1;
@@ -396,9 +400,9 @@ __global__ void mb_batch_bounds(const uint64_t* __restrict__ keys, const uint32_
 
 // Entries of rows [row0, n) regrouped by (batch, feature, row): the "sorted-key segmented
 // reduction" layout of the minibatch update kernels (one segment = one touched coordinate).
-void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
+template <class K>
+static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
 {
-  if (d->mb_batch == batch && d->mb_row0 == row0) return;
   fmwr_ctx* ctx = d->ctx;
   FMWR_REQUIRE(batch > 0, FMWR_ERR_ARG, "batch_size must be positive");
   const int64_t rows = d->n - row0;
@@ -418,10 +422,10 @@ void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
     d->mb_batch = batch; d->mb_row0 = row0;
     return;
   }
-  DBuf<uint64_t> keys_in, keys_out;
+  DBuf<K> keys_in, keys_out;
   DBuf<uint32_t> erow, idx_in, idx_out, head, segid;
   keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); idx_in.alloc(m); idx_out.alloc(m); head.alloc(m); segid.alloc(m);
-  FMWR_LAUNCH(ctx, mb_keys, ceil_div(rows * 32, 256), 256, 0, d->rowptr.p, d->col.p, row0, d->n, (uint32_t)batch, colbits,
+  FMWR_LAUNCH(ctx, mb_keys<K>, ceil_div(rows * 32, 256), 256, 0, d->rowptr.p, d->col.p, row0, d->n, (uint32_t)batch, colbits,
               keys_in.p, erow.p);
   FMWR_LAUNCH(ctx, iota_u32, ceil_div(m, 256), 256, 0, idx_in.p, m);
   size_t tmp_bytes = 0;
@@ -432,14 +436,14 @@ void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, idx_out.p, (int)m, 0,
                                             colbits + batchbits, ctx->stream));
   ctx->launches += 1;
-  FMWR_LAUNCH(ctx, mb_heads, ceil_div(m, 256), 256, 0, keys_out.p, m, head.p);
+  FMWR_LAUNCH(ctx, mb_heads<K>, ceil_div(m, 256), 256, 0, keys_out.p, m, head.p);
   exclusive_scan_u32(ctx, head.p, segid.p, m);
   uint32_t last_id = 0, last_head = 0;
   FMWR_CUDA(cudaMemcpy(&last_id, segid.p + (m - 1), 4, cudaMemcpyDeviceToHost));
   FMWR_CUDA(cudaMemcpy(&last_head, head.p + (m - 1), 4, cudaMemcpyDeviceToHost));
   const uint32_t n_seg = last_id + last_head;
   d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_rec.alloc(n_seg);
-  FMWR_LAUNCH(ctx, mb_emit, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, idx_out.p, erow.p, d->val.p, e0, m,
+  FMWR_LAUNCH(ctx, mb_emit<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, idx_out.p, erow.p, d->val.p, e0, m,
               colbits, d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
   FMWR_LAUNCH(ctx, mb_seg_len, ceil_div(n_seg, 256), 256, 0, d->mb_seg_ptr.p, d->mb_seg_rec.p, n_seg);
   DBuf<uint32_t> bseg;
@@ -447,7 +451,7 @@ void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
   // default every batch offset to n_seg (covers trailing empty batches), then fill real starts
   std::vector<uint32_t> fill(n_batches + 1, n_seg);
   FMWR_CUDA(cudaMemcpyAsync(bseg.p, fill.data(), 4 * (n_batches + 1), cudaMemcpyHostToDevice, ctx->stream));
-  FMWR_LAUNCH(ctx, mb_batch_bounds, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, m, colbits, n_batches, n_seg,
+  FMWR_LAUNCH(ctx, mb_batch_bounds<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, m, colbits, n_batches, n_seg,
               bseg.p);
   std::vector<uint32_t> hb(n_batches + 1);
   FMWR_CUDA(cudaMemcpyAsync(hb.data(), bseg.p, 4 * (n_batches + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -457,6 +461,17 @@ void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
   d->mb_batch_seg[n_batches] = n_seg;
   for (int64_t b = n_batches - 1; b >= 0; --b) if (d->mb_batch_seg[b] > d->mb_batch_seg[b + 1]) d->mb_batch_seg[b] = d->mb_batch_seg[b + 1];
   d->mb_batch = batch; d->mb_row0 = row0;
+}
+
+void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
+{
+  if (d->mb_batch == batch && d->mb_row0 == row0) return;
+  FMWR_REQUIRE(batch > 0, FMWR_ERR_ARG, "batch_size must be positive");
+  const int64_t rows = d->n - row0;
+  const int64_t n_batches = rows > 0 ? ceil_div64(rows, batch) : 0;
+  const int bits = bits_for((uint64_t)(d->p > 0 ? d->p - 1 : 0)) + bits_for((uint64_t)(n_batches > 0 ? n_batches - 1 : 0));
+  if (bits <= 32) minibatch_build_t<uint32_t>(d, row0, batch);     // (batch, feature) fits one word: half the sort traffic
+  else minibatch_build_t<uint64_t>(d, row0, batch);
 }
 
 // ------------------------------------------------------------------------------------------ scales / normalize

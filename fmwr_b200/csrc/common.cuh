@@ -238,6 +238,8 @@ int padded_k(int k, int prec);
 void build_link_tables(fmwr_ctx* ctx);
 void forward_launch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, int link, double lo, double hi);
 void transpose_build(fmwr_data* d);
+void launch_iota(fmwr_ctx* ctx, uint32_t* a, int64_t n);
+void sort_pairs_u32(fmwr_ctx* ctx, const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in, uint32_t* val_out, int64_t n, int bits);
 void phases_build(fmwr_data* d);
 void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch);
 void train_exact(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);

@@ -286,6 +286,24 @@ void transpose_build(fmwr_data* d)
   d->has_csc = true;
 }
 
+void launch_iota(fmwr_ctx* ctx, uint32_t* a, int64_t n)
+{
+  if (n > 0) FMWR_LAUNCH(ctx, iota_u32, ceil_div(n, 256), 256, 0, a, n);
+}
+
+// stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key
+void sort_pairs_u32(fmwr_ctx* ctx, const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in, uint32_t* val_out, int64_t n, int bits)
+{
+  if (n <= 0) return;
+  size_t tmp_bytes = 0;
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, val_in, val_out, (int)n, 0, bits, ctx->stream));
+  DBuf<char> tmp;
+  tmp.alloc(tmp_bytes);
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in, key_out, val_in, val_out, (int)n, 0, bits, ctx->stream));
+  ctx->launches += 1;
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 // ------------------------------------------------------------------------------------------ phases
 // prev[c] = max over rows containing c of the column that precedes c in that row (+1; 0 = none).
 __global__ void phase_prev(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t n,

@@ -15,6 +15,7 @@
 // alpha = 1, w0_mean_0 = 0), one attribute group (src/FM.cpp:75).
 #include "forward.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <random>
 
@@ -45,9 +46,11 @@ als_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restri
     const T score = row_forward<T, LPR, CH, U>(col, val, b, en, w, v, kp, w0, k0, k1, S);
     if (lane == 0) e[row] = score;
     if (q && lane < LPR) {
-      V16* dst = reinterpret_cast<V16*>(q + (size_t)row * kp);
+      // q is factor-major [kp][n]: the coordinate passes stream one factor's q over rows
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + lane] = arr_to_vec(S[ch]);
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int i = 0; i < Vec<T>::N; ++i) q[(size_t)((ch * LPR + lane) * Vec<T>::N + i) * n + row] = S[ch][i];
     }
   }
 }
@@ -214,7 +217,7 @@ struct CoordArgs {
   const uint32_t* colptr; const uint32_t* crow; const float* cval;
   uint32_t c_begin, c_end;           // the phase's feature range
   const uint32_t* long_cols; int n_long;
-  T* e; T* q; int kp; int f;         // q == nullptr for the w pass
+  T* e; T* q; int kp; int f; int64_t n;   // q == nullptr for the w pass; q is [kp][n]
   T* theta; int64_t theta_stride;    // w (stride 1) or V + f (stride kp)
   double alpha, lambda, mu;
   int do_sample; int w_sd_is_var;    // F7: w drawn with the variance as s.d.
@@ -245,7 +248,7 @@ __device__ __forceinline__ void coord_update(const CoordArgs<T>& a, uint32_t c, 
     for (uint32_t j = b + tid; j < en; j += part) {
       const float xf = a.cval[j];
       const uint32_t r = a.crow[j];
-      const double h = (double)xf * (double)a.q[(size_t)r * a.kp + a.f] - (double)(xf * xf) * old;
+      const double h = (double)xf * (double)a.q[(size_t)a.f * a.n + r] - (double)(xf * xf) * old;
       Bm += h * (double)a.e[r];
       A += h * h;
     }
@@ -277,7 +280,7 @@ __device__ __forceinline__ void coord_update(const CoordArgs<T>& a, uint32_t c, 
     for (uint32_t j = b + tid; j < en; j += part) {
       const float xf = a.cval[j];
       const uint32_t r = a.crow[j];
-      const size_t qi = (size_t)r * a.kp + a.f;
+      const size_t qi = (size_t)a.f * a.n + r;
       const double qv = (double)a.q[qi];
       const double h = (double)xf * qv - (double)(xf * xf) * old;
       a.q[qi] = T(qv - (double)xf * dlt);                               // :346
@@ -319,11 +322,278 @@ __global__ void __launch_bounds__(512) coord_block_kernel(CoordArgs<T> a)
   coord_update<T>(a, c, threadIdx.x, 512, block_sum);
 }
 
+
+// ---- row-major (streaming) coordinate passes ---------------------------------------------------------------
+// Inside a phase every row holds at most one of the phase's features, so the phase's non-zeros can be visited in ROW
+// order: e[r] and q[f][r] are then read and written as coalesced streams instead of 4-byte random gathers (which move a
+// 32-byte sector each).  Per (factor, phase):
+//   rm_extract   th[c]   <- current parameter of every feature of the phase (compact copy, L2-resident)
+//   rm_stats     A[c], B[c] <- sum h^2, sum h e   (w pass: sum x^2, sum (e x - w x^2)); warp-aggregated vector atomics,
+//                            shared-memory privatisation when the phase has few features
+//   rm_solve     new parameter per feature (ALS mean / MCMC draw, the reference's NaN/Inf guards), delta[c] = old - new
+//   rm_apply     e[r] -= h delta, q[f][r] -= x delta
+// The phase's non-zeros are stored once, grouped by phase in row order (build_row_major).
+struct RowMajor {
+  bool ok = false;
+  DBuf<uint32_t> row, col;      // [N] row id, feature id LOCAL to its phase
+  DBuf<float> val;              // [N]
+  std::vector<int64_t> ptr;     // [n_phases + 1] entry offsets
+  uint32_t max_cols = 0;
+  DBuf<uint32_t> hot_col;       // [n_phases][RM_HOT] phase-local feature id of each hot slot
+  DBuf<uint16_t> hot;           // [p] slot of a hot feature inside its phase's shared-memory table, 0xffff otherwise
+  std::vector<int> n_hot;       // [n_phases]
+};
+
+__global__ void rm_phase_keys(const uint32_t* __restrict__ col, int64_t nnz, const uint32_t* __restrict__ pbeg, int n_phases,
+                              uint32_t* __restrict__ key)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const uint32_t c = col[i];
+  int lo = 0, hi = n_phases;                       // last phase with begin <= c
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pbeg[mid] <= c) lo = mid; else hi = mid; }
+  key[i] = (uint32_t)lo;
+}
+
+__global__ void rm_emit(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key_sorted, const uint32_t* __restrict__ erow,
+                        const uint32_t* __restrict__ col, const float* __restrict__ val, const uint32_t* __restrict__ pbeg, int64_t nnz,
+                        uint32_t* __restrict__ orow, uint32_t* __restrict__ ocol, float* __restrict__ oval)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const uint32_t e = perm[i];
+  orow[i] = erow[e];
+  ocol[i] = col[e] - pbeg[key_sorted[i]];
+  oval[i] = val[e];
+}
+
+__global__ void rm_expand_rows(const uint32_t* __restrict__ rowptr, int64_t n, uint32_t* __restrict__ erow)
+{
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const uint32_t b = rowptr[row], e = rowptr[row + 1];
+  for (uint32_t j = b + (threadIdx.x & 31); j < e; j += 32) erow[j] = (uint32_t)row;
+}
+
+__global__ void rm_count_phase(const uint32_t* __restrict__ key_sorted, int64_t nnz, int n_phases, unsigned long long* __restrict__ first)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const uint32_t k = key_sorted[i];
+  if (i == 0 || key_sorted[i - 1] != k) first[k] = (unsigned long long)i;
+  (void)n_phases;
+}
+
+template <class T>
+struct RmArgs {
+  const uint32_t* row; const uint32_t* col; const float* val;
+  int64_t pb, pe;                    // entry range of the phase
+  uint32_t cb, ncols;                // first global feature / number of features of the phase
+  T* e; T* q; int64_t n; int f;      // q == nullptr: w pass.  q is [kp][n]
+  T* theta; int64_t theta_stride;    // w (stride 1) or V + f (stride kp)
+  const uint16_t* hot; const uint32_t* hot_col; int n_hot;   // hot-feature table of the phase (indexed by global feature id)
+  T* th; T* AB; T* delta;            // per-feature scratch of the phase: th[ncols], AB[2*ncols] interleaved, delta[ncols]
+  double alpha, lambda, mu;
+  int do_sample, w_sd_is_var;
+  const double* normals; long long n_normals, normal_base; uint64_t seed;
+};
+
+template <class T>
+__global__ void rm_extract_kernel(RmArgs<T> a)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncols) return;
+  a.th[c] = a.theta[(size_t)(a.cb + c) * a.theta_stride];
+  a.AB[2 * (size_t)c] = T(0); a.AB[2 * (size_t)c + 1] = T(0);
+}
+
+// A and B of a feature are interleaved (AB[2c], AB[2c+1]) so the fp32 path issues ONE 8-byte vector reduction per feature
+__device__ __forceinline__ void atomic_add2(float* AB, uint32_t c, float a, float b)
+{
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(AB + 2 * (size_t)c), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void atomic_add2(double* AB, uint32_t c, double a, double b) { atomicAdd(AB + 2 * (size_t)c, a); atomicAdd(AB + 2 * (size_t)c + 1, b); }
+
+constexpr int RM_SMEM_COLS = 2048;
+
+constexpr int RM_HOT = 1024;        // hot features per phase kept in a per-CTA shared-memory table
+constexpr int RM_HOT_MIN_LEN = 2048;  // a feature is hot when it has at least this many non-zeros
+
+// MODE 0: global vector atomics (warp-aggregated); 1: the whole phase fits the shared-memory table;
+// 2: hot features go to the shared-memory table, the rest to global atomics
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) rm_stats_kernel(RmArgs<T> a)
+{
+  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? RM_HOT : 1);
+  __shared__ T sA[SLOTS], sB[SLOTS];
+  const uint32_t n_slots = MODE == 1 ? a.ncols : (MODE == 2 ? (uint32_t)a.n_hot : 0u);
+  if (MODE != 0) {
+    for (uint32_t c = threadIdx.x; c < n_slots; c += blockDim.x) { sA[c] = T(0); sB[c] = T(0); }
+    __syncthreads();
+  }
+  const T* qf = a.q ? a.q + (size_t)a.f * a.n : nullptr;
+  for (int64_t i = a.pb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pe; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = a.row[i], c = a.col[i];
+    const float xf = a.val[i];
+    const T old = a.th[c];
+    const T er = a.e[r];
+    T sa, sb;
+    if (qf == nullptr) {                          // update_w statistics (reference :225-230)
+      const T x = T(xf);
+      sa = x * x;
+      sb = er * x - old * x * x;
+    } else {                                      // update_v statistics (reference :313-321)
+      const T h = T(xf) * qf[r] - T(xf * xf) * old;
+      sa = h * h;
+      sb = h * er;
+    }
+    if (MODE == 1) { atomicAdd(&sA[c], sa); atomicAdd(&sB[c], sb); continue; }
+    if (MODE == 2) {
+      const uint32_t slot = a.hot[a.cb + c];
+      if (slot != 0xffffu) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); continue; }
+    }
+    atomic_add2(a.AB, c, sa, sb);
+  }
+  if (MODE != 0) {
+    __syncthreads();
+    for (uint32_t sl = threadIdx.x; sl < n_slots; sl += blockDim.x)
+      if (sA[sl] != T(0) || sB[sl] != T(0)) {
+        const uint32_t c = MODE == 1 ? sl : a.hot_col[sl];
+        atomic_add2(a.AB, c, sA[sl], sB[sl]);
+      }
+  }
+}
+
+template <class T>
+__global__ void rm_solve_kernel(RmArgs<T> a)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncols) return;
+  const double old = (double)a.th[c];
+  const double A = (double)a.AB[2 * (size_t)c];
+  double Bm = (double)a.AB[2 * (size_t)c + 1];
+  if (a.q != nullptr) Bm -= old * A;                                    // reference :322
+  const double var = 1.0 / (a.lambda + a.alpha * A);
+  const double mean = -var * (a.alpha * Bm - a.mu * a.lambda);
+  double nv;
+  bool upd = true;
+  if (isnan(var) || isinf(var)) nv = 0.0;
+  else if (a.do_sample) {
+    const long long di = a.normal_base + (long long)(a.cb + c);
+    const double z = a.normals ? (di < a.n_normals ? a.normals[di] : 0.0) : hash_norm(a.seed ^ (uint64_t)di * 0x9E3779B97F4A7C15ull);
+    const double sd = (a.q == nullptr && a.w_sd_is_var) ? var : sqrt(var);
+    nv = mean + sd * z;
+  } else nv = mean;
+  if (isnan(nv) || isinf(nv)) { nv = old; upd = false; }
+  a.theta[(size_t)(a.cb + c) * a.theta_stride] = T(nv);
+  a.delta[c] = upd ? T(old - nv) : T(0);
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) rm_apply_kernel(RmArgs<T> a)
+{
+  T* qf = a.q ? a.q + (size_t)a.f * a.n : nullptr;
+  for (int64_t i = a.pb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pe; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = a.row[i], c = a.col[i];
+    const T d = a.delta[c];
+    if (d == T(0)) continue;
+    const float xf = a.val[i];
+    if (qf == nullptr) {
+      a.e[r] -= T(xf) * d;                                              // reference :251-253
+    } else {
+      const T qv = qf[r];
+      const T h = T(xf) * qv - T(xf * xf) * a.th[c];
+      qf[r] = qv - T(xf) * d;                                           // :346
+      a.e[r] -= h * d;                                                  // :347
+    }
+  }
+}
+
+static void build_row_major(fmwr_data* d, const std::vector<uint32_t>& pbeg_host, const std::vector<uint32_t>& cp, RowMajor& rm)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int np = (int)pbeg_host.size() - 1;
+  const int64_t nnz = d->nnz, n = d->n;
+  rm.ptr.assign(np + 1, 0);
+  rm.max_cols = 0;
+  for (int i = 0; i < np; ++i) rm.max_cols = std::max(rm.max_cols, pbeg_host[i + 1] - pbeg_host[i]);
+  if (nnz == 0) { rm.ok = true; return; }
+  DBuf<uint32_t> pbeg, key_in, key_out, idx_in, idx_out, erow;
+  DBuf<unsigned long long> first;
+  pbeg.alloc(np + 1); key_in.alloc(nnz); key_out.alloc(nnz); idx_in.alloc(nnz); idx_out.alloc(nnz); erow.alloc(nnz); first.alloc(np + 1);
+  FMWR_CUDA(cudaMemcpyAsync(pbeg.p, pbeg_host.data(), 4 * (np + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_LAUNCH(ctx, rm_phase_keys, ceil_div(nnz, 256), 256, 0, d->col.p, nnz, pbeg.p, np, key_in.p);
+  FMWR_LAUNCH(ctx, rm_expand_rows, ceil_div(n * 32, 256), 256, 0, d->rowptr.p, n, erow.p);
+  FMWR_CUDA(cudaMemsetAsync(first.p, 0xff, 8 * (np + 1), ctx->stream));
+  // stable sort of entry ids by phase id: CSR order (== row order) survives inside each phase
+  launch_iota(ctx, idx_in.p, nnz);
+  int bits = 1;
+  while ((1 << bits) < np) ++bits;
+  sort_pairs_u32(ctx, key_in.p, key_out.p, idx_in.p, idx_out.p, nnz, bits);
+  rm.row.alloc(nnz); rm.col.alloc(nnz); rm.val.alloc(nnz);
+  FMWR_LAUNCH(ctx, rm_emit, ceil_div(nnz, 256), 256, 0, idx_out.p, key_out.p, erow.p, d->col.p, d->val.p, pbeg.p, nnz, rm.row.p, rm.col.p, rm.val.p);
+  FMWR_LAUNCH(ctx, rm_count_phase, ceil_div(nnz, 256), 256, 0, key_out.p, nnz, np, first.p);
+  std::vector<unsigned long long> hf(np + 1);
+  FMWR_CUDA(cudaMemcpyAsync(hf.data(), first.p, 8 * (np + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  rm.ptr[np] = nnz;
+  for (int i = np - 1; i >= 0; --i) rm.ptr[i] = (hf[i] == ~0ull) ? rm.ptr[i + 1] : (int64_t)hf[i];   // empty phase: zero-length range
+  // hot features: the RM_HOT longest columns of every phase with at least RM_HOT_MIN_LEN non-zeros
+  std::vector<uint16_t> hot(d->p > 0 ? d->p : 1, 0xffff);
+  std::vector<uint32_t> hot_col((size_t)np * RM_HOT, 0);
+  rm.n_hot.assign(np, 0);
+  for (int i = 0; i < np; ++i) {
+    std::vector<std::pair<uint32_t, uint32_t>> cand;     // (length, feature)
+    for (uint32_t c = pbeg_host[i]; c < pbeg_host[i + 1]; ++c) {
+      const uint32_t len = cp[c + 1] - cp[c];
+      if (len >= (uint32_t)RM_HOT_MIN_LEN) cand.push_back({len, c});
+    }
+    if ((int)cand.size() > RM_HOT) {
+      std::partial_sort(cand.begin(), cand.begin() + RM_HOT, cand.end(), [](const std::pair<uint32_t, uint32_t>& x, const std::pair<uint32_t, uint32_t>& y) { return x.first > y.first; });
+      cand.resize(RM_HOT);
+    }
+    rm.n_hot[i] = (int)cand.size();
+    for (size_t s2 = 0; s2 < cand.size(); ++s2) { hot[cand[s2].second] = (uint16_t)s2; hot_col[(size_t)i * RM_HOT + s2] = cand[s2].second - pbeg_host[i]; }
+  }
+  rm.hot.alloc(hot.size()); rm.hot_col.alloc(hot_col.size() ? hot_col.size() : 1);
+  FMWR_CUDA(cudaMemcpyAsync(rm.hot.p, hot.data(), 2 * hot.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!hot_col.empty()) FMWR_CUDA(cudaMemcpyAsync(rm.hot_col.p, hot_col.data(), 4 * hot_col.size(), cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  rm.ok = true;
+}
+
+template <class T>
+static void run_phases_rm(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, const RowMajor& rm, RmArgs<T> a)
+{
+  const int np = (int)pbeg.size() - 1;
+  const int grid_stream = ctx->sm_count * 8;
+  for (int i = 0; i < np; ++i) {
+    a.pb = rm.ptr[i]; a.pe = rm.ptr[i + 1];
+    a.cb = pbeg[i]; a.ncols = pbeg[i + 1] - pbeg[i];
+    if (a.ncols == 0) continue;
+    FMWR_LAUNCH(ctx, rm_extract_kernel<T>, ceil_div(a.ncols, 256), 256, 0, a);
+    if (a.pe > a.pb) {
+      const int grid = (int)std::min<int64_t>(grid_stream, ceil_div64(a.pe - a.pb, 256));
+      a.n_hot = rm.n_hot[i];
+      a.hot_col = rm.hot_col.p + (size_t)i * RM_HOT;
+      if (a.ncols <= RM_SMEM_COLS) FMWR_LAUNCH(ctx, (rm_stats_kernel<T, 1>), grid, 256, 0, a);
+      else if (a.n_hot > 0) FMWR_LAUNCH(ctx, (rm_stats_kernel<T, 2>), grid, 256, 0, a);
+      else FMWR_LAUNCH(ctx, (rm_stats_kernel<T, 0>), grid, 256, 0, a);
+    }
+    FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(a.ncols, 256), 256, 0, a);
+    if (a.pe > a.pb) {
+      const int grid = (int)std::min<int64_t>(grid_stream, ceil_div64(a.pe - a.pb, 256));
+      FMWR_LAUNCH(ctx, rm_apply_kernel<T>, grid, 256, 0, a);
+    }
+  }
+}
+
 // ---- driver ----------------------------------------------------------------------------------------------
 struct PhaseInfo {
   std::vector<uint32_t> begin;                 // [n_phases + 1]
   std::vector<std::vector<uint32_t>> long_cols;
   DBuf<uint32_t> long_dev;                     // concatenated
+  std::vector<uint32_t> colptr_host;
   std::vector<size_t> long_off;
 };
 
@@ -336,6 +606,7 @@ static void build_phase_info(fmwr_data* d, PhaseInfo& ph)
   std::vector<uint32_t> cp(d->p + 1);
   FMWR_CUDA(cudaMemcpyAsync(cp.data(), d->colptr.p, 4 * (d->p + 1), cudaMemcpyDeviceToHost, ctx->stream));
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ph.colptr_host = cp;
   std::vector<uint32_t> all;
   ph.long_off.assign(np + 1, 0);
   for (int i = 0; i < np; ++i) {
@@ -405,6 +676,28 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   transpose_build(d);                                                    // src/FM.cpp:148-152
   PhaseInfo ph;
   build_phase_info(d, ph);
+
+  // streaming (row-major) coordinate passes when the data decomposes into few phases (field-structured data);
+  // otherwise the column-parallel kernels
+  RowMajor rm;
+  const int n_phases = (int)ph.begin.size() - 1;
+  const bool use_rm = n_phases <= 256 && d->nnz > 0 && getenv("FMWR_ALS_COLUMN") == nullptr;
+  DBuf<T> rm_th, rm_AB, rm_delta;
+  if (use_rm) {
+    build_row_major(d, ph.begin, ph.colptr_host, rm);
+    rm_th.alloc(rm.max_cols); rm_AB.alloc(2 * (size_t)rm.max_cols); rm_delta.alloc(rm.max_cols);
+  }
+  auto rm_args = [&](T* e_p, T* q_p, int f, T* theta, int64_t stride, double alpha_, double lambda_, double mu_, int sample, int w_sd_var,
+                     const double* normals_p, long long n_normals_, long long base, uint64_t seed_) {
+    RmArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.row = rm.row.p; a.col = rm.col.p; a.val = rm.val.p; a.hot = rm.hot.p;
+    a.e = e_p; a.q = q_p; a.n = n; a.f = f; a.theta = theta; a.theta_stride = stride;
+    a.th = rm_th.p; a.AB = rm_AB.p; a.delta = rm_delta.p;
+    a.alpha = alpha_; a.lambda = lambda_; a.mu = mu_; a.do_sample = sample; a.w_sd_is_var = w_sd_var;
+    a.normals = normals_p; a.n_normals = n_normals_; a.normal_base = base; a.seed = seed_;
+    return a;
+  };
 
   DBuf<T> e, q;
   e.alloc(n);
@@ -498,11 +791,13 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
       CoordArgs<T> a;
       memset(&a, 0, sizeof a);
       a.colptr = d->colptr.p; a.crow = d->crow.p; a.cval = d->cval.p;
-      a.e = e.p; a.q = nullptr; a.kp = kp; a.f = 0; a.theta = wp; a.theta_stride = 1;
+      a.e = e.p; a.q = nullptr; a.kp = kp; a.f = 0; a.n = n; a.theta = wp; a.theta_stride = 1;
       a.alpha = alpha; a.lambda = w_lambda; a.mu = w_mu; a.do_sample = do_sample;
       a.w_sd_is_var = (s->compat & FMWR_COMPAT_MCMC_W_SD) ? 1 : 0;
       a.normals = injected ? normals_dev.p : nullptr; a.n_normals = s->n_normals; a.normal_base = hs.i_normal; a.seed = s->seed;
-      run_phases<T>(ctx, ph, a);
+      if (use_rm) run_phases_rm<T>(ctx, ph.begin, rm, rm_args(e.p, nullptr, 0, wp, 1, alpha, w_lambda, w_mu, do_sample, a.w_sd_is_var,
+                                                               a.normals, a.n_normals, a.normal_base, a.seed));
+      else run_phases<T>(ctx, ph, a);
       if (do_sample) hs.i_normal += p;
     }
     if (enable_v) {
@@ -535,10 +830,12 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
         CoordArgs<T> a;
         memset(&a, 0, sizeof a);
         a.colptr = d->colptr.p; a.crow = d->crow.p; a.cval = d->cval.p;
-        a.e = e.p; a.q = q.p; a.kp = kp; a.f = f; a.theta = vp + f; a.theta_stride = kp;
+        a.e = e.p; a.q = q.p; a.kp = kp; a.f = f; a.n = n; a.theta = vp + f; a.theta_stride = kp;
         a.alpha = alpha; a.lambda = v_lambda[f]; a.mu = v_mu[f]; a.do_sample = do_sample; a.w_sd_is_var = 0;
         a.normals = injected ? normals_dev.p : nullptr; a.n_normals = s->n_normals; a.normal_base = hs.i_normal; a.seed = s->seed;
-        run_phases<T>(ctx, ph, a);
+        if (use_rm) run_phases_rm<T>(ctx, ph.begin, rm, rm_args(e.p, q.p, f, vp + f, kp, alpha, v_lambda[f], v_mu[f], do_sample, 0,
+                                                                 a.normals, a.n_normals, a.normal_base, a.seed));
+        else run_phases<T>(ctx, ph, a);
         if (do_sample) hs.i_normal += p;
       }
     }

@@ -94,6 +94,16 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(kernel, units_per_launch):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic_r01.json), scaled to this run's launch size"""
+    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        t = json.load(open(path))[kernel]
+        return int(t["dram_bytes"] * units_per_launch / t["rows_per_launch"])
+    except Exception:
+        return None
+
+
 def parse_profile(txt):
     agg = {}
     for line in txt.strip().split("\n"):
@@ -196,7 +206,11 @@ def run_engine(args):
         units = epoch * args.steps                      # samples whose coordinates the launches updated
         ach = units * (b_ftrl - b_fwd) / (ms * 1e-3) / 1e9
         roof = {"kernel": kn, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "peak_source": peak_src, "launches": launches, "avg_launch_ms": round(ms / launches, 5),
+                "traffic": ncu_traffic(kn, min(B, n)) if (p, k) == (999999, 32) else None,
+                "alg_bytes_per_launch": int((b_ftrl - b_fwd) * units / launches),
+                "traffic_note": "ncu dram bytes per launch (profiles/r01_ncu_full.csv); below the algorithmic bytes because a batch "
+                                "touches each coordinate ~2.6x and updates it once, and V re-reads hit L2",
+                "peak_source": peak_src, "launches": launches, "avg_launch_ms": round(ms / launches, 5),
                 "alg_bytes_per_sample": b_ftrl - b_fwd,
                 "share_of_step": round(ms / ms_train_prof, 4), "ms_per_step_with_events": round(ms_train_prof / args.steps, 3)}
     fwd_roof = None
@@ -204,7 +218,8 @@ def run_engine(args):
         launches, ms = prof_pred["forward_kernel"]
         ach = n * args.steps * b_fwd / (ms * 1e-3) / 1e9
         fwd_roof = {"kernel": "forward_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "alg_bytes_per_row": b_fwd, "avg_launch_ms": round(ms / launches, 4)}
+                    "frac": round(ach / peak, 4), "traffic": ncu_traffic("forward_kernel", n) if (p, k) == (999999, 32) else None,
+                    "alg_bytes_per_row": b_fwd, "avg_launch_ms": round(ms / launches, 4)}
     k1 = prof_train.get("mb_forward_kernel")
     kernels = {name: {"launches": v[0], "ms": round(v[1], 3)} for name, v in prof_train.items()}
 

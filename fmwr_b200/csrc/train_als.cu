@@ -588,6 +588,216 @@ static void run_phases_rm(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, cons
   }
 }
 
+
+// ---- dense (field-structured) fused passes ------------------------------------------------------------------------
+// When every row holds exactly one non-zero of every phase (one-hot fields: user/item/context, Criteo's 39 fields) the
+// phase's entries are stored [phase][row] with the row implicit, and consecutive coordinate steps are FUSED per row:
+//   fused(t) = apply(step t-1) ; stats(step t)
+// e[r] (and q_f[r] when both steps belong to the same factor) is read once and written once per step instead of being
+// read by stats, then read and written again by apply: 32 instead of 48 bytes per row and step, all of it 128-bit
+// coalesced streams (4 rows per thread).
+template <class T>
+struct StepScratch { T* th; T* AB; T* delta; };
+
+template <class T>
+struct FusedArgs {
+  int64_t n;
+  T* e;
+  int has_prev; const uint32_t* pcol; const float* pval; const T* pth; const T* pdelta; T* pq;
+  int has_cur; const uint32_t* ccol; const float* cval; const T* cth; T* cAB; T* cq;
+  uint32_t c_cb, c_ncols; const uint16_t* hot; const uint32_t* hot_col; int n_hot;
+};
+
+template <class T, int MODE>
+__device__ __forceinline__ void stats_add(const FusedArgs<T>& a, T* sA, T* sB, uint32_t c, T sa, T sb)
+{
+  if (MODE == 1) { atomicAdd(&sA[c], sa); atomicAdd(&sB[c], sb); return; }
+  if (MODE == 2) {
+    const uint32_t slot = a.hot[a.c_cb + c];
+    if (slot != 0xffffu) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); return; }
+  }
+  atomic_add2(a.cAB, c, sa, sb);
+}
+
+template <class T, int MODE, int VEC>
+__global__ void __launch_bounds__(256) fused_kernel(FusedArgs<T> a)
+{
+  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? RM_HOT : 1);
+  __shared__ T sA[SLOTS], sB[SLOTS];
+  const uint32_t n_slots = !a.has_cur ? 0u : (MODE == 1 ? a.c_ncols : (MODE == 2 ? (uint32_t)a.n_hot : 0u));
+  if (MODE != 0) {
+    for (uint32_t c = threadIdx.x; c < n_slots; c += blockDim.x) { sA[c] = T(0); sB[c] = T(0); }
+    __syncthreads();
+  }
+  const bool same_q = a.has_prev && a.has_cur && a.pq != nullptr && a.pq == a.cq;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; base < a.n; base += (int64_t)gridDim.x * blockDim.x * VEC) {
+    T ev[VEC], qv[VEC];
+    uint32_t pc[VEC], cc[VEC];
+    float px[VEC], cx[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<typename Vec<T>::type*>(ev) = *reinterpret_cast<const typename Vec<T>::type*>(a.e + base);
+      if (sizeof(T) == 8) *reinterpret_cast<typename Vec<T>::type*>(ev + 2) = *reinterpret_cast<const typename Vec<T>::type*>(a.e + base + 2);
+      if (a.has_prev) { *reinterpret_cast<uint4*>(pc) = *reinterpret_cast<const uint4*>(a.pcol + base); *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(a.pval + base); }
+      if (a.has_cur) { *reinterpret_cast<uint4*>(cc) = *reinterpret_cast<const uint4*>(a.ccol + base); *reinterpret_cast<float4*>(cx) = *reinterpret_cast<const float4*>(a.cval + base); }
+    } else {
+      ev[0] = a.e[base];
+      if (a.has_prev) { pc[0] = a.pcol[base]; px[0] = a.pval[base]; }
+      if (a.has_cur) { cc[0] = a.ccol[base]; cx[0] = a.cval[base]; }
+    }
+    // ---- apply the previous step (reference :251-253 for w, :338-349 for V)
+    if (a.has_prev) {
+      if (a.pq != nullptr) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] = a.pq[base + u];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+          const T d = a.pdelta[pc[u]];
+          const T h = T(px[u]) * qv[u] - T(px[u] * px[u]) * a.pth[pc[u]];
+          qv[u] -= T(px[u]) * d;
+          ev[u] -= h * d;
+        }
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) a.pq[base + u] = qv[u];
+      } else {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) ev[u] -= T(px[u]) * a.pdelta[pc[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) a.e[base + u] = ev[u];
+    }
+    // ---- statistics of the current step (reference :225-230 for w, :313-321 for V)
+    if (a.has_cur) {
+      if (a.cq != nullptr && !same_q) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] = a.cq[base + u];
+      }
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        const T old = a.cth[cc[u]];
+        T sa, sb;
+        if (a.cq == nullptr) {
+          const T x = T(cx[u]);
+          sa = x * x;
+          sb = ev[u] * x - old * x * x;
+        } else {
+          const T h = T(cx[u]) * qv[u] - T(cx[u] * cx[u]) * old;
+          sa = h * h;
+          sb = h * ev[u];
+        }
+        stats_add<T, MODE>(a, sA, sB, cc[u], sa, sb);
+      }
+    }
+  }
+  if (MODE != 0) {
+    __syncthreads();
+    for (uint32_t sl = threadIdx.x; sl < n_slots; sl += blockDim.x)
+      if (sA[sl] != T(0) || sB[sl] != T(0)) atomic_add2(a.cAB, MODE == 1 ? sl : a.hot_col[sl], sA[sl], sB[sl]);
+  }
+}
+
+struct DenseLayout {
+  bool ok = false;
+  DBuf<uint32_t> col;    // [n_phases][n] phase-local feature id
+  DBuf<float> val;       // [n_phases][n]
+};
+
+__global__ void dense_check_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t n, int np,
+                                   const uint32_t* __restrict__ pbeg, int* __restrict__ bad)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (rowptr[r] != (uint32_t)(r * np) || rowptr[r + 1] != (uint32_t)((r + 1) * np)) { *bad = 1; return; }
+  for (int j = 0; j < np; ++j) {
+    const uint32_t c = col[r * np + j];
+    if (c < pbeg[j] || c >= pbeg[j + 1]) { *bad = 1; return; }
+  }
+}
+
+__global__ void dense_build_kernel(const uint32_t* __restrict__ col, const float* __restrict__ val, int64_t n, int np,
+                                   const uint32_t* __restrict__ pbeg, uint32_t* __restrict__ ocol, float* __restrict__ oval)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // output-major: t = j * n + r
+  if (t >= n * np) return;
+  const int64_t j = t / n, r = t - j * n;
+  ocol[t] = col[r * np + j] - pbeg[j];
+  oval[t] = val[r * np + j];
+}
+
+static void build_dense(fmwr_data* d, const std::vector<uint32_t>& pbeg_host, DenseLayout& dl)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int np = (int)pbeg_host.size() - 1;
+  const int64_t n = d->n;
+  dl.ok = false;
+  if (np <= 0 || n <= 0 || d->nnz != n * np) return;
+  DBuf<uint32_t> pbeg;
+  DBuf<int> bad;
+  pbeg.alloc(np + 1); bad.alloc(1);
+  bad.zero(ctx->stream);
+  FMWR_CUDA(cudaMemcpyAsync(pbeg.p, pbeg_host.data(), 4 * (np + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_LAUNCH(ctx, dense_check_kernel, ceil_div(n, 256), 256, 0, d->rowptr.p, d->col.p, n, np, pbeg.p, bad.p);
+  int hbad = 1;
+  FMWR_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (hbad) return;
+  dl.col.alloc((size_t)n * np); dl.val.alloc((size_t)n * np);
+  FMWR_LAUNCH(ctx, dense_build_kernel, ceil_div(n * np, 256), 256, 0, d->col.p, d->val.p, n, np, pbeg.p, dl.col.p, dl.val.p);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  dl.ok = true;
+}
+
+// one coordinate step of a fused sequence
+template <class T>
+struct Step { int phase; T* q; int f; T* theta; int64_t stride; double lambda, mu; int w_sd_is_var; long long normal_base; };
+
+template <class T>
+static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, const RowMajor& rm, const DenseLayout& dl, int64_t n,
+                            T* e, const std::vector<Step<T>>& steps, StepScratch<T> sc[2], double alpha, int do_sample,
+                            const double* normals, long long n_normals, uint64_t seed)
+{
+  const int vec = (n % 4 == 0) ? 4 : 1;
+  const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, ceil_div64(ceil_div64(n, vec), 256));
+  const int T_ = (int)steps.size();
+  for (int t = 0; t <= T_; ++t) {
+    FusedArgs<T> fa;
+    memset(&fa, 0, sizeof fa);
+    fa.n = n; fa.e = e;
+    RmArgs<T> ra;                      // extract / solve arguments of the current step
+    memset(&ra, 0, sizeof ra);
+    if (t > 0) {
+      const Step<T>& ps = steps[t - 1];
+      fa.has_prev = 1;
+      fa.pcol = dl.col.p + (size_t)ps.phase * n; fa.pval = dl.val.p + (size_t)ps.phase * n;
+      fa.pth = sc[(t - 1) & 1].th; fa.pdelta = sc[(t - 1) & 1].delta;
+      fa.pq = ps.q ? ps.q + (size_t)ps.f * n : nullptr;
+    }
+    if (t < T_) {
+      const Step<T>& cs = steps[t];
+      const uint32_t cb = pbeg[cs.phase], ncols = pbeg[cs.phase + 1] - cb;
+      ra.cb = cb; ra.ncols = ncols; ra.q = cs.q; ra.n = n; ra.f = cs.f; ra.theta = cs.theta; ra.theta_stride = cs.stride;
+      ra.th = sc[t & 1].th; ra.AB = sc[t & 1].AB; ra.delta = sc[t & 1].delta;
+      ra.alpha = alpha; ra.lambda = cs.lambda; ra.mu = cs.mu; ra.do_sample = do_sample; ra.w_sd_is_var = cs.w_sd_is_var;
+      ra.normals = normals; ra.n_normals = n_normals; ra.normal_base = cs.normal_base; ra.seed = seed;
+      FMWR_LAUNCH(ctx, rm_extract_kernel<T>, ceil_div(ncols, 256), 256, 0, ra);
+      fa.has_cur = 1;
+      fa.ccol = dl.col.p + (size_t)cs.phase * n; fa.cval = dl.val.p + (size_t)cs.phase * n;
+      fa.cth = ra.th; fa.cAB = ra.AB; fa.cq = cs.q ? cs.q + (size_t)cs.f * n : nullptr;
+      fa.c_cb = cb; fa.c_ncols = ncols; fa.hot = rm.hot.p; fa.hot_col = rm.hot_col.p + (size_t)cs.phase * RM_HOT; fa.n_hot = rm.n_hot[cs.phase];
+    }
+    const int mode = !fa.has_cur ? 0 : (fa.c_ncols <= (uint32_t)RM_SMEM_COLS ? 1 : (fa.n_hot > 0 ? 2 : 0));
+    if (vec == 4) {
+      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 4>), grid, 256, 0, fa);
+      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 4>), grid, 256, 0, fa);
+      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 4>), grid, 256, 0, fa);
+    } else {
+      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 1>), grid, 256, 0, fa);
+      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 1>), grid, 256, 0, fa);
+      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 1>), grid, 256, 0, fa);
+    }
+    if (t < T_) FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(ra.ncols, 256), 256, 0, ra);
+  }
+}
+
 // ---- driver ----------------------------------------------------------------------------------------------
 struct PhaseInfo {
   std::vector<uint32_t> begin;                 // [n_phases + 1]
@@ -682,11 +892,15 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   RowMajor rm;
   const int n_phases = (int)ph.begin.size() - 1;
   const bool use_rm = n_phases <= 256 && d->nnz > 0 && getenv("FMWR_ALS_COLUMN") == nullptr;
-  DBuf<T> rm_th, rm_AB, rm_delta;
+  DBuf<T> rm_th, rm_AB, rm_delta, rm_th2, rm_AB2, rm_delta2;
+  DenseLayout dl;
   if (use_rm) {
     build_row_major(d, ph.begin, ph.colptr_host, rm);
     rm_th.alloc(rm.max_cols); rm_AB.alloc(2 * (size_t)rm.max_cols); rm_delta.alloc(rm.max_cols);
+    if (getenv("FMWR_ALS_NO_DENSE") == nullptr) build_dense(d, ph.begin, dl);
+    if (dl.ok) { rm_th2.alloc(rm.max_cols); rm_AB2.alloc(2 * (size_t)rm.max_cols); rm_delta2.alloc(rm.max_cols); }
   }
+  StepScratch<T> scr[2] = {{rm_th.p, rm_AB.p, rm_delta.p}, {rm_th2.p, rm_AB2.p, rm_delta2.p}};
   auto rm_args = [&](T* e_p, T* q_p, int f, T* theta, int64_t stride, double alpha_, double lambda_, double mu_, int sample, int w_sd_var,
                      const double* normals_p, long long n_normals_, long long base, uint64_t seed_) {
     RmArgs<T> a;
@@ -795,7 +1009,11 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
       a.alpha = alpha; a.lambda = w_lambda; a.mu = w_mu; a.do_sample = do_sample;
       a.w_sd_is_var = (s->compat & FMWR_COMPAT_MCMC_W_SD) ? 1 : 0;
       a.normals = injected ? normals_dev.p : nullptr; a.n_normals = s->n_normals; a.normal_base = hs.i_normal; a.seed = s->seed;
-      if (use_rm) run_phases_rm<T>(ctx, ph.begin, rm, rm_args(e.p, nullptr, 0, wp, 1, alpha, w_lambda, w_mu, do_sample, a.w_sd_is_var,
+      if (use_rm && dl.ok) {
+        std::vector<Step<T>> steps;
+        for (int j = 0; j < n_phases; ++j) steps.push_back({j, nullptr, 0, wp, 1, w_lambda, w_mu, a.w_sd_is_var, a.normal_base});
+        run_steps_dense<T>(ctx, ph.begin, rm, dl, n, e.p, steps, scr, alpha, do_sample, a.normals, a.n_normals, a.seed);
+      } else if (use_rm) run_phases_rm<T>(ctx, ph.begin, rm, rm_args(e.p, nullptr, 0, wp, 1, alpha, w_lambda, w_mu, do_sample, a.w_sd_is_var,
                                                                a.normals, a.n_normals, a.normal_base, a.seed));
       else run_phases<T>(ctx, ph, a);
       if (do_sample) hs.i_normal += p;
@@ -826,6 +1044,14 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
           if (!hbad(nm)) v_mu[f] = nm;
         }
       } else { for (int f = 0; f < k; ++f) v_mu[f] = mu_0; }
+      if (use_rm && dl.ok) {
+        std::vector<Step<T>> steps;
+        for (int f = 0; f < k; ++f) {
+          for (int j = 0; j < n_phases; ++j) steps.push_back({j, q.p, f, vp + f, (int64_t)kp, v_lambda[f], v_mu[f], 0, hs.i_normal});
+          if (do_sample) hs.i_normal += p;
+        }
+        run_steps_dense<T>(ctx, ph.begin, rm, dl, n, e.p, steps, scr, alpha, do_sample, injected ? normals_dev.p : nullptr, s->n_normals, s->seed);
+      } else
       for (int f = 0; f < k; ++f) {
         CoordArgs<T> a;
         memset(&a, 0, sizeof a);

@@ -45,11 +45,20 @@ def fields_ds(n, fields, seed, value_mode=1):
 
 @pytest.mark.parametrize("task", [O.CLASSIFICATION, O.REGRESSION])
 @pytest.mark.parametrize("enable_v", [0, 1])
-@pytest.mark.parametrize("layout", ["fields", "ragged"])
+@pytest.mark.parametrize("layout", ["fields", "fields_odd", "fields_sparse", "ragged"])
 def test_als_matches_oracle(gpu_ctx, port, task, enable_v, layout):
     rng = np.random.default_rng(1)
     if layout == "fields":
-        ds = fields_ds(3000, [40, 25, 8], 5)            # 3 independent phases (fields)
+        ds = fields_ds(3000, [40, 25, 8], 5)            # 3 independent phases (fields): dense fused path, 4 rows per thread
+    elif layout == "fields_odd":
+        ds = fields_ds(3001, [40, 2500, 8], 6)          # row count not a multiple of 4 (scalar path), one phase beyond the smem table
+    elif layout == "fields_sparse":
+        # field-structured but some rows miss a field: phases stay few, rows are no longer implicit (row-major unfused path)
+        ds = fields_ds(2000, [30, 20, 10], 7)
+        keep = np.ones(ds["col"].size, bool)
+        keep[np.arange(0, ds["col"].size, 7)] = False
+        cnt = np.add.reduceat(keep.astype(np.int64), ds["rowptr"][:-1].astype(np.int64))
+        ds = dict(n=2000, p=ds["p"], rowptr=np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32), col=ds["col"][keep], val=ds["val"][keep])
     else:
         rowptr, col, val = synth.random_csr(600, 70, 6, seed=5, empty_rows=True)     # general CSR: many small phases
         ds = dict(n=600, p=70, rowptr=rowptr, col=col, val=val)
@@ -60,7 +69,11 @@ def test_als_matches_oracle(gpu_ctx, port, task, enable_v, layout):
     cfg = O.make_cfg(task=task, solver=O.ALS, k=k, max_iter=sweeps, enable_v=enable_v, l2_w0=0.1,
                      min_target=float(y.min()), max_target=float(y.max()), step_size=1, metric=O.LL if task == O.CLASSIFICATION else O.RMSE)
     rw0, rw, rv, rt = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v, max_rec=20)
-    for prec, tol in ((L.F64, 1e-8), (L.F32, 1e-4)):
+    # fields_odd has ~1.2 non-zeros per feature in its wide field: 1/(alpha*A) amplifies the summation-order noise
+    t64 = 1e-6 if layout == "fields_odd" else 1e-8
+    # (fp32 is not compared on fields_odd: with one non-zero per feature h = x q - x^2 v cancels to rounding noise and
+    # 1/(alpha * sum h^2) blows it up -- the fp64 instantiation is the parity instrument there)
+    for prec, tol in ((L.F64, t64),) + (((L.F32, 1e-4),) if layout != "fields_odd" else ()):
         (gw0, gw, gv), gt, _ = gpu_als(gpu_ctx, prec, ds, y, task, L.ALS, k, w0, w, v, sweeps, enable_v, l2_w0=0.1, step_size=1,
                                        metric=L.LL if task == O.CLASSIFICATION else L.RMSE)
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol, (prec, relerr(gw0, rw0), relerr(gw, rw), relerr(gv, rv))

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <memory>
 
 #include "../../include/fmwr_b200.h"
 
@@ -161,6 +162,8 @@ struct fmwr_data {
   fmwr::DBuf<uint32_t> mb_ent_row;   // [nnz'] global row index
   fmwr::DBuf<float> mb_ent_val;      // [nnz']
   std::vector<int64_t> mb_batch_seg;  // [n_batches+1] segment offsets per batch (host)
+  // ALS/MCMC layouts (phases, row-major / dense copies), built on first use, dropped when the values change
+  std::shared_ptr<void> als_cache;
   // last forward result
   int pred_prec = FMWR_F32;
   fmwr::DBuf<float> pred32;      // [n]

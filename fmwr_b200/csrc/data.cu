@@ -547,7 +547,7 @@ void data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double*
   FMWR_CUDA(cudaMemcpyAsync(q.p, sd, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
   if (d->nnz > 0) FMWR_LAUNCH(ctx, col_rescale, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->val.p, d->nnz, s.p, q.p, 0);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-  d->has_csc = false; d->mb_batch = 0;   // derived layouts hold stale values
+  d->has_csc = false; d->mb_batch = 0; d->als_cache.reset();   // derived layouts hold stale values
 }
 
 void data_normalize(fmwr_data* d, const double* mean, const double* sd)
@@ -560,7 +560,7 @@ void data_normalize(fmwr_data* d, const double* mean, const double* sd)
   FMWR_CUDA(cudaMemcpyAsync(q.p, sd, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
   if (d->nnz > 0) FMWR_LAUNCH(ctx, col_rescale, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->val.p, d->nnz, s.p, q.p, 1);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-  d->has_csc = false; d->mb_batch = 0;
+  d->has_csc = false; d->mb_batch = 0; d->als_cache.reset();
 }
 
 // ------------------------------------------------------------------------------------------ synthetic data

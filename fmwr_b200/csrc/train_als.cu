@@ -34,37 +34,56 @@ als_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restri
                    const T* __restrict__ w, const T* __restrict__ v, const double* __restrict__ scal, int kp, int k0, int k1,
                    int64_t n, T* __restrict__ e, T* __restrict__ q)
 {
-  typedef typename Vec<T>::type V16;
   constexpr int U = (LPR >= 16) ? 8 : 4;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  constexpr int VN = Vec<T>::N;
+  constexpr int KP = LPR * CH * VN;
+  constexpr bool STAGE = (size_t)KP * 33 * sizeof(T) <= 40 * 1024;     // q is factor-major [kp][n]: stage 32 rows in shared
+  __shared__ T sS[STAGE ? 32 : 1][STAGE ? KP + 1 : 1];                // memory so every factor gets one coalesced 32-row store
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const T w0 = T(scal[0]);
-  for (int64_t row = warp0; row < n; row += nwarps) {
-    const uint32_t b = __ldg(rowptr + row), en = __ldg(rowptr + row + 1);
-    T S[CH][Vec<T>::N];
-    const T score = row_forward<T, LPR, CH, U>(col, val, b, en, w, v, kp, w0, k0, k1, S);
-    if (lane == 0) e[row] = score;
-    if (q && lane < LPR) {
-      // q is factor-major [kp][n]: the coordinate passes stream one factor's q over rows
+  const int64_t n_tiles = (n + 31) / 32;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * 32;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const int lr = warp * 4 + i;
+      const int64_t row = row0 + lr;
+      if (row >= n) break;
+      const uint32_t b = __ldg(rowptr + row), en = __ldg(rowptr + row + 1);
+      T S[CH][VN];
+      const T score = row_forward<T, LPR, CH, U>(col, val, b, en, w, v, kp, w0, k0, k1, S);
+      if (lane == 0) e[row] = score;
+      if (q && lane < LPR) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
+        for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-        for (int i = 0; i < Vec<T>::N; ++i) q[(size_t)((ch * LPR + lane) * Vec<T>::N + i) * n + row] = S[ch][i];
+          for (int j = 0; j < VN; ++j) {
+            const int f = (ch * LPR + lane) * VN + j;
+            if (STAGE) sS[lr][f] = S[ch][j];
+            else q[(size_t)f * n + row] = S[ch][j];
+          }
+      }
+    }
+    if (STAGE && q) {
+      __syncthreads();
+      const int64_t row = row0 + lane;
+      if (row < n)
+        for (int f = warp; f < KP; f += 8) q[(size_t)f * n + row] = sS[lane][f];
+      __syncthreads();
     }
   }
 }
 
 template <class T>
 struct AlsFwd {
-  fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; T* e; T* q;
+  fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; T* e; T* q; const uint32_t* col; const float* val;
   template <class TT, int LPR, int CH>
   void run()
   {
-    int64_t want = ceil_div64(d->n, 8);
+    int64_t want = ceil_div64(d->n, 32);
     int64_t cap = (int64_t)ctx->sm_count * 32;
     int grid = (int)std::max<int64_t>(1, std::min(want, cap));
-    FMWR_LAUNCH(ctx, (als_forward_kernel<TT, LPR, CH>), grid, 256, 0, d->rowptr.p, d->col.p, d->val.p, (const TT*)m->w.p,
+    FMWR_LAUNCH(ctx, (als_forward_kernel<TT, LPR, CH>), grid, 256, 0, d->rowptr.p, col, val, (const TT*)m->w.p,
                 (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1, d->n, e, q);
   }
 };
@@ -416,17 +435,18 @@ __device__ __forceinline__ void atomic_add2(double* AB, uint32_t c, double a, do
 
 constexpr int RM_SMEM_COLS = 2048;
 
-constexpr int RM_HOT = 1024;        // hot features per phase kept in a per-CTA shared-memory table
-constexpr int RM_HOT_MIN_LEN = 2048;  // a feature is hot when it has at least this many non-zeros
+constexpr int RM_HOT = 4096;        // hot features per phase kept in a per-CTA shared-memory table
+constexpr int RM_HOT_MIN_LEN = 512;   // a feature is hot when it has at least this many non-zeros
 
 // MODE 0: global vector atomics (warp-aggregated); 1: the whole phase fits the shared-memory table;
 // 2: hot features go to the shared-memory table, the rest to global atomics
 template <class T, int MODE>
 __global__ void __launch_bounds__(256) rm_stats_kernel(RmArgs<T> a)
 {
-  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? RM_HOT : 1);
+  constexpr int HOT_SLOTS = sizeof(T) == 8 ? RM_HOT / 2 : RM_HOT;   // 32 KB of shared memory either way
+  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? HOT_SLOTS : 1);
   __shared__ T sA[SLOTS], sB[SLOTS];
-  const uint32_t n_slots = MODE == 1 ? a.ncols : (MODE == 2 ? (uint32_t)a.n_hot : 0u);
+  const uint32_t n_slots = MODE == 1 ? a.ncols : (MODE == 2 ? (uint32_t)(a.n_hot < HOT_SLOTS ? a.n_hot : HOT_SLOTS) : 0u);
   if (MODE != 0) {
     for (uint32_t c = threadIdx.x; c < n_slots; c += blockDim.x) { sA[c] = T(0); sB[c] = T(0); }
     __syncthreads();
@@ -450,7 +470,7 @@ __global__ void __launch_bounds__(256) rm_stats_kernel(RmArgs<T> a)
     if (MODE == 1) { atomicAdd(&sA[c], sa); atomicAdd(&sB[c], sb); continue; }
     if (MODE == 2) {
       const uint32_t slot = a.hot[a.cb + c];
-      if (slot != 0xffffu) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); continue; }
+      if (slot < n_slots) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); continue; }
     }
     atomic_add2(a.AB, c, sa, sb);
   }
@@ -606,25 +626,47 @@ struct FusedArgs {
   int has_prev; const uint32_t* pcol; const float* pval; const T* pth; const T* pdelta; T* pq;
   int has_cur; const uint32_t* ccol; const float* cval; const T* cth; T* cAB; T* cq;
   uint32_t c_cb, c_ncols; const uint16_t* hot; const uint32_t* hot_col; int n_hot;
+  int cur_sorted;      // rows are sorted by the current phase's feature: equal features sit in consecutive lanes
 };
 
 template <class T, int MODE>
-__device__ __forceinline__ void stats_add(const FusedArgs<T>& a, T* sA, T* sB, uint32_t c, T sa, T sb)
+__device__ __forceinline__ void stats_add(const FusedArgs<T>& a, T* sA, T* sB, uint32_t n_slots, uint32_t c, T sa, T sb)
 {
   if (MODE == 1) { atomicAdd(&sA[c], sa); atomicAdd(&sB[c], sb); return; }
   if (MODE == 2) {
     const uint32_t slot = a.hot[a.c_cb + c];
-    if (slot != 0xffffu) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); return; }
+    if (slot < n_slots) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); return; }
   }
   atomic_add2(a.cAB, c, sa, sb);
 }
 
-template <class T, int MODE, int VEC>
-__global__ void __launch_bounds__(256) fused_kernel(FusedArgs<T> a)
+// rows sorted by this phase's feature: the lanes holding one feature form a contiguous run, so a segmented
+// shuffle reduction leaves the run's total in its first lane -> one vector atomic per run instead of one per row.
+// Must be called by every lane that is still inside the row loop (the loop tail drops the HIGHEST lanes only).
+template <class T>
+__device__ __forceinline__ void stats_add_sorted(const FusedArgs<T>& a, uint32_t c, T sa, T sb)
 {
-  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? RM_HOT : 1);
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, c);
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const T ta = __shfl_down_sync(act, sa, o);
+    const T tb = __shfl_down_sync(act, sb, o);
+    if (lane + o < 32 && ((peers >> (lane + o)) & 1u)) { sa += ta; sb += tb; }
+  }
+  if (lane == __ffs(peers) - 1) atomic_add2(a.cAB, c, sa, sb);
+}
+
+constexpr int FUSED_THREADS = 1024;  // few fat CTAs (2 per SM): the shared-memory tables are flushed once per CTA
+
+template <class T, int MODE, int VEC>
+__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(FusedArgs<T> a)
+{
+  constexpr int HOT_SLOTS = sizeof(T) == 8 ? RM_HOT / 2 : RM_HOT;   // 32 KB of shared memory either way
+  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? HOT_SLOTS : 1);
   __shared__ T sA[SLOTS], sB[SLOTS];
-  const uint32_t n_slots = !a.has_cur ? 0u : (MODE == 1 ? a.c_ncols : (MODE == 2 ? (uint32_t)a.n_hot : 0u));
+  const uint32_t n_slots = !a.has_cur ? 0u : (MODE == 1 ? a.c_ncols : (MODE == 2 ? (uint32_t)(a.n_hot < HOT_SLOTS ? a.n_hot : HOT_SLOTS) : 0u));
   if (MODE != 0) {
     for (uint32_t c = threadIdx.x; c < n_slots; c += blockDim.x) { sA[c] = T(0); sB[c] = T(0); }
     __syncthreads();
@@ -684,7 +726,8 @@ __global__ void __launch_bounds__(256) fused_kernel(FusedArgs<T> a)
           sa = h * h;
           sb = h * ev[u];
         }
-        stats_add<T, MODE>(a, sA, sB, cc[u], sa, sb);
+        if (MODE == 0 && a.cur_sorted) stats_add_sorted<T>(a, cc[u], sa, sb);
+        else stats_add<T, MODE>(a, sA, sB, n_slots, cc[u], sa, sb);
       }
     }
   }
@@ -699,6 +742,13 @@ struct DenseLayout {
   bool ok = false;
   DBuf<uint32_t> col;    // [n_phases][n] phase-local feature id
   DBuf<float> val;       // [n_phases][n]
+  // optional row permutation: rows sorted by the feature of the widest phase (so that phase needs ~1 atomic per
+  // run instead of per row).  e, q and the labels then live in permuted row order; parameters are unaffected.
+  bool permuted = false;
+  int sorted_phase = -1;
+  DBuf<uint32_t> pcol;   // [n][np] CSR columns of the permuted rows (global ids) for the forward pass
+  DBuf<float> pval;      // [n][np]
+  DBuf<float> py;        // [n] labels of the permuted rows
 };
 
 __global__ void dense_check_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t n, int np,
@@ -714,16 +764,37 @@ __global__ void dense_check_kernel(const uint32_t* __restrict__ rowptr, const ui
 }
 
 __global__ void dense_build_kernel(const uint32_t* __restrict__ col, const float* __restrict__ val, int64_t n, int np,
-                                   const uint32_t* __restrict__ pbeg, uint32_t* __restrict__ ocol, float* __restrict__ oval)
+                                   const uint32_t* __restrict__ pbeg, const uint32_t* __restrict__ perm,
+                                   uint32_t* __restrict__ ocol, float* __restrict__ oval)
 {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // output-major: t = j * n + r
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // output-major: t = j * n + i
   if (t >= n * np) return;
-  const int64_t j = t / n, r = t - j * n;
+  const int64_t j = t / n, i = t - j * n;
+  const int64_t r = perm ? (int64_t)perm[i] : i;
   ocol[t] = col[r * np + j] - pbeg[j];
   oval[t] = val[r * np + j];
 }
 
-static void build_dense(fmwr_data* d, const std::vector<uint32_t>& pbeg_host, DenseLayout& dl)
+__global__ void dense_phase_key_kernel(const uint32_t* __restrict__ col, int64_t n, int np, int j, uint32_t* __restrict__ key)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) key[r] = col[r * np + j];
+}
+
+__global__ void dense_permute_rows_kernel(const uint32_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ y,
+                                          int64_t n, int np, const uint32_t* __restrict__ perm, uint32_t* __restrict__ pcol,
+                                          float* __restrict__ pval, float* __restrict__ py)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // t = i * np + j
+  if (t >= n * np) return;
+  const int64_t i = t / np, j = t - i * np;
+  const int64_t r = perm[i];
+  pcol[t] = col[r * np + j];
+  pval[t] = val[r * np + j];
+  if (j == 0) py[i] = y[r];
+}
+
+static void build_dense(fmwr_data* d, const std::vector<uint32_t>& pbeg_host, DenseLayout& dl, bool allow_perm)
 {
   fmwr_ctx* ctx = d->ctx;
   const int np = (int)pbeg_host.size() - 1;
@@ -740,8 +811,27 @@ static void build_dense(fmwr_data* d, const std::vector<uint32_t>& pbeg_host, De
   FMWR_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   if (hbad) return;
+  // widest phase: if it does not fit the shared-memory table, sort the rows by its feature
+  int jstar = 0;
+  for (int j = 1; j < np; ++j) if (pbeg_host[j + 1] - pbeg_host[j] > pbeg_host[jstar + 1] - pbeg_host[jstar]) jstar = j;
+  DBuf<uint32_t> perm;
+  dl.permuted = false; dl.sorted_phase = -1;
+  if (allow_perm && pbeg_host[jstar + 1] - pbeg_host[jstar] > (uint32_t)RM_SMEM_COLS && d->has_labels) {
+    DBuf<uint32_t> key_in, key_out, idx_in;
+    key_in.alloc(n); key_out.alloc(n); idx_in.alloc(n); perm.alloc(n);
+    FMWR_LAUNCH(ctx, dense_phase_key_kernel, ceil_div(n, 256), 256, 0, d->col.p, n, np, jstar, key_in.p);
+    launch_iota(ctx, idx_in.p, n);
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (uint64_t)pbeg_host[np]) ++bits;
+    sort_pairs_u32(ctx, key_in.p, key_out.p, idx_in.p, perm.p, n, bits);
+    dl.pcol.alloc((size_t)n * np); dl.pval.alloc((size_t)n * np); dl.py.alloc(n);
+    FMWR_LAUNCH(ctx, dense_permute_rows_kernel, ceil_div(n * np, 256), 256, 0, d->col.p, d->val.p, d->y.p, n, np, perm.p, dl.pcol.p,
+                dl.pval.p, dl.py.p);
+    dl.permuted = true; dl.sorted_phase = jstar;
+  }
   dl.col.alloc((size_t)n * np); dl.val.alloc((size_t)n * np);
-  FMWR_LAUNCH(ctx, dense_build_kernel, ceil_div(n * np, 256), 256, 0, d->col.p, d->val.p, n, np, pbeg.p, dl.col.p, dl.val.p);
+  FMWR_LAUNCH(ctx, dense_build_kernel, ceil_div(n * np, 256), 256, 0, d->col.p, d->val.p, n, np, pbeg.p, dl.permuted ? perm.p : nullptr,
+              dl.col.p, dl.val.p);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   dl.ok = true;
 }
@@ -756,7 +846,7 @@ static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, co
                             const double* normals, long long n_normals, uint64_t seed)
 {
   const int vec = (n % 4 == 0) ? 4 : 1;
-  const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, ceil_div64(ceil_div64(n, vec), 256));
+  const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, ceil_div64(ceil_div64(n, vec), FUSED_THREADS));
   const int T_ = (int)steps.size();
   for (int t = 0; t <= T_; ++t) {
     FusedArgs<T> fa;
@@ -782,17 +872,18 @@ static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, co
       fa.has_cur = 1;
       fa.ccol = dl.col.p + (size_t)cs.phase * n; fa.cval = dl.val.p + (size_t)cs.phase * n;
       fa.cth = ra.th; fa.cAB = ra.AB; fa.cq = cs.q ? cs.q + (size_t)cs.f * n : nullptr;
+      fa.cur_sorted = (dl.permuted && dl.sorted_phase == cs.phase) ? 1 : 0;
       fa.c_cb = cb; fa.c_ncols = ncols; fa.hot = rm.hot.p; fa.hot_col = rm.hot_col.p + (size_t)cs.phase * RM_HOT; fa.n_hot = rm.n_hot[cs.phase];
     }
-    const int mode = !fa.has_cur ? 0 : (fa.c_ncols <= (uint32_t)RM_SMEM_COLS ? 1 : (fa.n_hot > 0 ? 2 : 0));
+    const int mode = !fa.has_cur ? 0 : (fa.c_ncols <= (uint32_t)RM_SMEM_COLS ? 1 : (fa.cur_sorted ? 0 : (fa.n_hot > 0 ? 2 : 0)));
     if (vec == 4) {
-      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 4>), grid, 256, 0, fa);
-      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 4>), grid, 256, 0, fa);
-      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 4>), grid, 256, 0, fa);
+      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 4>), grid, FUSED_THREADS, 0, fa);
+      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 4>), grid, FUSED_THREADS, 0, fa);
+      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 4>), grid, FUSED_THREADS, 0, fa);
     } else {
-      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 1>), grid, 256, 0, fa);
-      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 1>), grid, 256, 0, fa);
-      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 1>), grid, 256, 0, fa);
+      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 1>), grid, FUSED_THREADS, 0, fa);
+      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 1>), grid, FUSED_THREADS, 0, fa);
+      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 1>), grid, FUSED_THREADS, 0, fa);
     }
     if (t < T_) FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(ra.ncols, 256), 256, 0, ra);
   }
@@ -884,20 +975,32 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   FMWR_REQUIRE(n < (1ll << 31) && p < (1ll << 31), FMWR_ERR_UNSUPPORTED, "dimension too large");
 
   transpose_build(d);                                                    // src/FM.cpp:148-152
-  PhaseInfo ph;
-  build_phase_info(d, ph);
+  struct AlsCache { PhaseInfo ph; RowMajor rm; DenseLayout dl; bool rm_tried = false; };
+  if (d->als_cache && s->rands && static_cast<AlsCache*>(d->als_cache.get())->dl.permuted) d->als_cache.reset();
+  if (!d->als_cache) {
+    auto c = std::make_shared<AlsCache>();
+    build_phase_info(d, c->ph);
+    d->als_cache = c;
+  }
+  AlsCache& cache = *static_cast<AlsCache*>(d->als_cache.get());
+  PhaseInfo& ph = cache.ph;
 
   // streaming (row-major) coordinate passes when the data decomposes into few phases (field-structured data);
   // otherwise the column-parallel kernels
-  RowMajor rm;
+  RowMajor& rm = cache.rm;
   const int n_phases = (int)ph.begin.size() - 1;
   const bool use_rm = n_phases <= 256 && d->nnz > 0 && getenv("FMWR_ALS_COLUMN") == nullptr;
   DBuf<T> rm_th, rm_AB, rm_delta, rm_th2, rm_AB2, rm_delta2;
-  DenseLayout dl;
+  DenseLayout& dl = cache.dl;
   if (use_rm) {
-    build_row_major(d, ph.begin, ph.colptr_host, rm);
+    if (!cache.rm_tried) {
+      build_row_major(d, ph.begin, ph.colptr_host, rm);
+      // (an injected rand() stream is consumed in ORIGINAL row order, so such validation runs keep the rows unpermuted)
+      if (getenv("FMWR_ALS_NO_DENSE") == nullptr) build_dense(d, ph.begin, dl, s->rands == nullptr && getenv("FMWR_ALS_NO_PERM") == nullptr);
+      if (dl.ok) { rm.row.release(); rm.col.release(); rm.val.release(); }     // the dense copy supersedes the row-major one
+      cache.rm_tried = true;
+    }
     rm_th.alloc(rm.max_cols); rm_AB.alloc(2 * (size_t)rm.max_cols); rm_delta.alloc(rm.max_cols);
-    if (getenv("FMWR_ALS_NO_DENSE") == nullptr) build_dense(d, ph.begin, dl);
     if (dl.ok) { rm_th2.alloc(rm.max_cols); rm_AB2.alloc(2 * (size_t)rm.max_cols); rm_delta2.alloc(rm.max_cols); }
   }
   StepScratch<T> scr[2] = {{rm_th.p, rm_AB.p, rm_delta.p}, {rm_th2.p, rm_AB2.p, rm_delta2.p}};
@@ -955,17 +1058,19 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
       }
     }
     // e <- predict_batch (:100), q[r][f] <- S_f
-    AlsFwd<T> fw{ctx, m, d, e.p, enable_v ? q.p : nullptr};
+    const bool perm_rows = use_rm && dl.ok && dl.permuted;     // e, q, labels in permuted row order (see DenseLayout)
+    const float* yp = perm_rows ? dl.py.p : d->y.p;
+    AlsFwd<T> fw{ctx, m, d, e.p, enable_v ? q.p : nullptr, perm_rows ? dl.pcol.p : d->col.p, perm_rows ? dl.pval.p : d->val.p};
     dispatch_layout<T>(kp, fw);
     // calculate_error (:520-562)
     if (!cls) {
-      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, d->y.p, n, 0, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 0, ctx->dp_table.p, s->seed, (uint64_t)sweep);
     } else if (!do_sample) {
-      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, d->y.p, n, 1, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 1, ctx->dp_table.p, s->seed, (uint64_t)sweep);
     } else if (s->rands) {
       FMWR_LAUNCH(ctx, als_error_stream_kernel<T>, 1, 32, 0, e.p, d->y.p, n, rands_dev.p, (long long)s->n_rands, rand_pos.p);
     } else {
-      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, d->y.p, n, 2, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 2, ctx->dp_table.p, s->seed, (uint64_t)sweep);
     }
     // update_alpha (:360-380)
     if (!do_multilevel) alpha = alpha_0;

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfmwr_b200.so")
+LIB_PATH = os.environ.get("FMWR_LIB_PATH") or os.path.join(HERE, "libfmwr_b200.so")   # override: kernel-variant experiments only
 
 CLASSIFICATION, REGRESSION = 10, 20
 MCMC, ALS, SGD, FTRL, TDAP = 100, 200, 300, 500, 600

@@ -51,39 +51,53 @@ __device__ __forceinline__ T sgd_step(T theta, T g, T lr, T reg, int l1, T u, T&
   return theta;
 }
 
+// Throughput-mode arithmetic: MUFU approximations (sqrt.approx / rcp.approx, <= 2 ulp) instead of the IEEE
+// sequences (~10 instructions each) -- the minibatch update kernel is issue-bound on them.  FAST is only ever
+// set for the fp32 minibatch kernels; the exact (batch = 1) kernels and every fp64 instantiation keep IEEE ops.
+template <bool FAST> __device__ __forceinline__ float m_sqrt(float x)
+{
+  if (FAST) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  return sqrtf(x);
+}
+template <bool FAST> __device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
+template <bool FAST> __device__ __forceinline__ float m_div(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+template <bool FAST> __device__ __forceinline__ double m_div(double a, double b) { return a / b; }
+
 // FTRL-Proximal: state (z, n) in/out, returns refreshed theta
-template <class T>
+template <class T, bool FAST = false>
 __device__ __forceinline__ T ftrl_step(T theta, T g, T& z, T& n, T alpha, T beta, T l1, T l2)
 {
   const T n_old = n;
   n = n_old + g * g;
-  const T sq = sqrt(n);
-  const T sigma = (sq - sqrt(n_old)) / alpha;
+  const T sq = m_sqrt<FAST>(n);
+  const T sigma = m_div<FAST>(sq - m_sqrt<FAST>(n_old), alpha);
   z += g - sigma * theta;
   if (fabs(z) <= l1) return T(0);
   const T sign = z < T(0) ? T(-1) : T(1);
-  return -(z - sign * l1) / ((beta + sq) / alpha + l2);
+  return -m_div<FAST>(z - sign * l1, m_div<FAST>(beta + sq, alpha) + l2);
 }
 
 // TDAP state update: (u, nu, delta, h) in/out; returns z = nu - h
-template <class T>
+template <class T, bool FAST = false>
 __device__ __forceinline__ T tdap_state(T theta, T g, T& u, T& nu, T& delta, T& h, T alpha, T egamma)
 {
   const T u_old = u;
   u = u_old + g * g;
   nu += g;
-  const T sigma = (sqrt(u) - sqrt(u_old)) / alpha;
+  const T sigma = m_div<FAST>(m_sqrt<FAST>(u) - m_sqrt<FAST>(u_old), alpha);
   delta = egamma * (delta + sigma);
   h = egamma * (h + sigma * theta);
   return nu - h;
 }
 
-template <class T>
+template <class T, bool FAST = false>
 __device__ __forceinline__ T tdap_refresh(T z, T delta, T l1, T l2)
 {
   if (fabs(z) <= l1) return T(0);
   const T sign = z < T(0) ? T(-1) : T(1);
-  return -(z - sign * l1) / (delta + l2);
+  return -m_div<FAST>(z - sign * l1, delta + l2);
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 }  // namespace fmwr

@@ -19,6 +19,10 @@
 
 #include <cmath>
 
+#ifndef FMWR_K2_UE
+#define FMWR_K2_UE 4
+#endif
+
 namespace fmwr {
 
 int solver_state_count(const SolverParams<double>& sp);
@@ -82,7 +86,7 @@ mb_finalize_kernel(const float* __restrict__ y, const double* __restrict__ scal,
 template <class T>
 struct MbUpdArgs {
   const uint32_t* seg_ptr; const uint4* seg_rec; const uint32_t* ent_row; const float* ent_val;
-  uint32_t seg_begin, seg_end;
+  uint32_t seg_begin, seg_end, seg_total, pf_dist;
   int64_t row_begin; int rows;          // rows of this batch that take part (row filter for a truncated last batch)
   const T* mult; const T* Scache;
   T* w; T* v; double* scal;
@@ -98,13 +102,26 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
   typedef typename Vec<T>::type V16;
   constexpr int VN = Vec<T>::N;
   constexpr int G = 32 / LPR;
+  constexpr bool FAST = sizeof(T) == 4;
   const SolverParams<T> sp = a.sp;
 
-  // last block: the intercept (dense coordinate) -- fixed-order reduction of the batch's multipliers
-  if (blockIdx.x == gridDim.x - 1) {
+  // block 0: the intercept (dense coordinate) -- fixed-order reduction of the batch's multipliers.  It is the FIRST
+  // block so that its serial chain of loads overlaps the rest of the grid instead of forming the kernel's tail.
+  if (blockIdx.x == 0) {
     __shared__ double red[8];
     double acc = 0.0;
-    for (int r = threadIdx.x; r < a.rows; r += blockDim.x) acc += (double)a.mult[r];
+    {
+      constexpr int UN = 16;
+      int r = threadIdx.x;
+      for (; r + (UN - 1) * 256 < a.rows; r += UN * 256) {
+        T t[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) t[u] = a.mult[r + u * 256];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) acc += (double)t[u];
+      }
+      for (; r < a.rows; r += 256) acc += (double)a.mult[r];
+    }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -139,13 +156,35 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
 
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, l = lane % LPR;
-  const uint32_t seg = a.seg_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
+  const uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
   if (seg >= a.seg_end) return;
   // one 16-byte record: {feature, length, first row, first value}; everything below depends only on it, so the
   // parameter row, its optimizer state and the first row's cache line are all requested in the same round trip
   const uint4 rec = __ldg(a.seg_rec + seg);
+  const uint32_t eb = __ldg(a.seg_ptr + seg);
+  // software prefetch into L2: the group working on segment s requests the parameter / state rows and the first
+  // S-cache line of segment s + pf_dist (about the number of segments in flight on the device), so the demand loads
+  // below see L2 latency instead of DRAM latency.  Reaching into the NEXT batch's segments is harmless (L2 is the
+  // point of coherence; the rows may be rewritten by this launch and are then simply updated in place).
+  uint4 prec = make_uint4(0u, 0u, 0u, 0u);
+  const bool pf = a.pf_dist != 0u && seg + a.pf_dist < a.seg_total;
+  if (pf) prec = __ldg(a.seg_rec + seg + a.pf_dist);
   const uint32_t c = rec.x, len = rec.y;
   const int r0 = (int)((int64_t)rec.z - a.row_begin);
+  if (pf) {
+    constexpr int NSTP = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+    const size_t off = ((size_t)prec.x * a.kp + (size_t)l * Vec<T>::N) * sizeof(T);      // lane l covers its own 16 bytes' sector
+    if ((l * 16) % 32 == 0) {
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        prefetch_l2(reinterpret_cast<const char*>(a.v) + off + (size_t)ch * LPR * 16);
+        if (SOLVER != FMWR_SGD || sp.l1) {
+#pragma unroll
+          for (int st = 0; st < NSTP; ++st) prefetch_l2(reinterpret_cast<const char*>(a.sv[st]) + off + (size_t)ch * LPR * 16);
+        }
+      }
+    }
+  }
   if (r0 >= a.rows) return;                       // rows ascend inside a segment: nothing of it is in the (truncated) batch
   const int kp = a.kp;
 
@@ -172,6 +211,13 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       for (int st = 0; st < NST; ++st) stw[st] = a.sw[st][c];
     }
   }
+  // entries 2..len of the segment: lane l of the group fetches entry 1 + l in the SAME round trip as the
+  // parameter row, so a segment costs three dependent memory rounds whatever its length (record -> rows + entry
+  // list -> the other rows' cache lines, requested four at a time)
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+  uint32_t my_r = 0xffffffffu;
+  float my_x = 0.f;
+  if (1u + (uint32_t)l < len) { my_r = __ldg(a.ent_row + eb + 1 + l); my_x = __ldg(a.ent_val + eb + 1 + l); }
 
   T th[CH][VN], Gv[CH][VN];
   const T x0 = T(__uint_as_float(rec.w));
@@ -184,21 +230,40 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
 #pragma unroll
     for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = m0 * fm_grad(s[k2], th[ch][k2], x0);
   }
-  if (len > 1) {
-    const uint32_t eb = a.seg_ptr[seg];
-    for (uint32_t i = eb + 1; i < eb + len; ++i) {
-      const int r = (int)((int64_t)a.ent_row[i] - a.row_begin);
-      if (r >= a.rows) break;
-      const T x = T(a.ent_val[i]);
-      const T mr = a.mult[r];
-      const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)r * a.s_stride);
-      Gw += mr * x;
+  for (uint32_t base = 1; base < len; base += LPR) {
+    if (base > 1) {
+      my_r = 0xffffffffu; my_x = 0.f;
+      if (base + (uint32_t)l < len) { my_r = __ldg(a.ent_row + eb + base + l); my_x = __ldg(a.ent_val + eb + base + l); }
+    }
+    const int cnt = (int)min((uint32_t)LPR, len - base);
+    constexpr int UE = LPR < FMWR_K2_UE ? LPR : FMWR_K2_UE;
+    for (int j0 = 0; j0 < cnt; j0 += UE) {
+      T xe[UE], me[UE];
+      V16 se[UE][CH];
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        T s[VN];
-        vec_to_arr(sr[ch * LPR + l], s);
+      for (int u = 0; u < UE; ++u) {
+        const int src = g * LPR + ((j0 + u) & (LPR - 1));
+        const uint32_t rr = __shfl_sync(gmask, my_r, src);
+        xe[u] = T(__shfl_sync(gmask, my_x, src));
+        // rows ascend inside a segment; rows past a truncated last batch (and the padding lanes) contribute nothing
+        const int64_t rl = (int64_t)rr - a.row_begin;
+        const bool ok = (j0 + u < cnt) && rl < (int64_t)a.rows;
+        me[u] = ok ? a.mult[rl] : T(0);
+        const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)(ok ? rl : 0) * a.s_stride);
 #pragma unroll
-        for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] += mr * fm_grad(s[k2], th[ch][k2], x);
+        for (int ch = 0; ch < CH; ++ch) se[u][ch] = sr[ch * LPR + l];
+        if (!ok) xe[u] = T(0);
+      }
+#pragma unroll
+      for (int u = 0; u < UE; ++u) {
+        Gw += me[u] * xe[u];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          T s[VN];
+          vec_to_arr(se[u][ch], s);
+#pragma unroll
+          for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] += me[u] * fm_grad(s[k2], th[ch][k2], xe[u]);
+        }
       }
     }
   }
@@ -210,12 +275,12 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       tw = sgd_step(tw, Gw, sp.lr, sp.reg_w, sp.l1, a.u_w, q);
       if (sp.l1) a.sw[0][c] = q;
     } else if (SOLVER == FMWR_FTRL) {
-      tw = ftrl_step(tw, Gw, stw[0], stw[1], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
+      tw = ftrl_step<T, FAST>(tw, Gw, stw[0], stw[1], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
       a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1];
     } else {
-      const T z = tdap_state(tw, Gw, stw[0], stw[1], stw[2], stw[3], sp.alpha_w, sp.egamma);
+      const T z = tdap_state<T, FAST>(tw, Gw, stw[0], stw[1], stw[2], stw[3], sp.alpha_w, sp.egamma);
       a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1]; a.sw[2][c] = stw[2]; a.sw[3][c] = stw[3];
-      tw = tdap_refresh(z, stw[2], sp.l1_w, sp.l2_w);
+      tw = tdap_refresh<T, FAST>(z, stw[2], sp.l1_w, sp.l2_w);
     }
     a.w[c] = tw;
   }
@@ -237,7 +302,7 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       T z[VN], nn[VN];
       vec_to_arr(raw_st[0][ch], z); vec_to_arr(raw_st[1][ch], nn);
 #pragma unroll
-      for (int i = 0; i < VN; ++i) th[ch][i] = ftrl_step(th[ch][i], Gv[ch][i], z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
+      for (int i = 0; i < VN; ++i) th[ch][i] = ftrl_step<T, FAST>(th[ch][i], Gv[ch][i], z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
       reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(z);
       reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp)[vi] = arr_to_vec(nn);
     } else {
@@ -245,8 +310,8 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       vec_to_arr(raw_st[0][ch], u); vec_to_arr(raw_st[1][ch], nu); vec_to_arr(raw_st[2][ch], dl); vec_to_arr(raw_st[3][ch], h);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
-        const T z = tdap_state(th[ch][i], Gv[ch][i], u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
-        th[ch][i] = tdap_refresh(z, dl[i], sp.l1_v, sp.l2_v);
+        const T z = tdap_state<T, FAST>(th[ch][i], Gv[ch][i], u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
+        th[ch][i] = tdap_refresh<T, FAST>(z, dl[i], sp.l1_v, sp.l2_v);
       }
       reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(u);
       reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp)[vi] = arr_to_vec(nu);
@@ -329,6 +394,8 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   ua.mult = mult.p; ua.Scache = Scache.p;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
+  ua.seg_total = (uint32_t)d->mb_batch_seg[n_batches];
+  { const char* e = getenv("FMWR_K2_PF"); ua.pf_dist = e ? (uint32_t)atoi(e) : 32768u; }
   ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1; ua.s_stride = s_stride;
   ua.sp = params_from<T>(spd);
 

@@ -14,58 +14,110 @@
 
 namespace fmwr {
 
-template <class T>
-struct RowAcc {
-  // filled by row_forward: identical in every lane of the warp
-  T score;   // w0*k0 + linear + pairwise (no link)
-};
+// Loads that the compiler must keep in program order (volatile asm): the gather loop issues a whole batch of
+// column / value loads, then a whole batch of factor-row loads, and only then consumes them.  Left to itself the
+// compiler sinks every load next to its first use, which serialises the batch into one dependent round per entry.
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) { uint32_t r; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
+__device__ __forceinline__ float ld_nc_f32(const float* p) { float r; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p)); return r; }
+__device__ __forceinline__ float4 ld_nc_v16(const float4* p)
+{
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_nc_v16(const double2* p)
+{
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
 
-// LPR: lanes per V row (power of two), CH: 16-byte chunks per lane, U: non-zeros in flight per group.
-// On return S[ch][i] holds the complete S_f for factor (ch*LPR + l)*VN + i in EVERY group.
-template <class T, int LPR, int CH, int U>
-__device__ __forceinline__ void row_gather(const uint32_t* __restrict__ col, const float* __restrict__ val,
-                                           uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
-                                           int kp, int k1, T (&S)[CH][Vec<T>::N], T& lin_out, T& q_out)
+// ---- team forward ------------------------------------------------------------------------------------------
+// A TEAM of lanes owns a row: the whole warp (TEAM = 32; long rows) or one LPR-lane group (TEAM = LPR; rows with a
+// handful of non-zeros, 32/LPR rows per warp).  The team is NG = TEAM/LPR sub-groups; sub-group sg fetches entries
+// sg, sg + NG, ... of the row, U factor rows in flight.  These kernels are instruction-issue bound, so the loop is
+// written for instruction count: immediate-offset loads off a running pointer, an unpredicated path for full
+// batches, ONE scalar for sum_f Q_f (each (entry, factor) product lives in exactly one lane), the linear term on
+// a coalesced sweep of the row.
+//
+// Returns this lane's share of  lin - 1/2 sum Q (+ 1/2 sum_f S_f^2 when with_pair, counted in sub-group 0);
+// the caller sums it over the team (team_sum).  On return S[ch][i] is the complete S_f for factor
+// (ch*LPR + l)*VN + i in every sub-group of the team.
+template <class T, int LPR, int CH, int TEAM, int U>
+__device__ __forceinline__ T team_gather(const uint32_t* __restrict__ col, const float* __restrict__ val, uint32_t b,
+                                         uint32_t e, const T* __restrict__ w, const T* __restrict__ v, int kp, int k1,
+                                         bool with_pair, T (&S)[CH][Vec<T>::N])
 {
   typedef typename Vec<T>::type V16;
   constexpr int VN = Vec<T>::N;
-  constexpr int G = 32 / LPR;
-  const int lane = threadIdx.x & 31;
-  const int g = lane / LPR, l = lane % LPR;
+  constexpr int NG = TEAM / LPR;
+  const int tl = (threadIdx.x & 31) % TEAM;
+  const int sg = tl / LPR, l = tl % LPR;
 
-  T Q[CH][VN];
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-    for (int i = 0; i < VN; ++i) { S[ch][i] = T(0); Q[ch][i] = T(0); }
-  T lin = T(0);
+    for (int i = 0; i < VN; ++i) S[ch][i] = T(0);
+  T q = T(0), lin = T(0);
+  if (k1) {
+#pragma unroll 1
+    for (uint32_t j = b + tl; j < e; j += TEAM) lin += w[__ldg(col + j)] * T(__ldg(val + j));
+  }
 
-  for (uint32_t base = b; base < e; base += G * U) {
-    uint32_t c[U];
+  const T* vl = v + l * VN;
+  const uint32_t rowb = (uint32_t)kp * (uint32_t)sizeof(T);
+  uint32_t base = b;
+  for (; base + U * NG <= e; base += U * NG) {                 // full batches: no predicates
+    const uint32_t* cp = col + base + sg;
+    const float* xp = val + base + sg;
     T x[U];
+    uint32_t c[U];
+    V16 vv[U][CH];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ld_nc_u32(cp + u * NG);
+#pragma unroll
+    for (int u = 0; u < U; ++u) x[u] = T(ld_nc_f32(xp + u * NG));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const V16* vr = reinterpret_cast<const V16*>(reinterpret_cast<const char*>(vl) + (uint64_t)c[u] * rowb);
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) vv[u][ch] = ld_nc_v16(vr + ch * LPR);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        T a[VN];
+        vec_to_arr(vv[u][ch], a);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          const T t = a[i] * x[u];
+          S[ch][i] += t;
+          q += t * t;
+        }
+      }
+  }
+  if (base < e) {                                              // tail: predicated
+    const uint32_t rem = e - base;                             // 1 .. U*NG - 1
+    const uint32_t* cp = col + base + sg;
+    const float* xp = val + base + sg;
+    T x[U];
+    uint32_t c[U];
     V16 vv[U][CH];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t j = base + u * G + g;
-      const bool ok = j < e;
-      c[u] = ok ? __ldg(col + j) : 0u;
-      x[u] = ok ? T(__ldg(val + j)) : T(0);
+      const bool ok = (uint32_t)(u * NG + sg) < rem;
+      c[u] = 0u; x[u] = T(0);
+      if (ok) { c[u] = ld_nc_u32(cp + u * NG); x[u] = T(ld_nc_f32(xp + u * NG)); }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t j = base + u * G + g;
-      const V16* vr = reinterpret_cast<const V16*>(v + (size_t)c[u] * kp);
+      const bool ok = (uint32_t)(u * NG + sg) < rem;
+      const V16* vr = reinterpret_cast<const V16*>(reinterpret_cast<const char*>(vl) + (uint64_t)c[u] * rowb);
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
-        if (j < e) vv[u][ch] = vr[ch * LPR + l];
-        else memset(&vv[u][ch], 0, sizeof(V16));
-      }
-    }
-    if (k1 && l == 0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t j = base + u * G + g;
-        if (j < e) lin += w[c[u]] * x[u];
+        memset(&vv[u][ch], 0, sizeof(V16));
+        if (ok) vv[u][ch] = ld_nc_v16(vr + ch * LPR);
       }
     }
 #pragma unroll
@@ -78,62 +130,68 @@ __device__ __forceinline__ void row_gather(const uint32_t* __restrict__ col, con
         for (int i = 0; i < VN; ++i) {
           const T t = a[i] * x[u];
           S[ch][i] += t;
-          Q[ch][i] += t * t;
+          q += t * t;
         }
       }
   }
-
-  // combine the G groups
+  // combine the sub-groups.  q goes along so that sub-group 0 ends up with  sum_f S_f^2  AND  sum_f Q_f  of the same
+  // few factors: the two nearly cancel, and cancelling them inside one lane (instead of across the team sum) keeps
+  // the fp32 result within 1e-5 of the fp64 reference even for k = 128.
 #pragma unroll
-  for (int o = LPR; o < 32; o <<= 1)
+  for (int o = LPR; o < TEAM; o <<= 1) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
-        Q[ch][i] += __shfl_xor_sync(0xffffffffu, Q[ch][i], o);
-      }
-  // lin lives in lane 0 of every group; sum Q over this group's factors (identical in every group after the combine)
-  T qs = T(0);
+      for (int i = 0; i < VN; ++i) S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  T part = lin;
+  if (sg == 0) {
+    T pair = -q;
+    if (with_pair) {
 #pragma unroll
-  for (int ch = 0; ch < CH; ++ch)
+      for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-    for (int i = 0; i < VN; ++i) qs += Q[ch][i];
-  lin_out = lin;
-  q_out = (g == 0) ? qs : T(0);
+        for (int i = 0; i < VN; ++i) pair += S[ch][i] * S[ch][i];
+    }
+    part += T(0.5) * pair;
+  }
+  return part;
 }
 
-template <class T, int LPR, int CH, int U>
-__device__ __forceinline__ T row_forward(const uint32_t* __restrict__ col, const float* __restrict__ val,
-                                         uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
-                                         int kp, T w0, int k0, int k1, T (&S)[CH][Vec<T>::N])
+template <class T, int TEAM>
+__device__ __forceinline__ T team_sum(T x)
 {
-  constexpr int VN = Vec<T>::N;
-  const int g = (threadIdx.x & 31) / LPR;
-  T lin, qs;
-  row_gather<T, LPR, CH, U>(col, val, b, e, w, v, kp, k1, S, lin, qs);
-  T r = lin - T(0.5) * qs;
-  if (g == 0) {
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-      for (int i = 0; i < VN; ++i) r += T(0.5) * S[ch][i] * S[ch][i];
-  }
-  r = warp_sum(r);
-  return (k0 ? w0 : T(0)) + r;
+  for (int o = TEAM / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <int LPR> struct GatherDepth { enum { U = LPR >= 16 ? 8 : 4 }; };
+
+// score (no link) of the team's row, identical in every lane of the team
+template <class T, int LPR, int CH, int TEAM>
+__device__ __forceinline__ T team_forward(const uint32_t* __restrict__ col, const float* __restrict__ val, uint32_t b,
+                                          uint32_t e, const T* __restrict__ w, const T* __restrict__ v, int kp, T w0,
+                                          int k0, int k1, T (&S)[CH][Vec<T>::N])
+{
+  const T part = team_gather<T, LPR, CH, TEAM, GatherDepth<LPR>::U>(col, val, b, e, w, v, kp, k1, true, S);
+  return (k0 ? w0 : T(0)) + team_sum<T, TEAM>(part);
 }
 
 // column-slice variant: S_f of the slice plus the ADDITIVE part of the score (linear term - 1/2 sum Q);
 // 1/2 sum_f S_f^2 is formed after the partial S_f have been summed over the shards
-template <class T, int LPR, int CH, int U>
-__device__ __forceinline__ void row_forward_partial(const uint32_t* __restrict__ col, const float* __restrict__ val,
-                                                    uint32_t b, uint32_t e, const T* __restrict__ w, const T* __restrict__ v,
-                                                    int kp, int k1, T (&S)[CH][Vec<T>::N], T& addend)
+template <class T, int LPR, int CH, int TEAM>
+__device__ __forceinline__ T team_forward_partial(const uint32_t* __restrict__ col, const float* __restrict__ val,
+                                                  uint32_t b, uint32_t e, const T* __restrict__ w,
+                                                  const T* __restrict__ v, int kp, int k1, T (&S)[CH][Vec<T>::N])
 {
-  T lin, qs;
-  row_gather<T, LPR, CH, U>(col, val, b, e, w, v, kp, k1, S, lin, qs);
-  addend = warp_sum(lin - T(0.5) * qs);
+  const T part = team_gather<T, LPR, CH, TEAM, GatherDepth<LPR>::U>(col, val, b, e, w, v, kp, k1, false, S);
+  return team_sum<T, TEAM>(part);
 }
+
+// rows with at most this many non-zeros per LPR-lane group on average go one row per group
+__host__ __device__ inline bool short_rows(int64_t nnz, int64_t n, int lpr) { return lpr < 32 && n > 0 && nnz <= n * 2 * (32 / lpr); }
 
 // table-exact fast_pnorm (reference src/util/Random.h:95-111; Y table regenerated, see link_tables.cu)
 __device__ __forceinline__ double dev_fast_pnorm(const double* __restrict__ Y, double x)
@@ -184,6 +242,13 @@ __device__ __forceinline__ T grad_mult(int task, T y_hat, T y, T lo, T hi)
   }
   return -y * (T(1) - T(1) / (T(1) + exp(-y * y_hat)));
 }
+// throughput (minibatch) mode, fp32: MUFU exp / rcp (about 2 ulp) -- the forward kernel is issue-bound
+__device__ __forceinline__ float grad_mult_fast(int task, float y_hat, float y, float lo, float hi)
+{
+  if (task == FMWR_REGRESSION) return -(y - fmaxf(lo, fminf(hi, y_hat)));
+  return -y * (1.f - __fdividef(1.f, 1.f + __expf(-y * y_hat)));
+}
+__device__ __forceinline__ double grad_mult_fast(int task, double y_hat, double y, double lo, double hi) { return grad_mult<double>(task, y_hat, y, lo, hi); }
 
 // dispatch helper: calls F.template run<T, LPR, CH>() for the model's layout
 template <class T, class F>

@@ -28,37 +28,43 @@ int tracker_step_size(int step_size, int max_iter);
 constexpr int ALS_LONG = 4096;      // columns at least this long get a whole CTA
 
 // ---- forward: e = raw score, q[r][:] = S_f -----------------------------------------------------------
-template <class T, int LPR, int CH>
-__global__ void __launch_bounds__(256)
+// A CTA (8 warps) works on tiles of TILE = 8 * RW rows, RW = max(4, rows per warp per pass).  q is factor-major
+// [kp][n] (the coordinate passes stream one factor's q over rows), so the tile's S_f are staged in shared memory
+// and every factor gets coalesced TILE-row stores.
+template <class T, int LPR, int CH, int TEAM>
+__global__ void __launch_bounds__(256, 4)
 als_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                    const T* __restrict__ w, const T* __restrict__ v, const double* __restrict__ scal, int kp, int k0, int k1,
                    int64_t n, T* __restrict__ e, T* __restrict__ q)
 {
-  constexpr int U = (LPR >= 16) ? 8 : 4;
   constexpr int VN = Vec<T>::N;
   constexpr int KP = LPR * CH * VN;
-  constexpr bool STAGE = (size_t)KP * 33 * sizeof(T) <= 40 * 1024;     // q is factor-major [kp][n]: stage 32 rows in shared
-  __shared__ T sS[STAGE ? 32 : 1][STAGE ? KP + 1 : 1];                // memory so every factor gets one coalesced 32-row store
+  constexpr int TPW = 32 / TEAM;
+  constexpr int RW = TPW > 4 ? TPW : 4;
+  constexpr int TILE = 8 * RW;
+  constexpr bool STAGE = (size_t)(KP + 1) * TILE * sizeof(T) <= 40 * 1024;
+  __shared__ T sS[STAGE ? TILE : 1][STAGE ? KP + 1 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = lane / TEAM, tl = lane % TEAM;
   const T w0 = T(scal[0]);
-  const int64_t n_tiles = (n + 31) / 32;
+  const int64_t n_tiles = (n + TILE - 1) / TILE;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * 32;
+    const int64_t row0 = tile * TILE;
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-      const int lr = warp * 4 + i;
+    for (int i = 0; i < RW; i += TPW) {
+      const int lr = warp * RW + i + team;
       const int64_t row = row0 + lr;
-      if (row >= n) break;
-      const uint32_t b = __ldg(rowptr + row), en = __ldg(rowptr + row + 1);
+      uint32_t b = 0u, en = 0u;
+      if (row < n) { b = __ldg(rowptr + row); en = __ldg(rowptr + row + 1); }
       T S[CH][VN];
-      const T score = row_forward<T, LPR, CH, U>(col, val, b, en, w, v, kp, w0, k0, k1, S);
-      if (lane == 0) e[row] = score;
-      if (q && lane < LPR) {
+      const T score = team_forward<T, LPR, CH, TEAM>(col, val, b, en, w, v, kp, w0, k0, k1, S);
+      if (tl == 0 && row < n) e[row] = score;
+      if (q && tl < LPR && row < n) {
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
           for (int j = 0; j < VN; ++j) {
-            const int f = (ch * LPR + lane) * VN + j;
+            const int f = (ch * LPR + tl) * VN + j;
             if (STAGE) sS[lr][f] = S[ch][j];
             else q[(size_t)f * n + row] = S[ch][j];
           }
@@ -66,9 +72,10 @@ als_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restri
     }
     if (STAGE && q) {
       __syncthreads();
-      const int64_t row = row0 + lane;
-      if (row < n)
-        for (int f = warp; f < KP; f += 8) q[(size_t)f * n + row] = sS[lane][f];
+      for (int f = warp; f < KP; f += 8)
+#pragma unroll
+        for (int r = lane; r < TILE; r += 32)
+          if (row0 + r < n) q[(size_t)f * n + row0 + r] = sS[r][f];
       __syncthreads();
     }
   }
@@ -80,10 +87,18 @@ struct AlsFwd {
   template <class TT, int LPR, int CH>
   void run()
   {
-    int64_t want = ceil_div64(d->n, 32);
+    if (short_rows(d->nnz, d->n, LPR)) go<TT, LPR, CH, LPR>();
+    else go<TT, LPR, CH, 32>();
+  }
+  template <class TT, int LPR, int CH, int TEAM>
+  void go()
+  {
+    constexpr int TPW = 32 / TEAM;
+    constexpr int TILE = 8 * (TPW > 4 ? TPW : 4);
+    int64_t want = ceil_div64(d->n, TILE);
     int64_t cap = (int64_t)ctx->sm_count * 32;
     int grid = (int)std::max<int64_t>(1, std::min(want, cap));
-    FMWR_LAUNCH(ctx, (als_forward_kernel<TT, LPR, CH>), grid, 256, 0, d->rowptr.p, col, val, (const TT*)m->w.p,
+    FMWR_LAUNCH(ctx, (als_forward_kernel<TT, LPR, CH, TEAM>), grid, 256, 0, d->rowptr.p, col, val, (const TT*)m->w.p,
                 (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1, d->n, e, q);
   }
 };

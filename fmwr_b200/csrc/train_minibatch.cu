@@ -31,35 +31,40 @@ void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double s
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
-template <class T, int LPR, int CH>
-__global__ void __launch_bounds__(256)
+template <class T, int LPR, int CH, int TEAM>
+__global__ void __launch_bounds__(256, 4)
 mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                   const float* __restrict__ y, const T* __restrict__ w, const T* __restrict__ v,
                   const double* __restrict__ scal, int kp, int k0, int k1, int task, T lo, T hi,
                   int64_t row_begin, int rows, T* __restrict__ mult, T* __restrict__ Scache, int s_stride, int partial)
 {
   typedef typename Vec<T>::type V16;
-  constexpr int U = (LPR >= 16) ? 8 : 4;
+  constexpr int TPW = 32 / TEAM;
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  const int64_t row = row_begin + r;
-  const uint32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-  T S[CH][Vec<T>::N];
-  if (!partial) {
-    const T score = row_forward<T, LPR, CH, U>(col, val, b, e, w, v, kp, T(scal[0]), k0, k1, S);
-    if (lane == 0) mult[r] = grad_mult<T>(task, score, T(__ldg(y + row)), lo, hi);
-  } else {
-    // feature-parallel: this rank holds a column slice, so the row's score is not known yet.  Emit the partials
-    // [S_f (kp), lin - 1/2 sum Q + 1/2 sum S_f^2 is NOT additive] -> store S_f and the additive scalar (lin - 1/2 sum Q)
-    T addend;
-    row_forward_partial<T, LPR, CH, U>(col, val, b, e, w, v, kp, k1, S, addend);
-    if (lane == 0) Scache[(size_t)r * s_stride + kp] = addend;
-  }
-  if (lane < LPR) {
-    V16* dst = reinterpret_cast<V16*>(Scache + (size_t)r * s_stride);
+  const int tl = lane % TEAM;
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int step = gridDim.x * (blockDim.x >> 5) * TPW;
+  const T w0 = T(scal[0]);
+  for (int base = warp0 * TPW; base < rows; base += step) {       // uniform per warp: every lane reaches the shuffles
+    const int r = base + lane / TEAM;
+    const int64_t row = row_begin + r;
+    uint32_t b = 0u, e = 0u;
+    if (r < rows) { b = __ldg(rowptr + row); e = __ldg(rowptr + row + 1); }
+    T S[CH][Vec<T>::N];
+    if (!partial) {
+      const T score = team_forward<T, LPR, CH, TEAM>(col, val, b, e, w, v, kp, w0, k0, k1, S);
+      if (tl == 0 && r < rows) mult[r] = grad_mult_fast(task, score, T(__ldg(y + row)), lo, hi);
+    } else {
+      // feature-parallel: this rank holds a column slice, so the row's score is not known yet.  Emit the partials:
+      // S_f of the slice and the additive scalar (lin - 1/2 sum Q); 1/2 sum S_f^2 is formed after the exchange
+      const T addend = team_forward_partial<T, LPR, CH, TEAM>(col, val, b, e, w, v, kp, k1, S);
+      if (tl == 0 && r < rows) Scache[(size_t)r * s_stride + kp] = addend;
+    }
+    if (tl < LPR && r < rows) {
+      V16* dst = reinterpret_cast<V16*>(Scache + (size_t)r * s_stride);
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + lane] = arr_to_vec(S[ch]);
+      for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + tl] = arr_to_vec(S[ch]);
+    }
   }
 }
 
@@ -86,7 +91,7 @@ mb_finalize_kernel(const float* __restrict__ y, const double* __restrict__ scal,
 template <class T>
 struct MbUpdArgs {
   const uint32_t* seg_ptr; const uint4* seg_rec; const uint32_t* ent_row; const float* ent_val;
-  uint32_t seg_begin, seg_end, seg_total, pf_dist;
+  uint32_t seg_begin, seg_end;
   int64_t row_begin; int rows;          // rows of this batch that take part (row filter for a truncated last batch)
   const T* mult; const T* Scache;
   T* w; T* v; double* scal;
@@ -96,7 +101,7 @@ struct MbUpdArgs {
   T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
 };
 
-template <class T, int LPR, int CH, int SOLVER>
+template <class T, int LPR, int CH, int SOLVER, bool L1>
 __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
 {
   typedef typename Vec<T>::type V16;
@@ -159,76 +164,64 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
   const uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
   if (seg >= a.seg_end) return;
   // one 16-byte record: {feature, length, first row, first value}; everything below depends only on it, so the
-  // parameter row, its optimizer state and the first row's cache line are all requested in the same round trip
+  // parameter row, its optimizer state, the first row's cache line and the segment's entry list are all requested
+  // in the same round trip: three dependent memory rounds per segment whatever its length
   const uint4 rec = __ldg(a.seg_rec + seg);
   const uint32_t eb = __ldg(a.seg_ptr + seg);
-  // software prefetch into L2: the group working on segment s requests the parameter / state rows and the first
-  // S-cache line of segment s + pf_dist (about the number of segments in flight on the device), so the demand loads
-  // below see L2 latency instead of DRAM latency.  Reaching into the NEXT batch's segments is harmless (L2 is the
-  // point of coherence; the rows may be rewritten by this launch and are then simply updated in place).
-  uint4 prec = make_uint4(0u, 0u, 0u, 0u);
-  const bool pf = a.pf_dist != 0u && seg + a.pf_dist < a.seg_total;
-  if (pf) prec = __ldg(a.seg_rec + seg + a.pf_dist);
   const uint32_t c = rec.x, len = rec.y;
-  const int r0 = (int)((int64_t)rec.z - a.row_begin);
-  if (pf) {
-    constexpr int NSTP = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
-    const size_t off = ((size_t)prec.x * a.kp + (size_t)l * Vec<T>::N) * sizeof(T);      // lane l covers its own 16 bytes' sector
-    if ((l * 16) % 32 == 0) {
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        prefetch_l2(reinterpret_cast<const char*>(a.v) + off + (size_t)ch * LPR * 16);
-        if (SOLVER != FMWR_SGD || sp.l1) {
-#pragma unroll
-          for (int st = 0; st < NSTP; ++st) prefetch_l2(reinterpret_cast<const char*>(a.sv[st]) + off + (size_t)ch * LPR * 16);
-        }
-      }
-    }
-  }
-  if (r0 >= a.rows) return;                       // rows ascend inside a segment: nothing of it is in the (truncated) batch
-  const int kp = a.kp;
+  const uint32_t rb32 = (uint32_t)a.row_begin, nrows = (uint32_t)a.rows;
+  const uint32_t r0 = rec.z - rb32;
+  if (r0 >= nrows) return;                        // rows ascend inside a segment: nothing of it is in the (truncated) batch
 
-  V16* vr = reinterpret_cast<V16*>(a.v + (size_t)c * kp);
-  V16 raw_th[CH], raw_s0[CH], raw_st[4][CH];
   constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
-  const bool use_state = SOLVER != FMWR_SGD || sp.l1;
-  const V16* s0r = reinterpret_cast<const V16*>(a.Scache + (size_t)r0 * a.s_stride);
+  constexpr bool USE_STATE = SOLVER != FMWR_SGD || L1;
+  // TDAP keeps the per-entry gradient form of the exact mode (see fm_grad: a rounding residue flips theta by +-alpha);
+  // SGD / FTRL sum  A_f = sum_r (m_r x_r) S_rf  and  b = sum_r m_r x_r^2  and form  G_f = A_f - v_f b  once
+  constexpr bool ENTRY_FORM = SOLVER == FMWR_TDAP;
+  const size_t off = (size_t)c * a.kp + l * VN;
+  V16* vr = reinterpret_cast<V16*>(a.v + off);
+  V16 raw_th[CH], raw_s0[CH], raw_st[NST][CH];
+  const uint32_t lofs = l * VN;
+  const T* sbase = a.Scache + lofs;
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
-    raw_th[ch] = vr[ch * LPR + l];
-    raw_s0[ch] = s0r[ch * LPR + l];
-    if (use_state) {
+    raw_th[ch] = vr[ch * LPR];
+    raw_s0[ch] = reinterpret_cast<const V16*>(sbase + r0 * (uint32_t)a.s_stride)[ch * LPR];
+    if (USE_STATE) {
 #pragma unroll
-      for (int st = 0; st < NST; ++st) raw_st[st][ch] = reinterpret_cast<const V16*>(a.sv[st] + (size_t)c * kp)[ch * LPR + l];
+      for (int st = 0; st < NST; ++st) raw_st[st][ch] = reinterpret_cast<const V16*>(a.sv[st] + off)[ch * LPR];
     }
   }
   const T m0 = a.mult[r0];
-  T tw = T(0), stw[4] = {T(0), T(0), T(0), T(0)};
+  T tw = T(0), stw[NST];
+#pragma unroll
+  for (int st = 0; st < NST; ++st) stw[st] = T(0);
   if (a.k1 && l == 0) {
     tw = a.w[c];
-    if (use_state) {
+    if (USE_STATE) {
 #pragma unroll
       for (int st = 0; st < NST; ++st) stw[st] = a.sw[st][c];
     }
   }
-  // entries 2..len of the segment: lane l of the group fetches entry 1 + l in the SAME round trip as the
-  // parameter row, so a segment costs three dependent memory rounds whatever its length (record -> rows + entry
-  // list -> the other rows' cache lines, requested four at a time)
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
-  uint32_t my_r = 0xffffffffu;
+  uint32_t my_r = 0xffffffffu;                    // sentinel: (0xffffffff - row_begin) is never < rows
   float my_x = 0.f;
   if (1u + (uint32_t)l < len) { my_r = __ldg(a.ent_row + eb + 1 + l); my_x = __ldg(a.ent_val + eb + 1 + l); }
 
-  T th[CH][VN], Gv[CH][VN];
+  T th[CH][VN], Gv[CH][VN], G1[CH][VN];
   const T x0 = T(__uint_as_float(rec.w));
-  T Gw = m0 * x0;
+  const T mx0 = m0 * x0;
+  T Gw = mx0, bsum = mx0 * x0;
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
     T s[VN];
     vec_to_arr(raw_th[ch], th[ch]);
     vec_to_arr(raw_s0[ch], s);
 #pragma unroll
-    for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = m0 * fm_grad(s[k2], th[ch][k2], x0);
+    for (int k2 = 0; k2 < VN; ++k2) {
+      G1[ch][k2] = m0 * fm_grad(s[k2], th[ch][k2], x0);            // the exact-mode form: what a one-entry segment uses
+      Gv[ch][k2] = ENTRY_FORM ? G1[ch][k2] : mx0 * s[k2];
+    }
   }
   for (uint32_t base = 1; base < len; base += LPR) {
     if (base > 1) {
@@ -242,83 +235,90 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       V16 se[UE][CH];
 #pragma unroll
       for (int u = 0; u < UE; ++u) {
-        const int src = g * LPR + ((j0 + u) & (LPR - 1));
-        const uint32_t rr = __shfl_sync(gmask, my_r, src);
+        const int src = g * LPR + j0 + u;
+        const uint32_t rl = __shfl_sync(gmask, my_r, src) - rb32;
         xe[u] = T(__shfl_sync(gmask, my_x, src));
-        // rows ascend inside a segment; rows past a truncated last batch (and the padding lanes) contribute nothing
-        const int64_t rl = (int64_t)rr - a.row_begin;
-        const bool ok = (j0 + u < cnt) && rl < (int64_t)a.rows;
+        const bool ok = rl < nrows;                // false for the padding lanes and for rows past a truncated batch
         me[u] = ok ? a.mult[rl] : T(0);
-        const V16* sr = reinterpret_cast<const V16*>(a.Scache + (size_t)(ok ? rl : 0) * a.s_stride);
+        const T* sr = sbase + (ok ? rl : 0u) * (uint32_t)a.s_stride;
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) se[u][ch] = sr[ch * LPR + l];
-        if (!ok) xe[u] = T(0);
+        for (int ch = 0; ch < CH; ++ch) se[u][ch] = reinterpret_cast<const V16*>(sr)[ch * LPR];
       }
 #pragma unroll
       for (int u = 0; u < UE; ++u) {
-        Gw += me[u] * xe[u];
+        const T mxe = me[u] * xe[u];
+        Gw += mxe;
+        if (!ENTRY_FORM) bsum += mxe * xe[u];
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
           T s[VN];
           vec_to_arr(se[u][ch], s);
 #pragma unroll
-          for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] += me[u] * fm_grad(s[k2], th[ch][k2], xe[u]);
+          for (int k2 = 0; k2 < VN; ++k2) {
+            if (ENTRY_FORM) Gv[ch][k2] += me[u] * fm_grad(s[k2], th[ch][k2], xe[u]);
+            else Gv[ch][k2] += mxe * s[k2];
+          }
         }
       }
     }
+  }
+  if (!ENTRY_FORM) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = (len == 1u) ? G1[ch][k2] : Gv[ch][k2] - th[ch][k2] * bsum;
   }
 
   // ---- linear weight (lane 0 of the group)
   if (a.k1 && l == 0) {
     if (SOLVER == FMWR_SGD) {
       T q = stw[0];
-      tw = sgd_step(tw, Gw, sp.lr, sp.reg_w, sp.l1, a.u_w, q);
-      if (sp.l1) a.sw[0][c] = q;
+      tw = sgd_step(tw, Gw, sp.lr, sp.reg_w, L1 ? 1 : 0, a.u_w, q);
+      if (L1) a.sw[0][c] = q;
     } else if (SOLVER == FMWR_FTRL) {
-      tw = ftrl_step<T, FAST>(tw, Gw, stw[0], stw[1], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
-      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1];
+      tw = ftrl_step<T, FAST>(tw, Gw, stw[0], stw[1 % NST], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
+      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1 % NST];
     } else {
-      const T z = tdap_state<T, FAST>(tw, Gw, stw[0], stw[1], stw[2], stw[3], sp.alpha_w, sp.egamma);
-      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1]; a.sw[2][c] = stw[2]; a.sw[3][c] = stw[3];
-      tw = tdap_refresh<T, FAST>(z, stw[2], sp.l1_w, sp.l2_w);
+      const T z = tdap_state<T, FAST>(tw, Gw, stw[0], stw[1 % NST], stw[2 % NST], stw[3 % NST], sp.alpha_w, sp.egamma);
+      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1 % NST]; a.sw[2][c] = stw[2 % NST]; a.sw[3][c] = stw[3 % NST];
+      tw = tdap_refresh<T, FAST>(z, stw[2 % NST], sp.l1_w, sp.l2_w);
     }
     a.w[c] = tw;
   }
   // ---- factors
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
-    const int vi = ch * LPR + l;
     if (SOLVER == FMWR_SGD) {
       T q[VN];
-      if (sp.l1) vec_to_arr(raw_st[0][ch], q);
+      if (L1) vec_to_arr(raw_st[0][ch], q);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
-        T qq = sp.l1 ? q[i] : T(0);
-        th[ch][i] = sgd_step(th[ch][i], Gv[ch][i], sp.lr, sp.reg_v, sp.l1, a.u_v, qq);
-        if (sp.l1) q[i] = qq;
+        T qq = L1 ? q[i] : T(0);
+        th[ch][i] = sgd_step(th[ch][i], Gv[ch][i], sp.lr, sp.reg_v, L1 ? 1 : 0, a.u_v, qq);
+        if (L1) q[i] = qq;
       }
-      if (sp.l1) reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(q);
+      if (L1) reinterpret_cast<V16*>(a.sv[0] + off)[ch * LPR] = arr_to_vec(q);
     } else if (SOLVER == FMWR_FTRL) {
       T z[VN], nn[VN];
-      vec_to_arr(raw_st[0][ch], z); vec_to_arr(raw_st[1][ch], nn);
+      vec_to_arr(raw_st[0][ch], z); vec_to_arr(raw_st[1 % NST][ch], nn);
 #pragma unroll
       for (int i = 0; i < VN; ++i) th[ch][i] = ftrl_step<T, FAST>(th[ch][i], Gv[ch][i], z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
-      reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(z);
-      reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp)[vi] = arr_to_vec(nn);
+      reinterpret_cast<V16*>(a.sv[0] + off)[ch * LPR] = arr_to_vec(z);
+      reinterpret_cast<V16*>(a.sv[1] + off)[ch * LPR] = arr_to_vec(nn);
     } else {
       T u[VN], nu[VN], dl[VN], h[VN];
-      vec_to_arr(raw_st[0][ch], u); vec_to_arr(raw_st[1][ch], nu); vec_to_arr(raw_st[2][ch], dl); vec_to_arr(raw_st[3][ch], h);
+      vec_to_arr(raw_st[0][ch], u); vec_to_arr(raw_st[1 % NST][ch], nu); vec_to_arr(raw_st[2 % NST][ch], dl); vec_to_arr(raw_st[3 % NST][ch], h);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         const T z = tdap_state<T, FAST>(th[ch][i], Gv[ch][i], u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
         th[ch][i] = tdap_refresh<T, FAST>(z, dl[i], sp.l1_v, sp.l2_v);
       }
-      reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp)[vi] = arr_to_vec(u);
-      reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp)[vi] = arr_to_vec(nu);
-      reinterpret_cast<V16*>(a.sv[2] + (size_t)c * kp)[vi] = arr_to_vec(dl);
-      reinterpret_cast<V16*>(a.sv[3] + (size_t)c * kp)[vi] = arr_to_vec(h);
+      reinterpret_cast<V16*>(a.sv[0] + off)[ch * LPR] = arr_to_vec(u);
+      reinterpret_cast<V16*>(a.sv[1] + off)[ch * LPR] = arr_to_vec(nu);
+      reinterpret_cast<V16*>(a.sv[2] + off)[ch * LPR] = arr_to_vec(dl);
+      reinterpret_cast<V16*>(a.sv[3] + off)[ch * LPR] = arr_to_vec(h);
     }
-    vr[vi] = arr_to_vec(th[ch]);
+    vr[ch * LPR] = arr_to_vec(th[ch]);
   }
 }
 
@@ -327,25 +327,39 @@ struct MbLaunch {
   fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; const fmwr_solver_cfg* s;
   int64_t row_begin; int rows; T* mult; T* Scache; MbUpdArgs<T> ua; int phase;   // phase 0: K1, 1: K2
   int s_stride; int partial;
+  template <class TT, int LPR, int CH, int TEAM> void k1();
   template <class TT, int LPR, int CH>
   void run()
   {
     if (phase == 0) {
-      FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH>), ceil_div(rows, 8), 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
-                  (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
-                  m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial);
+      if (short_rows(d->nnz, d->n, LPR)) k1<TT, LPR, CH, LPR>();
+      else k1<TT, LPR, CH, 32>();
     } else {
       constexpr int G = 32 / LPR;
       const uint32_t nseg = ua.seg_end - ua.seg_begin;
       const int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
       switch (s->solver) {
-        case FMWR_SGD: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD>), grid, 256, 0, ua); break;
-        case FMWR_FTRL: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_FTRL>), grid, 256, 0, ua); break;
-        default: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_TDAP>), grid, 256, 0, ua); break;
+        case FMWR_SGD:
+          if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, true>), grid, 256, 0, ua);
+          else FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, false>), grid, 256, 0, ua);
+          break;
+        case FMWR_FTRL: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_FTRL, false>), grid, 256, 0, ua); break;
+        default: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_TDAP, false>), grid, 256, 0, ua); break;
       }
     }
   }
 };
+
+template <class T>
+template <class TT, int LPR, int CH, int TEAM>
+void MbLaunch<T>::k1()
+{
+  const int rpb = 8 * (32 / TEAM);
+  const int fgrid = (int)std::min<int64_t>(ceil_div(rows, rpb), (int64_t)ctx->sm_count * 16);
+  FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH, TEAM>), fgrid, 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
+              (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
+              m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial);
+}
 
 template <class T>
 static SolverParams<T> params_from(const SolverParams<double>& d)
@@ -383,6 +397,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   const int s_stride = multi ? m->kp + 4 : m->kp;
   DBuf<T> mult, Scache;
   mult.alloc(B);
+  FMWR_REQUIRE((uint64_t)B * (uint64_t)s_stride < (1ull << 32), FMWR_ERR_UNSUPPORTED, "batch_size x factors too large (the S cache is indexed with 32 bits)");
   Scache.alloc((size_t)B * s_stride);
   if (multi) FMWR_CUDA(cudaMemsetAsync(Scache.p, 0, Scache.bytes(), ctx->stream));
 
@@ -394,8 +409,6 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   ua.mult = mult.p; ua.Scache = Scache.p;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
-  ua.seg_total = (uint32_t)d->mb_batch_seg[n_batches];
-  { const char* e = getenv("FMWR_K2_PF"); ua.pf_dist = e ? (uint32_t)atoi(e) : 32768u; }
   ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1; ua.s_stride = s_stride;
   ua.sp = params_from<T>(spd);
 

@@ -37,11 +37,16 @@ __device__ __forceinline__ double2 ld_nc_v16(const double2* p)
 // handful of non-zeros, 32/LPR rows per warp).  The team is NG = TEAM/LPR sub-groups; sub-group sg fetches entries
 // sg, sg + NG, ... of the row, U factor rows in flight.  These kernels are instruction-issue bound, so the loop is
 // written for instruction count: immediate-offset loads off a running pointer, an unpredicated path for full
-// batches, ONE scalar for sum_f Q_f (each (entry, factor) product lives in exactly one lane), the linear term on
-// a coalesced sweep of the row.
+// batches, the linear term on a coalesced sweep of the row.
 //
-// Returns this lane's share of  lin - 1/2 sum Q (+ 1/2 sum_f S_f^2 when with_pair, counted in sub-group 0);
-// the caller sums it over the team (team_sum).  On return S[ch][i] is the complete S_f for factor
+// The pairwise term is accumulated WITHOUT the reference's cancellation 1/2 (S_f^2 - Q_f)
+// (src/core/Model.h:144-158): P_f += t * S_f before S_f += t gives sum_{i<j} t_i t_j directly, and the cross terms
+// between sub-groups are S_a * S_b at every combine stage.  Same number of instructions, and fp32 stays within
+// 1e-5 of the fp64 reference for any k.
+//
+// Returns this lane's share of  lin + sum_f P_f  (with_pair), or of the ADDITIVE part
+// lin + sum_f P_f - 1/2 sum_f S_f^2  of a column slice (!with_pair: 1/2 sum_f S_f^2 is formed after the slices'
+// S_f have been summed); the caller sums it over the team (team_sum).  On return S[ch][i] is the complete S_f for factor
 // (ch*LPR + l)*VN + i in every sub-group of the team.
 template <class T, int LPR, int CH, int TEAM, int U>
 __device__ __forceinline__ T team_gather(const uint32_t* __restrict__ col, const float* __restrict__ val, uint32_t b,
@@ -58,7 +63,10 @@ __device__ __forceinline__ T team_gather(const uint32_t* __restrict__ col, const
   for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
     for (int i = 0; i < VN; ++i) S[ch][i] = T(0);
-  T q = T(0), lin = T(0);
+  T P[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) P[i] = T(0);
+  T lin = T(0);
   if (k1) {
 #pragma unroll 1
     for (uint32_t j = b + tl; j < e; j += TEAM) lin += w[__ldg(col + j)] * T(__ldg(val + j));
@@ -92,8 +100,8 @@ __device__ __forceinline__ T team_gather(const uint32_t* __restrict__ col, const
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
           const T t = a[i] * x[u];
+          P[i] += t * S[ch][i];
           S[ch][i] += t;
-          q += t * t;
         }
       }
   }
@@ -129,32 +137,35 @@ __device__ __forceinline__ T team_gather(const uint32_t* __restrict__ col, const
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
           const T t = a[i] * x[u];
+          P[i] += t * S[ch][i];
           S[ch][i] += t;
-          q += t * t;
         }
       }
   }
-  // combine the sub-groups.  q goes along so that sub-group 0 ends up with  sum_f S_f^2  AND  sum_f Q_f  of the same
-  // few factors: the two nearly cancel, and cancelling them inside one lane (instead of across the team sum) keeps
-  // the fp32 result within 1e-5 of the fp64 reference even for k = 128.
+  // combine the sub-groups: partners a, b add 1/2^(stage+1) S_a S_b each (2^(stage+1) lanes hold the same product)
+  T wgt = T(0.5);
 #pragma unroll
   for (int o = LPR; o < TEAM; o <<= 1) {
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-      for (int i = 0; i < VN; ++i) S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
+      for (int i = 0; i < VN; ++i) {
+        const T other = __shfl_xor_sync(0xffffffffu, S[ch][i], o);
+        P[i] += wgt * (S[ch][i] * other);
+        S[ch][i] += other;
+      }
+    wgt *= T(0.5);
   }
   T part = lin;
-  if (sg == 0) {
-    T pair = -q;
-    if (with_pair) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
+  for (int i = 0; i < VN; ++i) part += P[i];
+  if (!with_pair && sg == 0) {
+    T sq = T(0);
 #pragma unroll
-        for (int i = 0; i < VN; ++i) pair += S[ch][i] * S[ch][i];
-    }
-    part += T(0.5) * pair;
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) sq += S[ch][i] * S[ch][i];
+    part -= T(0.5) * sq;
   }
   return part;
 }

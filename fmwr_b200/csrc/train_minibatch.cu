@@ -56,7 +56,7 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
       if (tl == 0 && r < rows) mult[r] = grad_mult_fast(task, score, T(__ldg(y + row)), lo, hi);
     } else {
       // feature-parallel: this rank holds a column slice, so the row's score is not known yet.  Emit the partials:
-      // S_f of the slice and the additive scalar (lin - 1/2 sum Q); 1/2 sum S_f^2 is formed after the exchange
+      // S_f of the slice and its additive scalar (see team_gather); 1/2 sum S_f^2 is formed after the exchange
       const T addend = team_forward_partial<T, LPR, CH, TEAM>(col, val, b, e, w, v, kp, k1, S);
       if (tl == 0 && r < rows) Scache[(size_t)r * s_stride + kp] = addend;
     }
@@ -101,122 +101,139 @@ struct MbUpdArgs {
   T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
 };
 
+// the intercept (dense coordinate): fixed-order reduction of the batch's multipliers by ONE block.  It is block 0 so
+// that its serial chain of loads overlaps the rest of the grid instead of forming the kernel's tail.
+template <class T, int SOLVER>
+__device__ __forceinline__ void mb_intercept(const MbUpdArgs<T>& a)
+{
+  const SolverParams<T>& sp = a.sp;
+  __shared__ double red[8];
+  double acc = 0.0;
+  {
+    constexpr int UN = 16;
+    int r = threadIdx.x;
+    for (; r + (UN - 1) * 256 < a.rows; r += UN * 256) {
+      T t[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) t[u] = a.mult[r + u * 256];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) acc += (double)t[u];
+    }
+    for (; r < a.rows; r += 256) acc += (double)a.mult[r];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double gsum = 0;
+    for (int i = 0; i < 8; ++i) gsum += red[i];
+    double* sc = a.scal;
+    if (SOLVER == FMWR_SGD) {
+      if (a.k0) sc[0] -= (double)sp.lr * (gsum / (double)a.rows + (double)sp.reg_w0 * sc[0]);
+    } else if (SOLVER == FMWR_FTRL) {
+      if (a.k0) {
+        const double old = sc[2];
+        sc[2] += gsum * gsum;
+        const double delta = (sqrt(sc[2]) - sqrt(old)) / (double)sp.alpha_w;
+        sc[1] += gsum - delta * sc[0];
+      }
+      sc[0] = -sc[1] * (double)sp.alpha_w / ((double)sp.beta_w + sqrt(sc[2]));
+    } else {
+      if (a.k0) {
+        const double old = sc[1];
+        sc[1] += gsum * gsum; sc[2] += gsum;
+        const double sigma = (sqrt(sc[1]) - sqrt(old)) / (double)sp.alpha_w;
+        sc[3] = (double)sp.egamma * (sc[3] + sigma);
+        sc[4] = (double)sp.egamma * (sc[4] + sigma * sc[0]);
+        sc[5] = sc[2] - sc[4];
+      }
+      sc[0] = -sc[5] / sc[3];
+    }
+  }
+}
+
+// Everything a segment needs that depends only on its 16-byte record {feature, length, first row, first value}:
+// the parameter row, its optimizer state, the first row's S-cache line and multiplier, and the next LPR entries
+// of the segment (lane l fetches entry 1 + l).  seg_issue requests all of it in one go; seg_finish consumes it.
+template <class T, int CH, int NST>
+struct SegStage {
+  typename Vec<T>::type th[CH], s0[CH], st[NST][CH];
+  T m0, tw, stw[NST];
+  uint32_t c, len, eb, r0, my_r;
+  float x0, my_x;
+  bool live;
+};
+
 template <class T, int LPR, int CH, int SOLVER, bool L1>
-__global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
+__device__ __forceinline__ void seg_issue(const MbUpdArgs<T>& a, const uint4 rec, const uint32_t eb, const int l, bool live,
+                                          SegStage<T, CH, (SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4))>& sg)
 {
   typedef typename Vec<T>::type V16;
   constexpr int VN = Vec<T>::N;
-  constexpr int G = 32 / LPR;
-  constexpr bool FAST = sizeof(T) == 4;
-  const SolverParams<T> sp = a.sp;
-
-  // block 0: the intercept (dense coordinate) -- fixed-order reduction of the batch's multipliers.  It is the FIRST
-  // block so that its serial chain of loads overlaps the rest of the grid instead of forming the kernel's tail.
-  if (blockIdx.x == 0) {
-    __shared__ double red[8];
-    double acc = 0.0;
-    {
-      constexpr int UN = 16;
-      int r = threadIdx.x;
-      for (; r + (UN - 1) * 256 < a.rows; r += UN * 256) {
-        T t[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) t[u] = a.mult[r + u * 256];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) acc += (double)t[u];
-      }
-      for (; r < a.rows; r += 256) acc += (double)a.mult[r];
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double gsum = 0;
-      for (int i = 0; i < 8; ++i) gsum += red[i];
-      double* sc = a.scal;
-      if (SOLVER == FMWR_SGD) {
-        if (a.k0) sc[0] -= (double)sp.lr * (gsum / (double)a.rows + (double)sp.reg_w0 * sc[0]);
-      } else if (SOLVER == FMWR_FTRL) {
-        if (a.k0) {
-          const double old = sc[2];
-          sc[2] += gsum * gsum;
-          const double delta = (sqrt(sc[2]) - sqrt(old)) / (double)sp.alpha_w;
-          sc[1] += gsum - delta * sc[0];
-        }
-        sc[0] = -sc[1] * (double)sp.alpha_w / ((double)sp.beta_w + sqrt(sc[2]));
-      } else {
-        if (a.k0) {
-          const double old = sc[1];
-          sc[1] += gsum * gsum; sc[2] += gsum;
-          const double sigma = (sqrt(sc[1]) - sqrt(old)) / (double)sp.alpha_w;
-          sc[3] = (double)sp.egamma * (sc[3] + sigma);
-          sc[4] = (double)sp.egamma * (sc[4] + sigma * sc[0]);
-          sc[5] = sc[2] - sc[4];
-        }
-        sc[0] = -sc[5] / sc[3];
-      }
-    }
-    return;
-  }
-
-  const int lane = threadIdx.x & 31;
-  const int g = lane / LPR, l = lane % LPR;
-  const uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
-  if (seg >= a.seg_end) return;
-  // one 16-byte record: {feature, length, first row, first value}; everything below depends only on it, so the
-  // parameter row, its optimizer state, the first row's cache line and the segment's entry list are all requested
-  // in the same round trip: three dependent memory rounds per segment whatever its length
-  const uint4 rec = __ldg(a.seg_rec + seg);
-  const uint32_t eb = __ldg(a.seg_ptr + seg);
-  const uint32_t c = rec.x, len = rec.y;
-  const uint32_t rb32 = (uint32_t)a.row_begin, nrows = (uint32_t)a.rows;
-  const uint32_t r0 = rec.z - rb32;
-  if (r0 >= nrows) return;                        // rows ascend inside a segment: nothing of it is in the (truncated) batch
-
   constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
   constexpr bool USE_STATE = SOLVER != FMWR_SGD || L1;
+  sg.c = rec.x; sg.len = rec.y; sg.eb = eb; sg.x0 = __uint_as_float(rec.w);
+  sg.r0 = rec.z - (uint32_t)a.row_begin;
+  live = live && sg.r0 < (uint32_t)a.rows;        // rows ascend inside a segment: r0 outside = nothing of it in the (truncated) batch
+  sg.live = live;
+  sg.my_r = 0xffffffffu;                          // sentinel: (0xffffffff - row_begin) is never < rows
+  sg.my_x = 0.f;
+  sg.tw = T(0); sg.m0 = T(0);
+#pragma unroll
+  for (int st = 0; st < NST; ++st) sg.stw[st] = T(0);
+  if (!live) return;
+  const size_t off = (size_t)sg.c * a.kp + l * VN;
+  const T* sbase = a.Scache + l * VN + sg.r0 * (uint32_t)a.s_stride;
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    sg.th[ch] = reinterpret_cast<const V16*>(a.v + off)[ch * LPR];
+    sg.s0[ch] = reinterpret_cast<const V16*>(sbase)[ch * LPR];
+    if (USE_STATE) {
+#pragma unroll
+      for (int st = 0; st < NST; ++st) sg.st[st][ch] = reinterpret_cast<const V16*>(a.sv[st] + off)[ch * LPR];
+    }
+  }
+  sg.m0 = a.mult[sg.r0];
+  if (a.k1 && l == 0) {
+    sg.tw = a.w[sg.c];
+    if (USE_STATE) {
+#pragma unroll
+      for (int st = 0; st < NST; ++st) sg.stw[st] = a.sw[st][sg.c];
+    }
+  }
+  if (1u + (uint32_t)l < sg.len) { sg.my_r = __ldg(a.ent_row + eb + 1 + l); sg.my_x = __ldg(a.ent_val + eb + 1 + l); }
+}
+
+template <class T, int LPR, int CH, int SOLVER, bool L1>
+__device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, const int l,
+                                           SegStage<T, CH, (SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4))>& sg)
+{
+  typedef typename Vec<T>::type V16;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+  constexpr bool FAST = sizeof(T) == 4;
   // TDAP keeps the per-entry gradient form of the exact mode (see fm_grad: a rounding residue flips theta by +-alpha);
   // SGD / FTRL sum  A_f = sum_r (m_r x_r) S_rf  and  b = sum_r m_r x_r^2  and form  G_f = A_f - v_f b  once
   constexpr bool ENTRY_FORM = SOLVER == FMWR_TDAP;
+  if (!sg.live) return;
+  const SolverParams<T>& sp = a.sp;
+  const uint32_t c = sg.c, len = sg.len, eb = sg.eb;
+  const uint32_t rb32 = (uint32_t)a.row_begin, nrows = (uint32_t)a.rows;
   const size_t off = (size_t)c * a.kp + l * VN;
-  V16* vr = reinterpret_cast<V16*>(a.v + off);
-  V16 raw_th[CH], raw_s0[CH], raw_st[NST][CH];
-  const uint32_t lofs = l * VN;
-  const T* sbase = a.Scache + lofs;
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch) {
-    raw_th[ch] = vr[ch * LPR];
-    raw_s0[ch] = reinterpret_cast<const V16*>(sbase + r0 * (uint32_t)a.s_stride)[ch * LPR];
-    if (USE_STATE) {
-#pragma unroll
-      for (int st = 0; st < NST; ++st) raw_st[st][ch] = reinterpret_cast<const V16*>(a.sv[st] + off)[ch * LPR];
-    }
-  }
-  const T m0 = a.mult[r0];
-  T tw = T(0), stw[NST];
-#pragma unroll
-  for (int st = 0; st < NST; ++st) stw[st] = T(0);
-  if (a.k1 && l == 0) {
-    tw = a.w[c];
-    if (USE_STATE) {
-#pragma unroll
-      for (int st = 0; st < NST; ++st) stw[st] = a.sw[st][c];
-    }
-  }
+  const T* sbase = a.Scache + l * VN;
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
-  uint32_t my_r = 0xffffffffu;                    // sentinel: (0xffffffff - row_begin) is never < rows
-  float my_x = 0.f;
-  if (1u + (uint32_t)l < len) { my_r = __ldg(a.ent_row + eb + 1 + l); my_x = __ldg(a.ent_val + eb + 1 + l); }
+  uint32_t my_r = sg.my_r;
+  float my_x = sg.my_x;
 
   T th[CH][VN], Gv[CH][VN], G1[CH][VN];
-  const T x0 = T(__uint_as_float(rec.w));
+  const T x0 = T(sg.x0), m0 = sg.m0;
   const T mx0 = m0 * x0;
   T Gw = mx0, bsum = mx0 * x0;
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
     T s[VN];
-    vec_to_arr(raw_th[ch], th[ch]);
-    vec_to_arr(raw_s0[ch], s);
+    vec_to_arr(sg.th[ch], th[ch]);
+    vec_to_arr(sg.s0[ch], s);
 #pragma unroll
     for (int k2 = 0; k2 < VN; ++k2) {
       G1[ch][k2] = m0 * fm_grad(s[k2], th[ch][k2], x0);            // the exact-mode form: what a one-entry segment uses
@@ -271,17 +288,18 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
 
   // ---- linear weight (lane 0 of the group)
   if (a.k1 && l == 0) {
+    T tw = sg.tw;
     if (SOLVER == FMWR_SGD) {
-      T q = stw[0];
+      T q = sg.stw[0];
       tw = sgd_step(tw, Gw, sp.lr, sp.reg_w, L1 ? 1 : 0, a.u_w, q);
       if (L1) a.sw[0][c] = q;
     } else if (SOLVER == FMWR_FTRL) {
-      tw = ftrl_step<T, FAST>(tw, Gw, stw[0], stw[1 % NST], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
-      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1 % NST];
+      tw = ftrl_step<T, FAST>(tw, Gw, sg.stw[0], sg.stw[1 % NST], sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
+      a.sw[0][c] = sg.stw[0]; a.sw[1][c] = sg.stw[1 % NST];
     } else {
-      const T z = tdap_state<T, FAST>(tw, Gw, stw[0], stw[1 % NST], stw[2 % NST], stw[3 % NST], sp.alpha_w, sp.egamma);
-      a.sw[0][c] = stw[0]; a.sw[1][c] = stw[1 % NST]; a.sw[2][c] = stw[2 % NST]; a.sw[3][c] = stw[3 % NST];
-      tw = tdap_refresh<T, FAST>(z, stw[2 % NST], sp.l1_w, sp.l2_w);
+      const T z = tdap_state<T, FAST>(tw, Gw, sg.stw[0], sg.stw[1 % NST], sg.stw[2 % NST], sg.stw[3 % NST], sp.alpha_w, sp.egamma);
+      a.sw[0][c] = sg.stw[0]; a.sw[1][c] = sg.stw[1 % NST]; a.sw[2][c] = sg.stw[2 % NST]; a.sw[3][c] = sg.stw[3 % NST];
+      tw = tdap_refresh<T, FAST>(z, sg.stw[2 % NST], sp.l1_w, sp.l2_w);
     }
     a.w[c] = tw;
   }
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
   for (int ch = 0; ch < CH; ++ch) {
     if (SOLVER == FMWR_SGD) {
       T q[VN];
-      if (L1) vec_to_arr(raw_st[0][ch], q);
+      if (L1) vec_to_arr(sg.st[0][ch], q);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         T qq = L1 ? q[i] : T(0);
@@ -300,14 +318,14 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       if (L1) reinterpret_cast<V16*>(a.sv[0] + off)[ch * LPR] = arr_to_vec(q);
     } else if (SOLVER == FMWR_FTRL) {
       T z[VN], nn[VN];
-      vec_to_arr(raw_st[0][ch], z); vec_to_arr(raw_st[1 % NST][ch], nn);
+      vec_to_arr(sg.st[0][ch], z); vec_to_arr(sg.st[1 % NST][ch], nn);
 #pragma unroll
       for (int i = 0; i < VN; ++i) th[ch][i] = ftrl_step<T, FAST>(th[ch][i], Gv[ch][i], z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
       reinterpret_cast<V16*>(a.sv[0] + off)[ch * LPR] = arr_to_vec(z);
       reinterpret_cast<V16*>(a.sv[1] + off)[ch * LPR] = arr_to_vec(nn);
     } else {
       T u[VN], nu[VN], dl[VN], h[VN];
-      vec_to_arr(raw_st[0][ch], u); vec_to_arr(raw_st[1 % NST][ch], nu); vec_to_arr(raw_st[2 % NST][ch], dl); vec_to_arr(raw_st[3 % NST][ch], h);
+      vec_to_arr(sg.st[0][ch], u); vec_to_arr(sg.st[1 % NST][ch], nu); vec_to_arr(sg.st[2 % NST][ch], dl); vec_to_arr(sg.st[3 % NST][ch], h);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         const T z = tdap_state<T, FAST>(th[ch][i], Gv[ch][i], u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
@@ -318,7 +336,60 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
       reinterpret_cast<V16*>(a.sv[2] + off)[ch * LPR] = arr_to_vec(dl);
       reinterpret_cast<V16*>(a.sv[3] + off)[ch * LPR] = arr_to_vec(h);
     }
-    vr[ch * LPR] = arr_to_vec(th[ch]);
+    reinterpret_cast<V16*>(a.v + off)[ch * LPR] = arr_to_vec(th[ch]);
+  }
+}
+
+// one lane group per segment, one segment per group (generic: any layout, TDAP)
+template <class T, int LPR, int CH, int SOLVER, bool L1>
+__global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
+{
+  constexpr int G = 32 / LPR;
+  constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+  if (blockIdx.x == 0) { mb_intercept<T, SOLVER>(a); return; }
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
+  if (seg >= a.seg_end) return;
+  const uint4 rec = __ldg(a.seg_rec + seg);
+  const uint32_t eb = __ldg(a.seg_ptr + seg);
+  SegStage<T, CH, NST> sg;
+  seg_issue<T, LPR, CH, SOLVER, L1>(a, rec, eb, l, true, sg);
+  seg_finish<T, LPR, CH, SOLVER, L1>(a, g, l, sg);
+}
+
+// Persistent, software-pipelined variant (SGD / FTRL, one 16-byte chunk per lane): a group walks the segments
+// seg, seg + stride, ...; while it finishes segment i, the rows of segment i+1 and the record of segment i+2 are
+// already in flight, so a segment exposes one memory round (the other rows' S-cache lines) instead of three.
+// Two segments of one batch never share a coordinate, so fetching the next parameter row early is safe.
+template <class T, int LPR, int SOLVER, bool L1, int BLOCKS>
+__global__ void __launch_bounds__(256, BLOCKS) mb_update_pipe_kernel(MbUpdArgs<T> a)
+{
+  constexpr int G = 32 / LPR;
+  constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+  if (blockIdx.x == 0) { mb_intercept<T, SOLVER>(a); return; }
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const uint32_t stride = (gridDim.x - 1) * (blockDim.x >> 5) * G;
+  uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
+  if (seg >= a.seg_end) return;
+  SegStage<T, 1, NST> cur, nxt;
+  uint4 rec2 = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t eb2 = 0u;
+  {
+    const uint4 rec = __ldg(a.seg_rec + seg);
+    const uint32_t eb = __ldg(a.seg_ptr + seg);
+    if (seg + stride < a.seg_end) { rec2 = __ldg(a.seg_rec + seg + stride); eb2 = __ldg(a.seg_ptr + seg + stride); }
+    seg_issue<T, LPR, 1, SOLVER, L1>(a, rec, eb, l, true, cur);
+  }
+  while (true) {
+    const bool has_next = seg + stride < a.seg_end;           // group-uniform
+    seg_issue<T, LPR, 1, SOLVER, L1>(a, rec2, eb2, l, has_next, nxt);
+    if (seg + 2 * stride < a.seg_end) { rec2 = __ldg(a.seg_rec + seg + 2 * stride); eb2 = __ldg(a.seg_ptr + seg + 2 * stride); }
+    seg_finish<T, LPR, 1, SOLVER, L1>(a, g, l, cur);
+    if (!has_next) break;
+    cur = nxt;
+    seg += stride;
   }
 }
 
@@ -338,7 +409,12 @@ struct MbLaunch {
       constexpr int G = 32 / LPR;
       const uint32_t nseg = ua.seg_end - ua.seg_begin;
       const int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
-      switch (s->solver) {
+      // persistent pipelined kernel: 3 resident CTAs per SM
+      const int pblocks = s->solver == FMWR_SGD && !ua.sp.l1 ? 3 : 2;      // measured: SGD likes occupancy, FTRL registers
+      const int pgrid = (int)std::min<int64_t>(grid, (int64_t)ctx->sm_count * pblocks + 1);
+      const bool pipe = CH == 1 && s->solver != FMWR_TDAP && getenv("FMWR_K2_NOPIPE") == nullptr;
+      if (pipe) launch_pipe<TT, LPR>(pgrid);
+      else switch (s->solver) {
         case FMWR_SGD:
           if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, true>), grid, 256, 0, ua);
           else FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, false>), grid, 256, 0, ua);
@@ -346,6 +422,16 @@ struct MbLaunch {
         case FMWR_FTRL: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_FTRL, false>), grid, 256, 0, ua); break;
         default: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_TDAP, false>), grid, 256, 0, ua); break;
       }
+    }
+  }
+  template <class TT, int LPR>
+  void launch_pipe(int pgrid)
+  {
+    if (s->solver == FMWR_SGD) {
+      if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_pipe_kernel<TT, LPR, FMWR_SGD, true, 2>), pgrid, 256, 0, ua);
+      else FMWR_LAUNCH(ctx, (mb_update_pipe_kernel<TT, LPR, FMWR_SGD, false, 3>), pgrid, 256, 0, ua);
+    } else {
+      FMWR_LAUNCH(ctx, (mb_update_pipe_kernel<TT, LPR, FMWR_FTRL, false, 2>), pgrid, 256, 0, ua);
     }
   }
 };

@@ -311,6 +311,7 @@ int fmwr_ctx_create(int device, fmwr_ctx** out)
     try {
       c->device = device;
       c->sm_count = prop.multiProcessorCount;
+      if (prop.sharedMemPerBlockOptin > 0) c->smem_optin = (int)prop.sharedMemPerBlockOptin;
       FMWR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       FMWR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
       FMWR_CUDA(cudaEventCreate(&c->ev0));

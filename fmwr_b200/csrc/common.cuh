@@ -117,6 +117,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 struct fmwr_ctx {
   int device = 0;
   int sm_count = 148;
+  int smem_optin = 227 * 1024;   // largest dynamic shared memory a CTA may opt in to
   cudaStream_t stream = nullptr;       // compute stream
   cudaStream_t copy_stream = nullptr;  // H2D / D2H staging
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

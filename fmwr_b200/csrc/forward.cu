@@ -5,7 +5,7 @@
 namespace fmwr {
 
 template <class T, int LPR, int CH, int TEAM>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, FMWR_FWD_BLOCKS)
 forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                const T* __restrict__ w, const T* __restrict__ v, const double* __restrict__ scal, int kp, int k0, int k1,
                int64_t n, int link, double lo, double hi, const double* __restrict__ pnY, double* __restrict__ out)

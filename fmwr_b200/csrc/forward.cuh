@@ -178,7 +178,14 @@ __device__ __forceinline__ T team_sum(T x)
   return x;
 }
 
-template <int LPR> struct GatherDepth { enum { U = LPR >= 16 ? 8 : 4 }; };
+#ifndef FMWR_FWD_U
+#define FMWR_FWD_U 4
+#endif
+#ifndef FMWR_FWD_BLOCKS
+#define FMWR_FWD_BLOCKS 4
+#endif
+// factor rows in flight per sub-group: long rows (warp team) take the experiment knobs, short rows 4
+template <int LPR, int TEAM = 32> struct GatherDepth { enum { U = LPR >= 16 ? 8 : (TEAM == 32 ? FMWR_FWD_U : 4) }; };
 
 // score (no link) of the team's row, identical in every lane of the team
 template <class T, int LPR, int CH, int TEAM>
@@ -186,7 +193,7 @@ __device__ __forceinline__ T team_forward(const uint32_t* __restrict__ col, cons
                                           uint32_t e, const T* __restrict__ w, const T* __restrict__ v, int kp, T w0,
                                           int k0, int k1, T (&S)[CH][Vec<T>::N])
 {
-  const T part = team_gather<T, LPR, CH, TEAM, GatherDepth<LPR>::U>(col, val, b, e, w, v, kp, k1, true, S);
+  const T part = team_gather<T, LPR, CH, TEAM, GatherDepth<LPR, TEAM>::U>(col, val, b, e, w, v, kp, k1, true, S);
   return (k0 ? w0 : T(0)) + team_sum<T, TEAM>(part);
 }
 
@@ -197,7 +204,7 @@ __device__ __forceinline__ T team_forward_partial(const uint32_t* __restrict__ c
                                                   uint32_t b, uint32_t e, const T* __restrict__ w,
                                                   const T* __restrict__ v, int kp, int k1, T (&S)[CH][Vec<T>::N])
 {
-  const T part = team_gather<T, LPR, CH, TEAM, GatherDepth<LPR>::U>(col, val, b, e, w, v, kp, k1, false, S);
+  const T part = team_gather<T, LPR, CH, TEAM, GatherDepth<LPR, TEAM>::U>(col, val, b, e, w, v, kp, k1, false, S);
   return team_sum<T, TEAM>(part);
 }
 

@@ -25,6 +25,10 @@ double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solv
 void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
 int tracker_step_size(int step_size, int max_iter);
 
+template <class T> struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<double> { typedef double2 type; };
+
 constexpr int ALS_LONG = 4096;      // columns at least this long get a whole CTA
 
 // ---- forward: e = raw score, q[r][:] = S_f -----------------------------------------------------------
@@ -221,6 +225,64 @@ __global__ void als_reduce_kernel(const T* __restrict__ x, int64_t n, int64_t st
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
     part[blockIdx.x] = s;
   }
+}
+
+// all factors at once: part[blk][f] = sum_c V[c][f], part[blk][kp + f] = sum_c (V[c][f] - mu[f])^2 over the block's
+// columns.  One launch and one host round trip replace 2k of them in the MCMC hyper-prior step; the block partials are
+// summed on the host in block order, so the result is deterministic.
+template <class T>
+__global__ void __launch_bounds__(256) als_reduce_v_kernel(const T* __restrict__ v, int64_t p, int kp, const double* __restrict__ mu,
+                                                           int64_t cols_per_block, double* __restrict__ part)
+{
+  __shared__ double s1[256], s2[256];
+  const int lanes_f = kp < 256 ? kp : 256;
+  const int rows_par = 256 / lanes_f;
+  const int my_f0 = threadIdx.x % lanes_f, my_r = threadIdx.x / lanes_f;
+  const int64_t c0 = (int64_t)blockIdx.x * cols_per_block, c1 = c0 + cols_per_block < p ? c0 + cols_per_block : p;
+  for (int fo = 0; fo < kp; fo += lanes_f) {
+    const int f = fo + my_f0;
+    double a1 = 0.0, a2 = 0.0;
+    if (f < kp && my_r < rows_par) {
+      const double m = mu[f];
+      for (int64_t c = c0 + my_r; c < c1; c += rows_par) {
+        const double x = (double)v[c * kp + f];
+        a1 += x; a2 += (x - m) * (x - m);
+      }
+    }
+    s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
+    __syncthreads();
+    if (my_r == 0 && f < kp) {
+      for (int r = 1; r < rows_par; ++r) { a1 += s1[r * lanes_f + my_f0]; a2 += s2[r * lanes_f + my_f0]; }
+      part[(size_t)blockIdx.x * 2 * kp + f] = a1;
+      part[(size_t)blockIdx.x * 2 * kp + kp + f] = a2;
+    }
+    __syncthreads();
+  }
+}
+
+// sums[f] = sum_c V[c][f], sq[f] = sum_c (V[c][f] - mu[f])^2, row0[f] = V[0][f]
+template <class T>
+static void reduce_v_all(fmwr_ctx* ctx, const T* v, int64_t p, int k, int kp, const std::vector<double>& mu, std::vector<double>& sums,
+                         std::vector<double>& sq, std::vector<double>& row0)
+{
+  sums.assign(k, 0.0); sq.assign(k, 0.0); row0.assign(k, 0.0);
+  if (p <= 0 || k <= 0) return;
+  const int nblk = (int)std::min<int64_t>(256, std::max<int64_t>(1, ceil_div64(p, 512)));
+  const int64_t cpb = ceil_div64(p, nblk);
+  DBuf<double> mu_dev, part;
+  mu_dev.alloc(kp); part.alloc((size_t)nblk * 2 * kp);
+  std::vector<double> hm(kp, 0.0);
+  for (int f = 0; f < k; ++f) hm[f] = mu[f];
+  FMWR_CUDA(cudaMemcpyAsync(mu_dev.p, hm.data(), 8 * kp, cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_LAUNCH(ctx, als_reduce_v_kernel<T>, nblk, 256, 0, v, p, kp, mu_dev.p, cpb, part.p);
+  std::vector<double> h((size_t)nblk * 2 * kp);
+  std::vector<T> r0(kp);
+  FMWR_CUDA(cudaMemcpyAsync(h.data(), part.p, 8 * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaMemcpyAsync(r0.data(), v, sizeof(T) * kp, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < nblk; ++b)
+    for (int f = 0; f < k; ++f) { sums[f] += h[(size_t)b * 2 * kp + f]; sq[f] += h[(size_t)b * 2 * kp + kp + f]; }
+  for (int f = 0; f < k; ++f) row0[f] = (double)r0[f];
 }
 
 template <class T>
@@ -426,19 +488,48 @@ struct RmArgs {
   T* e; T* q; int64_t n; int f;      // q == nullptr: w pass.  q is [kp][n]
   T* theta; int64_t theta_stride;    // w (stride 1) or V + f (stride kp)
   const uint16_t* hot; const uint32_t* hot_col; int n_hot;   // hot-feature table of the phase (indexed by global feature id)
-  T* th; T* AB; T* delta;            // per-feature scratch of the phase: th[ncols], AB[2*ncols] interleaved, delta[ncols]
+  T* th; T* AB; T* delta;            // per-feature scratch of the phase: th[ncols], AB[n_rep][2*ncols] interleaved, delta[ncols]
+  typename Vec2<T>::type* thd;       // (th, delta) interleaved: the fused passes fetch both with one gather (may be null)
+  int n_rep;                         // replicas of the AB table (0/1: one); the fused passes spread their reductions over them
   double alpha, lambda, mu;
   int do_sample, w_sd_is_var;
   const double* normals; long long n_normals, normal_base; uint64_t seed;
 };
 
+template <class T> __device__ __forceinline__ void rm_extract_one(const RmArgs<T>& a, uint32_t c);
+template <class T> __device__ __forceinline__ void rm_solve_one(const RmArgs<T>& a, uint32_t c);
+
 template <class T>
 __global__ void rm_extract_kernel(RmArgs<T> a)
 {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.ncols) return;
-  a.th[c] = a.theta[(size_t)(a.cb + c) * a.theta_stride];
-  a.AB[2 * (size_t)c] = T(0); a.AB[2 * (size_t)c + 1] = T(0);
+  if (c < a.ncols) rm_extract_one(a, c);
+}
+
+template <class T>
+__global__ void rm_solve_kernel(RmArgs<T> a)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.ncols) rm_solve_one(a, c);
+}
+
+// solve of step t and extract of step t + 1 in one launch (they touch different features and different scratch)
+template <class T>
+__global__ void rm_solve_extract_kernel(RmArgs<T> a, RmArgs<T> b)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.ncols) rm_solve_one(a, c);
+  if (c < b.ncols) rm_extract_one(b, c);
+}
+
+template <class T>
+__device__ __forceinline__ void rm_extract_one(const RmArgs<T>& a, uint32_t c)
+{
+  const T th = a.theta[(size_t)(a.cb + c) * a.theta_stride];
+  a.th[c] = th;
+  if (a.thd) a.thd[c].x = th;
+  const int R = a.n_rep > 1 ? a.n_rep : 1;
+  for (int r = 0; r < R; ++r) { a.AB[2 * ((size_t)r * a.ncols + c)] = T(0); a.AB[2 * ((size_t)r * a.ncols + c) + 1] = T(0); }
 }
 
 // A and B of a feature are interleaved (AB[2c], AB[2c+1]) so the fp32 path issues ONE 8-byte vector reduction per feature
@@ -500,13 +591,19 @@ __global__ void __launch_bounds__(256) rm_stats_kernel(RmArgs<T> a)
 }
 
 template <class T>
-__global__ void rm_solve_kernel(RmArgs<T> a)
+__device__ __forceinline__ void rm_solve_one(const RmArgs<T>& a, uint32_t c)
 {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.ncols) return;
   const double old = (double)a.th[c];
-  const double A = (double)a.AB[2 * (size_t)c];
-  double Bm = (double)a.AB[2 * (size_t)c + 1];
+  double A = 0.0, Bm = 0.0;
+  {
+    const int R = a.n_rep > 1 ? a.n_rep : 1;
+    typedef typename Vec2<T>::type V2;
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) {
+      const V2 ab = reinterpret_cast<const V2*>(a.AB)[(size_t)r * a.ncols + c];
+      A += (double)ab.x; Bm += (double)ab.y;
+    }
+  }
   if (a.q != nullptr) Bm -= old * A;                                    // reference :322
   const double var = 1.0 / (a.lambda + a.alpha * A);
   const double mean = -var * (a.alpha * Bm - a.mu * a.lambda);
@@ -522,6 +619,7 @@ __global__ void rm_solve_kernel(RmArgs<T> a)
   if (isnan(nv) || isinf(nv)) { nv = old; upd = false; }
   a.theta[(size_t)(a.cb + c) * a.theta_stride] = T(nv);
   a.delta[c] = upd ? T(old - nv) : T(0);
+  if (a.thd) a.thd[c].y = upd ? T(old - nv) : T(0);
 }
 
 template <class T>
@@ -632,105 +730,107 @@ static void run_phases_rm(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, cons
 // read by stats, then read and written again by apply: 32 instead of 48 bytes per row and step, all of it 128-bit
 // coalesced streams (4 rows per thread).
 template <class T>
-struct StepScratch { T* th; T* AB; T* delta; };
+struct StepScratch { T* th; T* AB; T* delta; typename Vec2<T>::type* thd; };
 
 template <class T>
 struct FusedArgs {
   int64_t n;
   T* e;
-  int has_prev; const uint32_t* pcol; const float* pval; const T* pth; const T* pdelta; T* pq;
+  int has_prev; const uint32_t* pcol; const float* pval; const typename Vec2<T>::type* pthd; T* pq;
   int has_cur; const uint32_t* ccol; const float* cval; const T* cth; T* cAB; T* cq;
-  uint32_t c_cb, c_ncols; const uint16_t* hot; const uint32_t* hot_col; int n_hot;
-  int cur_sorted;      // rows are sorted by the current phase's feature: equal features sit in consecutive lanes
+  uint32_t p_ncols, c_ncols; int n_rep;
 };
 
-template <class T, int MODE>
-__device__ __forceinline__ void stats_add(const FusedArgs<T>& a, T* sA, T* sB, uint32_t n_slots, uint32_t c, T sa, T sb)
-{
-  if (MODE == 1) { atomicAdd(&sA[c], sa); atomicAdd(&sB[c], sb); return; }
-  if (MODE == 2) {
-    const uint32_t slot = a.hot[a.c_cb + c];
-    if (slot < n_slots) { atomicAdd(&sA[slot], sa); atomicAdd(&sB[slot], sb); return; }
-  }
-  atomic_add2(a.cAB, c, sa, sb);
-}
+#ifndef FMWR_FUSED_BLOCKS
+#define FMWR_FUSED_BLOCKS 3
+#endif
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_BLOCKS = FMWR_FUSED_BLOCKS;  // resident CTAs per SM
+constexpr int FUSED_MAX_REP = 64;           // replicas of the per-feature (A, B) table
+constexpr size_t FUSED_AB_BYTES = 8u << 20; // ... as many as fit this budget (L2-resident)
 
-// rows sorted by this phase's feature: the lanes holding one feature form a contiguous run, so a segmented
-// shuffle reduction leaves the run's total in its first lane -> one vector atomic per run instead of one per row.
-// Must be called by every lane that is still inside the row loop (the loop tail drops the HIGHEST lanes only).
-template <class T>
-__device__ __forceinline__ void stats_add_sorted(const FusedArgs<T>& a, uint32_t c, T sa, T sb)
+// Statistics go to global memory with ONE native 8-byte vector reduction per run (red.global.add.v2.f32).  Shared-memory
+// float atomics are compare-and-swap loops on this architecture (ATOMS.CAST.SPIN) and cost more than the whole streaming
+// pass; the global reduction unit is spread over n_rep copies of the table (chosen so that they stay L2-resident), which
+// keeps same-address serialisation negligible even for a 2048-feature field.  A thread owns VEC consecutive rows and first
+// combines the rows that share a feature -- with the rows sorted by the widest field that is one reduction per thread.
+// ONES: every value of the data is 1.0 (one-hot fields): the value streams are not read at all.
+template <class T, int VEC, bool ONES>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_BLOCKS) fused_kernel(FusedArgs<T> a)
 {
-  const unsigned act = __activemask();
-  const unsigned peers = __match_any_sync(act, c);
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const T ta = __shfl_down_sync(act, sa, o);
-    const T tb = __shfl_down_sync(act, sb, o);
-    if (lane + o < 32 && ((peers >> (lane + o)) & 1u)) { sa += ta; sb += tb; }
-  }
-  if (lane == __ffs(peers) - 1) atomic_add2(a.cAB, c, sa, sb);
-}
-
-constexpr int FUSED_THREADS = 1024;  // few fat CTAs (2 per SM): the shared-memory tables are flushed once per CTA
-
-template <class T, int MODE, int VEC>
-__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(FusedArgs<T> a)
-{
-  constexpr int HOT_SLOTS = sizeof(T) == 8 ? RM_HOT / 2 : RM_HOT;   // 32 KB of shared memory either way
-  constexpr int SLOTS = MODE == 1 ? RM_SMEM_COLS : (MODE == 2 ? HOT_SLOTS : 1);
-  __shared__ T sA[SLOTS], sB[SLOTS];
-  const uint32_t n_slots = !a.has_cur ? 0u : (MODE == 1 ? a.c_ncols : (MODE == 2 ? (uint32_t)(a.n_hot < HOT_SLOTS ? a.n_hot : HOT_SLOTS) : 0u));
-  if (MODE != 0) {
-    for (uint32_t c = threadIdx.x; c < n_slots; c += blockDim.x) { sA[c] = T(0); sB[c] = T(0); }
-    __syncthreads();
-  }
+  typedef typename Vec2<T>::type V2;
+  // (staging these lookup tables in shared memory was measured and does not pay: the pass is bound by the reductions)
+  const V2* __restrict__ ptab = a.pthd;
+  const T* __restrict__ ctab = a.cth;
   const bool same_q = a.has_prev && a.has_cur && a.pq != nullptr && a.pq == a.cq;
+  T* AB = a.cAB + (a.has_cur ? 2 * (size_t)(blockIdx.x % (unsigned)a.n_rep) * a.c_ncols : 0);
   for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; base < a.n; base += (int64_t)gridDim.x * blockDim.x * VEC) {
     T ev[VEC], qv[VEC];
     uint32_t pc[VEC], cc[VEC];
     float px[VEC], cx[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) { px[u] = 1.f; cx[u] = 1.f; pc[u] = 0u; cc[u] = 0u; }
     if (VEC == 4) {
       *reinterpret_cast<typename Vec<T>::type*>(ev) = *reinterpret_cast<const typename Vec<T>::type*>(a.e + base);
       if (sizeof(T) == 8) *reinterpret_cast<typename Vec<T>::type*>(ev + 2) = *reinterpret_cast<const typename Vec<T>::type*>(a.e + base + 2);
-      if (a.has_prev) { *reinterpret_cast<uint4*>(pc) = *reinterpret_cast<const uint4*>(a.pcol + base); *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(a.pval + base); }
-      if (a.has_cur) { *reinterpret_cast<uint4*>(cc) = *reinterpret_cast<const uint4*>(a.ccol + base); *reinterpret_cast<float4*>(cx) = *reinterpret_cast<const float4*>(a.cval + base); }
+      if (a.has_prev) {
+        *reinterpret_cast<uint4*>(pc) = *reinterpret_cast<const uint4*>(a.pcol + base);
+        if (!ONES) *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(a.pval + base);
+      }
+      if (a.has_cur) {
+        *reinterpret_cast<uint4*>(cc) = *reinterpret_cast<const uint4*>(a.ccol + base);
+        if (!ONES) *reinterpret_cast<float4*>(cx) = *reinterpret_cast<const float4*>(a.cval + base);
+      }
     } else {
       ev[0] = a.e[base];
-      if (a.has_prev) { pc[0] = a.pcol[base]; px[0] = a.pval[base]; }
-      if (a.has_cur) { cc[0] = a.ccol[base]; cx[0] = a.cval[base]; }
+      if (a.has_prev) { pc[0] = a.pcol[base]; if (!ONES) px[0] = a.pval[base]; }
+      if (a.has_cur) { cc[0] = a.ccol[base]; if (!ONES) cx[0] = a.cval[base]; }
     }
     // ---- apply the previous step (reference :251-253 for w, :338-349 for V)
     if (a.has_prev) {
       if (a.pq != nullptr) {
+        if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(qv) = *reinterpret_cast<const typename Vec<T>::type*>(a.pq + base);
+        else {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) qv[u] = a.pq[base + u];
+          for (int u = 0; u < VEC; ++u) qv[u] = a.pq[base + u];
+        }
 #pragma unroll
         for (int u = 0; u < VEC; ++u) {
-          const T d = a.pdelta[pc[u]];
-          const T h = T(px[u]) * qv[u] - T(px[u] * px[u]) * a.pth[pc[u]];
+          const V2 td = ptab[pc[u]];
+          const T d = td.y;
+          const T h = T(px[u]) * qv[u] - T(px[u] * px[u]) * td.x;
           qv[u] -= T(px[u]) * d;
           ev[u] -= h * d;
         }
+        if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(a.pq + base) = *reinterpret_cast<const typename Vec<T>::type*>(qv);
+        else {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) a.pq[base + u] = qv[u];
+          for (int u = 0; u < VEC; ++u) a.pq[base + u] = qv[u];
+        }
       } else {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) ev[u] -= T(px[u]) * a.pdelta[pc[u]];
+        for (int u = 0; u < VEC; ++u) ev[u] -= T(px[u]) * ptab[pc[u]].y;
       }
+      if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(a.e + base) = *reinterpret_cast<const typename Vec<T>::type*>(ev);
+      else {
 #pragma unroll
-      for (int u = 0; u < VEC; ++u) a.e[base + u] = ev[u];
+        for (int u = 0; u < VEC; ++u) a.e[base + u] = ev[u];
+      }
     }
     // ---- statistics of the current step (reference :225-230 for w, :313-321 for V)
     if (a.has_cur) {
       if (a.cq != nullptr && !same_q) {
+        if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(qv) = *reinterpret_cast<const typename Vec<T>::type*>(a.cq + base);
+        else {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) qv[u] = a.cq[base + u];
+          for (int u = 0; u < VEC; ++u) qv[u] = a.cq[base + u];
+        }
       }
+      T ra = T(0), rb = T(0);
+      uint32_t rc = cc[0];
 #pragma unroll
       for (int u = 0; u < VEC; ++u) {
-        const T old = a.cth[cc[u]];
+        const T old = ctab[cc[u]];
         T sa, sb;
         if (a.cq == nullptr) {
           const T x = T(cx[u]);
@@ -741,15 +841,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(FusedArgs<T> a)
           sa = h * h;
           sb = h * ev[u];
         }
-        if (MODE == 0 && a.cur_sorted) stats_add_sorted<T>(a, cc[u], sa, sb);
-        else stats_add<T, MODE>(a, sA, sB, n_slots, cc[u], sa, sb);
+        if (u > 0 && cc[u] != rc) { atomic_add2(AB, rc, ra, rb); rc = cc[u]; ra = T(0); rb = T(0); }
+        ra += sa; rb += sb;
       }
+      atomic_add2(AB, rc, ra, rb);
     }
-  }
-  if (MODE != 0) {
-    __syncthreads();
-    for (uint32_t sl = threadIdx.x; sl < n_slots; sl += blockDim.x)
-      if (sA[sl] != T(0) || sB[sl] != T(0)) atomic_add2(a.cAB, MODE == 1 ? sl : a.hot_col[sl], sA[sl], sB[sl]);
   }
 }
 
@@ -761,6 +857,7 @@ struct DenseLayout {
   // run instead of per row).  e, q and the labels then live in permuted row order; parameters are unaffected.
   bool permuted = false;
   int sorted_phase = -1;
+  bool all_ones = false;  // every stored value is 1.0f: the fused passes skip the value streams
   DBuf<uint32_t> pcol;   // [n][np] CSR columns of the permuted rows (global ids) for the forward pass
   DBuf<float> pval;      // [n][np]
   DBuf<float> py;        // [n] labels of the permuted rows
@@ -788,6 +885,12 @@ __global__ void dense_build_kernel(const uint32_t* __restrict__ col, const float
   const int64_t r = perm ? (int64_t)perm[i] : i;
   ocol[t] = col[r * np + j] - pbeg[j];
   oval[t] = val[r * np + j];
+}
+
+__global__ void dense_not_one_kernel(const float* __restrict__ val, int64_t m, int* __restrict__ flag)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m && val[i] != 1.0f) *flag = 1;
 }
 
 __global__ void dense_phase_key_kernel(const uint32_t* __restrict__ col, int64_t n, int np, int j, uint32_t* __restrict__ key)
@@ -847,9 +950,28 @@ static void build_dense(fmwr_data* d, const std::vector<uint32_t>& pbeg_host, De
   dl.col.alloc((size_t)n * np); dl.val.alloc((size_t)n * np);
   FMWR_LAUNCH(ctx, dense_build_kernel, ceil_div(n * np, 256), 256, 0, d->col.p, d->val.p, n, np, pbeg.p, dl.permuted ? perm.p : nullptr,
               dl.col.p, dl.val.p);
+  {
+    DBuf<int> flag;
+    flag.alloc(1);
+    flag.zero(ctx->stream);
+    FMWR_LAUNCH(ctx, dense_not_one_kernel, ceil_div(n * np, 256), 256, 0, d->val.p, n * np, flag.p);
+    int hf = 1;
+    FMWR_CUDA(cudaMemcpyAsync(&hf, flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    dl.all_ones = hf == 0;
+  }
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   dl.ok = true;
 }
+
+template <class T>
+static int fused_replicas(uint32_t ncols, int grid)
+{
+  const size_t per = 2 * sizeof(T) * (size_t)std::max<uint32_t>(ncols, 1);
+  return (int)std::max<size_t>(1, std::min<size_t>({(size_t)FUSED_MAX_REP, (size_t)grid, FUSED_AB_BYTES / per}));
+}
+template <class T>
+static size_t fused_ab_elems(uint32_t max_cols) { return std::max<size_t>(2 * (size_t)max_cols, FUSED_AB_BYTES / sizeof(T)); }
 
 // one coordinate step of a fused sequence
 template <class T>
@@ -861,46 +983,60 @@ static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, co
                             const double* normals, long long n_normals, uint64_t seed)
 {
   const int vec = (n % 4 == 0) ? 4 : 1;
-  const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, ceil_div64(ceil_div64(n, vec), FUSED_THREADS));
+  const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * FUSED_BLOCKS, ceil_div64(ceil_div64(n, vec), FUSED_THREADS));
   const int T_ = (int)steps.size();
+  auto step_args = [&](int t) {
+    RmArgs<T> ra;                      // extract / solve arguments of step t
+    memset(&ra, 0, sizeof ra);
+    const Step<T>& cs = steps[t];
+    const uint32_t cb = pbeg[cs.phase], ncols = pbeg[cs.phase + 1] - cb;
+    ra.cb = cb; ra.ncols = ncols; ra.q = cs.q; ra.n = n; ra.f = cs.f; ra.theta = cs.theta; ra.theta_stride = cs.stride;
+    ra.th = sc[t & 1].th; ra.AB = sc[t & 1].AB; ra.delta = sc[t & 1].delta; ra.thd = sc[t & 1].thd;
+    ra.n_rep = fused_replicas<T>(ncols, grid);
+    ra.alpha = alpha; ra.lambda = cs.lambda; ra.mu = cs.mu; ra.do_sample = do_sample; ra.w_sd_is_var = cs.w_sd_is_var;
+    ra.normals = normals; ra.n_normals = n_normals; ra.normal_base = cs.normal_base; ra.seed = seed;
+    return ra;
+  };
+  RmArgs<T> ra, rnext;
+  memset(&ra, 0, sizeof ra);
+  if (T_ > 0) {
+    rnext = step_args(0);
+    FMWR_LAUNCH(ctx, rm_extract_kernel<T>, ceil_div(rnext.ncols, 256), 256, 0, rnext);
+  }
   for (int t = 0; t <= T_; ++t) {
     FusedArgs<T> fa;
     memset(&fa, 0, sizeof fa);
-    fa.n = n; fa.e = e;
-    RmArgs<T> ra;                      // extract / solve arguments of the current step
-    memset(&ra, 0, sizeof ra);
+    fa.n = n; fa.e = e; fa.n_rep = 1;
     if (t > 0) {
       const Step<T>& ps = steps[t - 1];
       fa.has_prev = 1;
       fa.pcol = dl.col.p + (size_t)ps.phase * n; fa.pval = dl.val.p + (size_t)ps.phase * n;
-      fa.pth = sc[(t - 1) & 1].th; fa.pdelta = sc[(t - 1) & 1].delta;
+      fa.pthd = sc[(t - 1) & 1].thd; fa.p_ncols = pbeg[ps.phase + 1] - pbeg[ps.phase];
       fa.pq = ps.q ? ps.q + (size_t)ps.f * n : nullptr;
     }
     if (t < T_) {
+      ra = rnext;                      // extracted by the previous iteration's solve+extract launch
       const Step<T>& cs = steps[t];
-      const uint32_t cb = pbeg[cs.phase], ncols = pbeg[cs.phase + 1] - cb;
-      ra.cb = cb; ra.ncols = ncols; ra.q = cs.q; ra.n = n; ra.f = cs.f; ra.theta = cs.theta; ra.theta_stride = cs.stride;
-      ra.th = sc[t & 1].th; ra.AB = sc[t & 1].AB; ra.delta = sc[t & 1].delta;
-      ra.alpha = alpha; ra.lambda = cs.lambda; ra.mu = cs.mu; ra.do_sample = do_sample; ra.w_sd_is_var = cs.w_sd_is_var;
-      ra.normals = normals; ra.n_normals = n_normals; ra.normal_base = cs.normal_base; ra.seed = seed;
-      FMWR_LAUNCH(ctx, rm_extract_kernel<T>, ceil_div(ncols, 256), 256, 0, ra);
       fa.has_cur = 1;
       fa.ccol = dl.col.p + (size_t)cs.phase * n; fa.cval = dl.val.p + (size_t)cs.phase * n;
       fa.cth = ra.th; fa.cAB = ra.AB; fa.cq = cs.q ? cs.q + (size_t)cs.f * n : nullptr;
-      fa.cur_sorted = (dl.permuted && dl.sorted_phase == cs.phase) ? 1 : 0;
-      fa.c_cb = cb; fa.c_ncols = ncols; fa.hot = rm.hot.p; fa.hot_col = rm.hot_col.p + (size_t)cs.phase * RM_HOT; fa.n_hot = rm.n_hot[cs.phase];
+      fa.c_ncols = ra.ncols; fa.n_rep = ra.n_rep;
     }
-    const int mode = !fa.has_cur ? 0 : (fa.c_ncols <= (uint32_t)RM_SMEM_COLS ? 1 : (fa.cur_sorted ? 0 : (fa.n_hot > 0 ? 2 : 0)));
     if (vec == 4) {
-      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 4>), grid, FUSED_THREADS, 0, fa);
-      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 4>), grid, FUSED_THREADS, 0, fa);
-      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 4>), grid, FUSED_THREADS, 0, fa);
+      if (dl.all_ones) FMWR_LAUNCH(ctx, (fused_kernel<T, 4, true>), grid, FUSED_THREADS, 0, fa);
+      else FMWR_LAUNCH(ctx, (fused_kernel<T, 4, false>), grid, FUSED_THREADS, 0, fa);
     } else {
-      if (mode == 0) FMWR_LAUNCH(ctx, (fused_kernel<T, 0, 1>), grid, FUSED_THREADS, 0, fa);
-      else if (mode == 1) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, 1>), grid, FUSED_THREADS, 0, fa);
-      else FMWR_LAUNCH(ctx, (fused_kernel<T, 2, 1>), grid, FUSED_THREADS, 0, fa);
+      if (dl.all_ones) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, true>), grid, FUSED_THREADS, 0, fa);
+      else FMWR_LAUNCH(ctx, (fused_kernel<T, 1, false>), grid, FUSED_THREADS, 0, fa);
     }
-    if (t < T_) FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(ra.ncols, 256), 256, 0, ra);
+    if (t < T_) {
+      if (t + 1 < T_) {
+        // solve(t) and extract(t+1) share a launch: step t+1 is another (phase, factor), i.e. other features, and its
+        // scratch (parity (t+1)&1) was last read by the fused pass that has just finished
+        rnext = step_args(t + 1);
+        FMWR_LAUNCH(ctx, rm_solve_extract_kernel<T>, ceil_div(std::max(ra.ncols, rnext.ncols), 256), 256, 0, ra, rnext);
+      } else FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(ra.ncols, 256), 256, 0, ra);
+    }
   }
 }
 
@@ -1005,7 +1141,7 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   RowMajor& rm = cache.rm;
   const int n_phases = (int)ph.begin.size() - 1;
   const bool use_rm = n_phases <= 256 && d->nnz > 0 && getenv("FMWR_ALS_COLUMN") == nullptr;
-  DBuf<T> rm_th, rm_AB, rm_delta, rm_th2, rm_AB2, rm_delta2;
+  DBuf<T> rm_th, rm_AB, rm_delta, rm_th2, rm_AB2, rm_delta2, rm_thd, rm_thd2;
   DenseLayout& dl = cache.dl;
   if (use_rm) {
     if (!cache.rm_tried) {
@@ -1015,10 +1151,11 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
       if (dl.ok) { rm.row.release(); rm.col.release(); rm.val.release(); }     // the dense copy supersedes the row-major one
       cache.rm_tried = true;
     }
-    rm_th.alloc(rm.max_cols); rm_AB.alloc(2 * (size_t)rm.max_cols); rm_delta.alloc(rm.max_cols);
-    if (dl.ok) { rm_th2.alloc(rm.max_cols); rm_AB2.alloc(2 * (size_t)rm.max_cols); rm_delta2.alloc(rm.max_cols); }
+    rm_th.alloc(rm.max_cols); rm_AB.alloc(dl.ok ? fused_ab_elems<T>(rm.max_cols) : 2 * (size_t)rm.max_cols); rm_delta.alloc(rm.max_cols);
+    if (dl.ok) { rm_th2.alloc(rm.max_cols); rm_AB2.alloc(fused_ab_elems<T>(rm.max_cols)); rm_delta2.alloc(rm.max_cols); rm_thd.alloc(2 * (size_t)rm.max_cols); rm_thd2.alloc(2 * (size_t)rm.max_cols); }
   }
-  StepScratch<T> scr[2] = {{rm_th.p, rm_AB.p, rm_delta.p}, {rm_th2.p, rm_AB2.p, rm_delta2.p}};
+  typedef typename Vec2<T>::type V2T;
+  StepScratch<T> scr[2] = {{rm_th.p, rm_AB.p, rm_delta.p, (V2T*)rm_thd.p}, {rm_th2.p, rm_AB2.p, rm_delta2.p, (V2T*)rm_thd2.p}};
   auto rm_args = [&](T* e_p, T* q_p, int f, T* theta, int64_t stride, double alpha_, double lambda_, double mu_, int sample, int w_sd_var,
                      const double* normals_p, long long n_normals_, long long base, uint64_t seed_) {
     RmArgs<T> a;
@@ -1141,8 +1278,12 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
     if (enable_v) {
       // update_v_lambda (:486-517) for every factor, then update_v_mu (:448-483), then update_v (:272-354)
       if (do_multilevel) {
+        // V is not touched between these 2k draws and v_lambda[f] / v_mu[f] only depend on factor f's own sums, so all
+        // the sums come from one batched reduction (the draw ORDER -- k lambdas, then k mus -- is the reference's)
+        std::vector<double> vsum, vsq, vrow0;
+        reduce_v_all<T>(ctx, vp, p, k, kp, v_mu, vsum, vsq, vrow0);
         for (int f = 0; f < k; ++f) {
-          double g = reduce<T>(ctx, vp + f, p, kp, 2, v_mu[f]);
+          double g = vsq[f];
           g += beta_0 * (v_mu[f] - mu_0) * (v_mu[f] - mu_0) + gamma_0;
           const double la = alpha_0 + (double)p + 1;
           const double nl = do_sample ? hs.gamma(la / 2.0, 2.0 / g) : la / g;
@@ -1152,12 +1293,10 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
           double mm;
           if (s->compat & FMWR_COMPAT_MCMC_VMU_IDX) {
             // F7: the reference sums v(f, attr_group[i]) == v(f, 0), p times (:462)
-            T v0;
-            FMWR_CUDA(cudaMemcpyAsync(&v0, vp + f, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-            FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+            const T v0 = T(vrow0[f]);
             mm = 0.0;
             for (int64_t i = 0; i < p; ++i) mm += (double)v0;
-          } else mm = reduce<T>(ctx, vp + f, p, kp, 0, 0.0);
+          } else mm = vsum[f];
           mm = (mm + beta_0 * mu_0) / ((double)p + beta_0);
           const double var = 1.0 / (((double)p + beta_0) * v_lambda[f]);
           const double nm = do_sample ? hs.normal(mm, std::sqrt(var)) : mm;

@@ -19,9 +19,6 @@
 
 #include <cmath>
 
-#ifndef FMWR_K2_UE
-#define FMWR_K2_UE 4
-#endif
 
 namespace fmwr {
 
@@ -32,7 +29,7 @@ void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
 template <class T, int LPR, int CH, int TEAM>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, FMWR_FWD_BLOCKS)
 mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                   const float* __restrict__ y, const T* __restrict__ w, const T* __restrict__ v,
                   const double* __restrict__ scal, int kp, int k0, int k1, int task, T lo, T hi,
@@ -100,6 +97,8 @@ struct MbUpdArgs {
   SolverParams<T> sp;
   T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
 };
+
+template <int SOLVER> struct K2Tune { enum { BLOCKS = SOLVER == FMWR_TDAP ? 3 : 6, UE = SOLVER == FMWR_TDAP ? 4 : 2 }; };
 
 // the intercept (dense coordinate): fixed-order reduction of the batch's multipliers by ONE block.  It is block 0 so
 // that its serial chain of loads overlaps the rest of the grid instead of forming the kernel's tail.
@@ -246,7 +245,7 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
       if (base + (uint32_t)l < len) { my_r = __ldg(a.ent_row + eb + base + l); my_x = __ldg(a.ent_val + eb + base + l); }
     }
     const int cnt = (int)min((uint32_t)LPR, len - base);
-    constexpr int UE = LPR < FMWR_K2_UE ? LPR : FMWR_K2_UE;
+    constexpr int UE = LPR < K2Tune<SOLVER>::UE ? LPR : K2Tune<SOLVER>::UE;
     for (int j0 = 0; j0 < cnt; j0 += UE) {
       T xe[UE], me[UE];
       V16 se[UE][CH];
@@ -340,9 +339,12 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
   }
 }
 
-// one lane group per segment, one segment per group (generic: any layout, TDAP)
+// One lane group per segment.  Measured on B200 (profiles/r01_summary.md): occupancy beats per-warp depth here -- a
+// 40-register build (6 CTAs/SM, entries taken two at a time) is as fast as a persistent software-pipelined variant
+// with three segments in flight per group, and simpler.  TDAP carries 4 state rows and keeps 80 registers.
+
 template <class T, int LPR, int CH, int SOLVER, bool L1>
-__global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 && CH == 1) ? K2Tune<SOLVER>::BLOCKS : 1) mb_update_kernel(MbUpdArgs<T> a)
 {
   constexpr int G = 32 / LPR;
   constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
@@ -356,41 +358,6 @@ __global__ void __launch_bounds__(256) mb_update_kernel(MbUpdArgs<T> a)
   SegStage<T, CH, NST> sg;
   seg_issue<T, LPR, CH, SOLVER, L1>(a, rec, eb, l, true, sg);
   seg_finish<T, LPR, CH, SOLVER, L1>(a, g, l, sg);
-}
-
-// Persistent, software-pipelined variant (SGD / FTRL, one 16-byte chunk per lane): a group walks the segments
-// seg, seg + stride, ...; while it finishes segment i, the rows of segment i+1 and the record of segment i+2 are
-// already in flight, so a segment exposes one memory round (the other rows' S-cache lines) instead of three.
-// Two segments of one batch never share a coordinate, so fetching the next parameter row early is safe.
-template <class T, int LPR, int SOLVER, bool L1, int BLOCKS>
-__global__ void __launch_bounds__(256, BLOCKS) mb_update_pipe_kernel(MbUpdArgs<T> a)
-{
-  constexpr int G = 32 / LPR;
-  constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
-  if (blockIdx.x == 0) { mb_intercept<T, SOLVER>(a); return; }
-  const int lane = threadIdx.x & 31;
-  const int g = lane / LPR, l = lane % LPR;
-  const uint32_t stride = (gridDim.x - 1) * (blockDim.x >> 5) * G;
-  uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
-  if (seg >= a.seg_end) return;
-  SegStage<T, 1, NST> cur, nxt;
-  uint4 rec2 = make_uint4(0u, 0u, 0u, 0u);
-  uint32_t eb2 = 0u;
-  {
-    const uint4 rec = __ldg(a.seg_rec + seg);
-    const uint32_t eb = __ldg(a.seg_ptr + seg);
-    if (seg + stride < a.seg_end) { rec2 = __ldg(a.seg_rec + seg + stride); eb2 = __ldg(a.seg_ptr + seg + stride); }
-    seg_issue<T, LPR, 1, SOLVER, L1>(a, rec, eb, l, true, cur);
-  }
-  while (true) {
-    const bool has_next = seg + stride < a.seg_end;           // group-uniform
-    seg_issue<T, LPR, 1, SOLVER, L1>(a, rec2, eb2, l, has_next, nxt);
-    if (seg + 2 * stride < a.seg_end) { rec2 = __ldg(a.seg_rec + seg + 2 * stride); eb2 = __ldg(a.seg_ptr + seg + 2 * stride); }
-    seg_finish<T, LPR, 1, SOLVER, L1>(a, g, l, cur);
-    if (!has_next) break;
-    cur = nxt;
-    seg += stride;
-  }
 }
 
 template <class T>
@@ -409,12 +376,7 @@ struct MbLaunch {
       constexpr int G = 32 / LPR;
       const uint32_t nseg = ua.seg_end - ua.seg_begin;
       const int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
-      // persistent pipelined kernel: 3 resident CTAs per SM
-      const int pblocks = s->solver == FMWR_SGD && !ua.sp.l1 ? 3 : 2;      // measured: SGD likes occupancy, FTRL registers
-      const int pgrid = (int)std::min<int64_t>(grid, (int64_t)ctx->sm_count * pblocks + 1);
-      const bool pipe = CH == 1 && s->solver != FMWR_TDAP && getenv("FMWR_K2_NOPIPE") == nullptr;
-      if (pipe) launch_pipe<TT, LPR>(pgrid);
-      else switch (s->solver) {
+      switch (s->solver) {
         case FMWR_SGD:
           if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, true>), grid, 256, 0, ua);
           else FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, false>), grid, 256, 0, ua);
@@ -422,16 +384,6 @@ struct MbLaunch {
         case FMWR_FTRL: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_FTRL, false>), grid, 256, 0, ua); break;
         default: FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_TDAP, false>), grid, 256, 0, ua); break;
       }
-    }
-  }
-  template <class TT, int LPR>
-  void launch_pipe(int pgrid)
-  {
-    if (s->solver == FMWR_SGD) {
-      if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_pipe_kernel<TT, LPR, FMWR_SGD, true, 2>), pgrid, 256, 0, ua);
-      else FMWR_LAUNCH(ctx, (mb_update_pipe_kernel<TT, LPR, FMWR_SGD, false, 3>), pgrid, 256, 0, ua);
-    } else {
-      FMWR_LAUNCH(ctx, (mb_update_pipe_kernel<TT, LPR, FMWR_FTRL, false, 2>), pgrid, 256, 0, ua);
     }
   }
 };

@@ -404,6 +404,9 @@ def run_engine_multi(args, rank, world, local):
     ctx.comm_init(multi.exchange_unique_id(dist, L.Context, rank), rank, world)
     peak, peak_src = measured_peak()
     n, F, k, B = args.rows, 39, args.k, args.batch
+    use_peer = os.environ.get("FMWR_BENCH_NCCL", "0") != "1"
+    if use_peer:
+        multi.open_peer_windows(dist, ctx, rank, world, B, k)      # per-batch exchange inside our kernels (NVLink), no NCCL call
     field = args.features // F
     p = field * F
     f0, f1, c0, c1 = multi.field_partition([field] * F, world)[rank]
@@ -478,8 +481,9 @@ def run_engine_multi(args, rank, world, local):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: Criteo-shaped %d rows x %d nnz, %d features, k=%d, FTRL L1+L2 binary logloss" % (n, F, p, k),
                        "rows": n, "nnz_per_row": F, "features": p, "k": k, "batch_size": B, "mode": "minibatch",
-                       "parallelism": "feature-parallel x%d (fields split %s), one NCCL all-reduce of rows x (k+4) f32 per minibatch; predict row-sharded" % (
-                           world, [b - a for a, b, _, _ in multi.field_partition([field] * F, world)]),
+                       "parallelism": "feature-parallel x%d (fields split %s), per minibatch one exchange of rows x (k+4) f32 partials %s; predict row-sharded" % (
+                           world, [b - a for a, b, _, _ in multi.field_partition([field] * F, world)],
+                           "inside the forward/exchange/update kernels (peer-memory stores over NVLink + in-kernel flags)" if use_peer else "by NCCL all-reduce"),
                        "l2_flush": "inputs larger than L2"},
             "roofline": roof,
             "step_roofline": {"alg_bytes_per_sample": b_ftrl, "achieved": round(train_sps * b_ftrl / 1e9, 1), "unit": "GB/s",

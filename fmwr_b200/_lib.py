@@ -141,6 +141,21 @@ class Context:
     def comm_destroy(self):
         check(lib().fmwr_comm_destroy(self.h))
 
+    @staticmethod
+    def comm_peer_bytes(batch_size, k, world):
+        lib().fmwr_comm_peer_bytes.restype = C.c_int64
+        return int(lib().fmwr_comm_peer_bytes(C.c_int64(batch_size), C.c_int32(k), C.c_int32(world)))
+
+    def comm_peer_alloc(self, nbytes):
+        buf = (C.c_uint8 * 64)()
+        check(lib().fmwr_comm_peer_alloc(self.h, C.c_int64(nbytes), buf))
+        return bytes(buf)
+
+    def comm_peer_open(self, handles):
+        raw = b"".join(handles)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        check(lib().fmwr_comm_peer_open(self.h, buf))
+
     def link_table(self, which, x):
         x = np.ascontiguousarray(x, np.float64)
         out = np.zeros_like(x)

@@ -92,10 +92,70 @@ int fmwr_comm_init(fmwr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t wo
   });
 }
 
+int64_t fmwr_comm_peer_bytes(int64_t batch_size, int32_t k, int32_t world)
+{
+  if (batch_size <= 0 || k < 0 || world < 1) return 0;
+  // stride <= 2k + 8 covers the padding of either precision; slabs: world x ceil(B / world) rows, S cache: B rows, mult: B
+  const int64_t stride = 2 * (int64_t)k + 8;
+  const int64_t rpo = (batch_size + world - 1) / world;
+  return PEER_CTL_BYTES + 8 * (world * rpo * stride + batch_size * stride + batch_size) + 3 * 256;
+}
+
+int fmwr_comm_peer_alloc(fmwr_ctx* ctx, int64_t bytes, uint8_t* handle64)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx && handle64 && bytes >= PEER_CTL_BYTES, FMWR_ERR_ARG, "bad argument");
+    FMWR_REQUIRE(ctx->world > 1 && ctx->world <= 8, FMWR_ERR_ARG, "peer windows need an initialised communicator of 2..8 ranks");
+    FMWR_REQUIRE(!ctx->peer.base[ctx->rank], FMWR_ERR_ARG, "peer window already allocated");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    FMWR_CUDA(cudaMalloc(&p, (size_t)bytes));                  // a plain allocation: IPC handles name whole allocations
+    FMWR_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    FMWR_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    FMWR_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    ctx->peer.base[ctx->rank] = p;
+    ctx->peer.bytes = (size_t)bytes;
+  });
+}
+
+int fmwr_comm_peer_open(fmwr_ctx* ctx, const uint8_t* handles)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx && handles, FMWR_ERR_ARG, "null argument");
+    FMWR_REQUIRE(ctx->peer.base[ctx->rank] && !ctx->peer.ready, FMWR_ERR_ARG, "allocate the local window first (once)");
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->world; ++r) {
+      if (r == ctx->rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + 64 * r, 64);
+      void* p = nullptr;
+      FMWR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      ctx->peer.base[r] = p;
+    }
+    ctx->peer.ready = true;
+  });
+}
+
+static void peer_close(fmwr_ctx* ctx)
+{
+  for (int r = 0; r < 8; ++r) {
+    if (!ctx->peer.base[r]) continue;
+    if (r == ctx->rank) cudaFree(ctx->peer.base[r]);
+    else cudaIpcCloseMemHandle(ctx->peer.base[r]);
+    ctx->peer.base[r] = nullptr;
+  }
+  ctx->peer.ready = false; ctx->peer.bytes = 0;
+}
+
 int fmwr_comm_destroy(fmwr_ctx* ctx)
 {
   return guarded([&] {
     FMWR_REQUIRE(ctx, FMWR_ERR_ARG, "null ctx");
+    cudaStreamSynchronize(ctx->stream);
+    peer_close(ctx);
     if (ctx->nccl_comm) {
       cudaStreamSynchronize(ctx->stream);
       g_nccl.comm_destroy(ctx->nccl_comm);

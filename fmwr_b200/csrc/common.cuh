@@ -134,6 +134,8 @@ struct fmwr_ctx {
   // feature-parallel communicator (NCCL, resolved at run time; null on a single GPU)
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // peer window (CUDA IPC over NVLink): base[r] = rank r's window mapped into this process (base[rank] = our own)
+  struct PeerWin { void* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t bytes = 0; bool ready = false; } peer;
   fmwr::DBuf<double> red_scratch;  // reductions
   fmwr::HBuf<double> h_scalar;
 };
@@ -200,6 +202,59 @@ __device__ __forceinline__ T warp_sum(T v)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---- peer window: control block layout (uint32 words) and in-kernel barriers ---------------------------------------
+// [FLAG1 + 32 r]  arrival of rank r at barrier 1 (partials stored)      -- written by rank r into EVERY rank's window
+// [FLAG2 + 32 r]  arrival of rank r at barrier 2 (row totals stored)
+// EPOCH1/2, COUNT1/2, ERR: local words of the owning rank.  Flags sit in separate 128-byte lines.
+enum { PEER_FLAG1 = 0, PEER_FLAG2 = 256, PEER_EPOCH1 = 512, PEER_EPOCH2 = 513, PEER_COUNT1 = 514, PEER_COUNT2 = 515, PEER_ERR = 516,
+       PEER_CTL_BYTES = 4096 };
+
+struct PeerArgs {
+  char* base[8];       // every rank's window
+  int rank, world;
+  int rows_per_owner;  // rows of a batch a rank finalises: owner(r) = r / rows_per_owner
+  size_t off_P, off_S, off_mult;   // byte offsets of the partial slabs [world][rows_per_owner][stride], S cache [B][stride], mult [B]
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// Called by every thread of every CTA at the END of a kernel whose stores the peers will read: the last CTA to get here
+// publishes this rank's arrival (a new epoch number) in every rank's window.
+__device__ __forceinline__ void peer_signal(const PeerArgs& pa, int flag_base, int epoch_word, int count_word)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(pa.base[pa.rank]);
+    __threadfence_system();                                   // this CTA's (peer) stores before the count
+    const unsigned done = atomicAdd(ctl + count_word, 1u);
+    if (done == gridDim.x - 1) {
+      ctl[count_word] = 0u;
+      const uint32_t ep = ctl[epoch_word] + 1u;
+      ctl[epoch_word] = ep;
+      __threadfence_system();
+      for (int h = 0; h < pa.world; ++h) st_release_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
+    }
+  }
+}
+
+// Called by every thread at the START of the kernel that reads what the peers stored.  The local epoch word was bumped
+// by this rank's own signalling kernel (earlier in the stream), so it names the barrier to wait for.
+__device__ __forceinline__ void peer_wait(const PeerArgs& pa, int flag_base, int epoch_word)
+{
+  if ((int)threadIdx.x < pa.world) {
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(pa.base[pa.rank]);
+    const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(ctl + epoch_word);
+    const uint32_t* f = ctl + flag_base + 32 * threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - ep) < 0) {
+      if (clock64() - t0 > 40000000000ll) { ctl[PEER_ERR] = 1u; break; }   // ~20 s: a peer died; the host reports it
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
 }
 
 // 16-byte vector views of the parameter rows

@@ -209,7 +209,7 @@ __device__ __forceinline__ T team_forward_partial(const uint32_t* __restrict__ c
 }
 
 // rows with at most this many non-zeros per LPR-lane group on average go one row per group
-__host__ __device__ inline bool short_rows(int64_t nnz, int64_t n, int lpr) { return lpr < 32 && n > 0 && nnz <= n * 2 * (32 / lpr); }
+__host__ __device__ inline bool short_rows(int64_t nnz, int64_t n, int lpr) { return lpr < 32 && n > 0 && nnz <= n * 4 * (32 / lpr); }
 
 // table-exact fast_pnorm (reference src/util/Random.h:95-111; Y table regenerated, see link_tables.cu)
 __device__ __forceinline__ double dev_fast_pnorm(const double* __restrict__ Y, double x)

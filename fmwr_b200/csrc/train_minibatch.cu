@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, FMWR_FWD_BLOCKS)
 mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                   const float* __restrict__ y, const T* __restrict__ w, const T* __restrict__ v,
                   const double* __restrict__ scal, int kp, int k0, int k1, int task, T lo, T hi,
-                  int64_t row_begin, int rows, T* __restrict__ mult, T* __restrict__ Scache, int s_stride, int partial)
+                  int64_t row_begin, int rows, T* __restrict__ mult, T* __restrict__ Scache, int s_stride, int partial, PeerArgs pa)
 {
   typedef typename Vec<T>::type V16;
   constexpr int TPW = 32 / TEAM;
@@ -55,6 +55,25 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
       // feature-parallel: this rank holds a column slice, so the row's score is not known yet.  Emit the partials:
       // S_f of the slice and its additive scalar (see team_gather); 1/2 sum S_f^2 is formed after the exchange
       const T addend = team_forward_partial<T, LPR, CH, TEAM>(col, val, b, e, w, v, kp, k1, S);
+      if (partial == 2) {
+        // peer window: the partial goes straight into the memory of the rank that finalises this row (NVLink stores)
+        if (r < rows) {
+          const int owner = r / pa.rows_per_owner;
+          T* dst = reinterpret_cast<T*>(pa.base[owner] + pa.off_P) + ((size_t)pa.rank * pa.rows_per_owner + (r - owner * pa.rows_per_owner)) * s_stride;
+          if (tl == 0) {                      // a whole 16-byte vector {addend, 0..}: no partial-sector write over NVLink
+            T pad[Vec<T>::N];
+#pragma unroll
+            for (int i = 0; i < Vec<T>::N; ++i) pad[i] = T(0);
+            pad[0] = addend;
+            *reinterpret_cast<V16*>(dst + kp) = arr_to_vec(pad);
+          }
+          if (tl < LPR) {
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) reinterpret_cast<V16*>(dst)[ch * LPR + tl] = arr_to_vec(S[ch]);
+          }
+        }
+        continue;
+      }
       if (tl == 0 && r < rows) Scache[(size_t)r * s_stride + kp] = addend;
     }
     if (tl < LPR && r < rows) {
@@ -63,6 +82,74 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
       for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + tl] = arr_to_vec(S[ch]);
     }
   }
+  if (partial == 2) peer_signal(pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1);
+}
+
+// ---- peer exchange: the rank that owns a row sums the world's partials IN RANK ORDER (deterministic), forms the
+// score and the multiplier, and stores the row [S_f totals (kp), multiplier, 0...] into every rank's S cache.
+// One LPR-lane group per row (32/LPR rows per warp), 16-byte loads and stores throughout. -------------------------
+template <class T, int LPR, int CH>
+__global__ void __launch_bounds__(256)
+mb_exchange_kernel(const float* __restrict__ y, const double* __restrict__ scal, int kp, int k0, int task, T lo, T hi,
+                   int64_t row_begin, int rows, int s_stride, PeerArgs pa)
+{
+  typedef typename Vec<T>::type V16;
+  constexpr int VN = Vec<T>::N;
+  constexpr int G = 32 / LPR;
+  peer_wait(pa, PEER_FLAG1, PEER_EPOCH1);
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const int grp0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
+  const int ngrp = gridDim.x * (blockDim.x >> 5) * G;
+  const int r_lo = pa.rank * pa.rows_per_owner;
+  const int r_hi = min(rows, r_lo + pa.rows_per_owner);
+  const int n_local = max(0, r_hi - r_lo);
+  const T* P = reinterpret_cast<const T*>(pa.base[pa.rank] + pa.off_P);
+  const T w0 = k0 ? T(scal[0]) : T(0);
+  for (int base = 0; base < n_local; base += ngrp) {             // warp-uniform trip count: the shuffles below need every lane
+    const int rl = base + grp0;
+    const bool ok = rl < n_local;
+    const int r = r_lo + rl;
+    T S[CH][VN];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) S[ch][i] = T(0);
+    T add = T(0);
+    if (ok) {
+      for (int h = 0; h < pa.world; ++h) {
+        const T* row = P + ((size_t)h * pa.rows_per_owner + rl) * s_stride;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          T t[VN];
+          vec_to_arr(reinterpret_cast<const V16*>(row)[ch * LPR + l], t);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) S[ch][i] += t[i];
+        }
+        if (l == 0) add += row[kp];
+      }
+    }
+    T acc = add;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc += T(0.5) * S[ch][i] * S[ch][i];
+    acc = team_sum<T, LPR>(acc);
+    if (ok) {
+      const T m = grad_mult_fast(task, w0 + acc, T(__ldg(y + row_begin + r)), lo, hi);
+      T tail[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) tail[i] = T(0);
+      tail[0] = m;
+      for (int h = 0; h < pa.world; ++h) {
+        T* dst = reinterpret_cast<T*>(pa.base[h] + pa.off_S) + (size_t)r * s_stride;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) reinterpret_cast<V16*>(dst)[ch * LPR + l] = arr_to_vec(S[ch]);
+        if (l == 0) *reinterpret_cast<V16*>(dst + kp) = arr_to_vec(tail);
+      }
+    }
+  }
+  peer_signal(pa, PEER_FLAG2, PEER_EPOCH2, PEER_COUNT2);
 }
 
 // after the all-reduce: score = w0 + addend + 1/2 sum_f S_f^2 ; one warp per row
@@ -96,6 +183,9 @@ struct MbUpdArgs {
   int kp, k0, k1, s_stride;
   SolverParams<T> sp;
   T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
+  int mult_stride;                      // 1, or the S-cache row stride when the multiplier lives in the row's padding (peer mode)
+  int peer;                             // peer-window exchange: wait for every rank's row totals first
+  PeerArgs pa;
 };
 
 template <int SOLVER> struct K2Tune { enum { BLOCKS = SOLVER == FMWR_TDAP ? 3 : 6, UE = SOLVER == FMWR_TDAP ? 4 : 2 }; };
@@ -114,11 +204,11 @@ __device__ __forceinline__ void mb_intercept(const MbUpdArgs<T>& a)
     for (; r + (UN - 1) * 256 < a.rows; r += UN * 256) {
       T t[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) t[u] = a.mult[r + u * 256];
+      for (int u = 0; u < UN; ++u) t[u] = a.mult[(size_t)(r + u * 256) * a.mult_stride];
 #pragma unroll
       for (int u = 0; u < UN; ++u) acc += (double)t[u];
     }
-    for (; r < a.rows; r += 256) acc += (double)a.mult[r];
+    for (; r < a.rows; r += 256) acc += (double)a.mult[(size_t)r * a.mult_stride];
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -192,7 +282,7 @@ __device__ __forceinline__ void seg_issue(const MbUpdArgs<T>& a, const uint4 rec
       for (int st = 0; st < NST; ++st) sg.st[st][ch] = reinterpret_cast<const V16*>(a.sv[st] + off)[ch * LPR];
     }
   }
-  sg.m0 = a.mult[sg.r0];
+  sg.m0 = a.mult[sg.r0 * (uint32_t)a.mult_stride];
   if (a.k1 && l == 0) {
     sg.tw = a.w[sg.c];
     if (USE_STATE) {
@@ -255,7 +345,7 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
         const uint32_t rl = __shfl_sync(gmask, my_r, src) - rb32;
         xe[u] = T(__shfl_sync(gmask, my_x, src));
         const bool ok = rl < nrows;                // false for the padding lanes and for rows past a truncated batch
-        me[u] = ok ? a.mult[rl] : T(0);
+        me[u] = ok ? a.mult[rl * (uint32_t)a.mult_stride] : T(0);
         const T* sr = sbase + (ok ? rl : 0u) * (uint32_t)a.s_stride;
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) se[u][ch] = reinterpret_cast<const V16*>(sr)[ch * LPR];
@@ -348,6 +438,7 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 && CH == 1) ? K2Tune<SOLV
 {
   constexpr int G = 32 / LPR;
   constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+  if (a.peer) peer_wait(a.pa, PEER_FLAG2, PEER_EPOCH2);
   if (blockIdx.x == 0) { mb_intercept<T, SOLVER>(a); return; }
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, l = lane % LPR;
@@ -364,12 +455,17 @@ template <class T>
 struct MbLaunch {
   fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; const fmwr_solver_cfg* s;
   int64_t row_begin; int rows; T* mult; T* Scache; MbUpdArgs<T> ua; int phase;   // phase 0: K1, 1: K2
-  int s_stride; int partial;
+  int s_stride; int partial; PeerArgs pa;
   template <class TT, int LPR, int CH, int TEAM> void k1();
   template <class TT, int LPR, int CH>
   void run()
   {
-    if (phase == 0) {
+    if (phase == 2) {
+      constexpr int G = 32 / LPR;
+      const int xgrid = (int)std::min<int64_t>(ceil_div(pa.rows_per_owner, 8 * G), (int64_t)ctx->sm_count * 4);
+      FMWR_LAUNCH(ctx, (mb_exchange_kernel<TT, LPR, CH>), xgrid, 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
+                  m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, s_stride, pa);
+    } else if (phase == 0) {
       if (short_rows(d->nnz, d->n, LPR)) k1<TT, LPR, CH, LPR>();
       else k1<TT, LPR, CH, 32>();
     } else {
@@ -393,10 +489,11 @@ template <class TT, int LPR, int CH, int TEAM>
 void MbLaunch<T>::k1()
 {
   const int rpb = 8 * (32 / TEAM);
-  const int fgrid = (int)std::min<int64_t>(ceil_div(rows, rpb), (int64_t)ctx->sm_count * 16);
+  // peer mode: one release fence per CTA at the end (it waits for the CTA's NVLink stores), so few fat CTAs
+  const int fgrid = (int)std::min<int64_t>(ceil_div(rows, rpb), (int64_t)ctx->sm_count * (partial == 2 ? 4 : 16));
   FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH, TEAM>), fgrid, 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
               (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
-              m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial);
+              m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial, pa);
 }
 
 template <class T>
@@ -433,18 +530,37 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   const bool multi = ctx->nccl_comm != nullptr && ctx->world > 1;
   FMWR_REQUIRE(!(multi && s->step_size > 0), FMWR_ERR_UNSUPPORTED, "the tracker is not available on a feature-sharded model (score the gathered model instead)");
   const int s_stride = multi ? m->kp + 4 : m->kp;
+  // peer window open: the exchange runs inside our own kernels (NVLink stores + flags), no NCCL call per batch
+  const bool peer = multi && ctx->peer.ready && getenv("FMWR_NO_PEER") == nullptr;
+  PeerArgs pa;
+  memset(&pa, 0, sizeof pa);
   DBuf<T> mult, Scache;
-  mult.alloc(B);
+  if (peer) {
+    pa.rank = ctx->rank; pa.world = ctx->world;
+    pa.rows_per_owner = (int)ceil_div64(B, ctx->world);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    pa.off_P = PEER_CTL_BYTES;
+    pa.off_S = up(pa.off_P + (size_t)ctx->world * pa.rows_per_owner * s_stride * sizeof(T));
+    pa.off_mult = up(pa.off_S + (size_t)B * s_stride * sizeof(T));
+    FMWR_REQUIRE(up(pa.off_mult + (size_t)B * sizeof(T)) <= ctx->peer.bytes, FMWR_ERR_COMM,
+                 "peer window too small for this batch size / factor count (see fmwr_comm_peer_bytes)");
+    for (int r = 0; r < ctx->world; ++r) pa.base[r] = (char*)ctx->peer.base[r];
+  }
+  mult.alloc(peer ? 1 : B);
   FMWR_REQUIRE((uint64_t)B * (uint64_t)s_stride < (1ull << 32), FMWR_ERR_UNSUPPORTED, "batch_size x factors too large (the S cache is indexed with 32 bits)");
-  Scache.alloc((size_t)B * s_stride);
-  if (multi) FMWR_CUDA(cudaMemsetAsync(Scache.p, 0, Scache.bytes(), ctx->stream));
+  Scache.alloc(peer ? 1 : (size_t)B * s_stride);
+  if (multi && !peer) FMWR_CUDA(cudaMemsetAsync(Scache.p, 0, Scache.bytes(), ctx->stream));
+  T* sc_p = peer ? reinterpret_cast<T*>(pa.base[pa.rank] + pa.off_S) : Scache.p;
+  T* mult_p = peer ? sc_p + m->kp : mult.p;          // peer mode: the multiplier travels in the padding of the S-cache row
 
   MbLaunch<T> L;
-  L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = mult.p; L.Scache = Scache.p; L.s_stride = s_stride; L.partial = multi ? 1 : 0;
+  L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = mult_p; L.Scache = sc_p; L.s_stride = s_stride; L.partial = peer ? 2 : (multi ? 1 : 0);
+  L.pa = pa;
   MbUpdArgs<T>& ua = L.ua;
   memset(&ua, 0, sizeof ua);
   ua.seg_ptr = d->mb_seg_ptr.p; ua.seg_rec = d->mb_seg_rec.p; ua.ent_row = d->mb_ent_row.p; ua.ent_val = d->mb_ent_val.p;
-  ua.mult = mult.p; ua.Scache = Scache.p;
+  ua.mult = mult_p; ua.Scache = sc_p;
+  ua.peer = peer ? 1 : 0; ua.pa = pa; ua.mult_stride = peer ? s_stride : 1;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
   ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1; ua.s_stride = s_stride;
@@ -458,7 +574,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   // The per-batch launches are recorded into CUDA graphs (chunks of GRAPH_CHUNK batches) and replayed by the device,
   // so the epoch does not depend on host launch latency / host jitter.  Per-kernel profiling, the tracker and the
   // NCCL path use plain launches.
-  const bool use_graph = !ctx->profile && step <= 0 && !multi && getenv("FMWR_NO_GRAPH") == nullptr;
+  const bool use_graph = !ctx->profile && step <= 0 && (!multi || peer) && getenv("FMWR_NO_GRAPH") == nullptr;
   constexpr int GRAPH_CHUNK = 2048;
   std::vector<cudaGraphExec_t> execs;
   std::vector<cudaGraph_t> graphs;
@@ -482,7 +598,10 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
       L.row_begin = rb; L.rows = (int)rows;
       L.phase = 0;
       dispatch_layout<T>(m->kp, L);
-      if (multi) {
+      if (peer) {
+        L.phase = 2;
+        dispatch_layout<T>(m->kp, L);
+      } else if (multi) {
         // one exchange per minibatch: sum the per-row partials over the feature shards (NCCL over NVLink / NVSwitch)
         comm_allreduce_sum(ctx, Scache.p, (size_t)rows * s_stride, sizeof(T) == 8);
         FMWR_LAUNCH(ctx, mb_finalize_kernel<T>, ceil_div(rows, 8), 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
@@ -510,6 +629,11 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   }
   flush_graph();
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (peer) {
+    uint32_t err = 0;
+    FMWR_CUDA(cudaMemcpy(&err, reinterpret_cast<uint32_t*>(pa.base[pa.rank]) + PEER_ERR, 4, cudaMemcpyDeviceToHost));
+    FMWR_REQUIRE(err == 0, FMWR_ERR_COMM, "a peer rank did not reach the in-kernel barrier (timeout); the model is invalid");
+  }
   for (auto ge : execs) cudaGraphExecDestroy(ge);
   for (auto g : graphs) cudaGraphDestroy(g);
   if (tr) { tr->n_rec = n_rec; tr->convergent = convergent; tr->iters_done = (int)iter; }

@@ -52,3 +52,16 @@ def exchange_unique_id(dist, ctx_cls, rank):
         t = torch.zeros(128, dtype=torch.uint8)
     dist.broadcast(t, src=0)
     return bytes(t.tolist())
+
+
+def open_peer_windows(dist, ctx, rank, world, batch_size, k):
+    """map every rank's exchange window into every other rank (CUDA IPC over NVLink): afterwards the feature-parallel
+    minibatch path exchanges its per-row partials inside its own kernels instead of calling NCCL (csrc/train_minibatch.cu)"""
+    import torch
+    nbytes = ctx.comm_peer_bytes(batch_size, k, world)
+    mine = ctx.comm_peer_alloc(nbytes)
+    t = torch.tensor(list(mine), dtype=torch.uint8)
+    allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(allh, t)
+    ctx.comm_peer_open([bytes(h.tolist()) for h in allh])
+    dist.barrier()          # every window is zeroed and mapped before anyone stores into it

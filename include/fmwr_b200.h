@@ -167,6 +167,16 @@ int fmwr_data_slice_columns(fmwr_data* d, int64_t col_begin, int64_t col_end, fm
 int fmwr_comm_unique_id(uint8_t* id128);
 int fmwr_comm_init(fmwr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
 int fmwr_comm_destroy(fmwr_ctx* ctx);
+/* Peer window (optional, after fmwr_comm_init): every rank allocates `bytes` of device memory that the other ranks of
+ * the box map through CUDA IPC.  With a window open, the per-batch exchange of the feature-parallel path no longer
+ * calls NCCL: the forward kernel stores its partials straight into the owning rank's memory over NVLink, the owner
+ * sums them in a fixed order and stores the row totals into every rank, with in-kernel release/acquire flags as the
+ * only synchronisation (csrc/train_minibatch.cu).  fmwr_comm_peer_bytes gives the size needed for a batch size and
+ * factor count; the 64-byte handles of all ranks (rank order) go to fmwr_comm_peer_open on every rank, and the host
+ * must place a barrier between the last fmwr_comm_peer_open and the first training call. */
+int64_t fmwr_comm_peer_bytes(int64_t batch_size, int32_t k, int32_t world);
+int fmwr_comm_peer_alloc(fmwr_ctx* ctx, int64_t bytes, uint8_t* handle64);
+int fmwr_comm_peer_open(fmwr_ctx* ctx, const uint8_t* handles /*[world][64]*/);
 
 /* ---- model ---- */
 int fmwr_model_create(fmwr_ctx* ctx, const fmwr_model_cfg* cfg, int64_t p, int32_t precision, fmwr_model** out);

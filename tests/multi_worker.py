@@ -26,38 +26,42 @@ def main():
     w = rng.normal(0, 0.05, p); v = rng.normal(0, 0.05, (p, k)); w0 = 0.1
     f0, f1, c0, c1 = multi.field_partition(fields, world)[rank]
     ok = True
-    for solver, prec, tol in ((L.FTRL, L.F64, 1e-9), (L.SGD, L.F64, 1e-9), (L.TDAP, L.F64, 1e-7), (L.FTRL, L.F32, 2e-4)):
-        iters = 2 * (n - 1) + 77
-        mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l1_w1=1e-3, l2_w1=1e-3, l2_v=1e-3)
-        sc = L.SolverCfg(solver=solver, max_iter=iters, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
-                         gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=prec,
-                         compat=L.COMPAT_SKIP_ROW0, step_size=-1)
-        full = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)
-        part = full.slice_columns(c0, c1)
-        full.close()
-        m = L.Model(ctx, mc, c1 - c0, prec)
-        m.set(w0, w[c0:c1], v[c0:c1])
-        L.train_dev(ctx, m, part, sc)
-        mine = m.get()
-        m.close(); part.close()
-        parts = [None] * world
-        dist.all_gather_object(parts, mine)
-        if rank == 0:
-            gw0, gw, gv = multi.gather_model(parts)
-            solo = L.Context(local)                      # no communicator: the single-GPU path
-            d1 = L.Data.from_csr32(solo, n, p, rowptr, col, val, y)
-            m1 = L.Model(solo, mc, p, prec)
-            m1.set(w0, w, v)
-            L.train_dev(solo, m1, d1, sc)
-            sw0, sw, sv = m1.get()
-            m1.close(); d1.close(); solo.close()
-            err = max(abs(gw0 - sw0), float(np.max(np.abs(gw - sw) / np.maximum(1, np.abs(sw)))),
-                      float(np.max(np.abs(gv - sv) / np.maximum(1, np.abs(sv)))))
-            moved = float(np.max(np.abs(sv - v)))
-            print("solver=%d prec=%d world=%d max rel err vs single GPU = %.3e (params moved by %.3e)" % (solver, prec, world, err, moved), flush=True)
-            ok = ok and err < tol and moved > 1e-3
-            for q in parts[1:]:
-                ok = ok and q[0] == parts[0][0]          # w0 is replicated bit for bit
+    for exchange in ("nccl", "peer"):
+      if exchange == "peer":
+          # same runs again with the peer windows open: partials exchanged by our own kernels over NVLink, no NCCL call
+          multi.open_peer_windows(dist, ctx, rank, world, B, k)
+      for solver, prec, tol in ((L.FTRL, L.F64, 1e-9), (L.SGD, L.F64, 1e-9), (L.TDAP, L.F64, 1e-7), (L.FTRL, L.F32, 2e-4)):
+          iters = 2 * (n - 1) + 77
+          mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l1_w1=1e-3, l2_w1=1e-3, l2_v=1e-3)
+          sc = L.SolverCfg(solver=solver, max_iter=iters, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                           gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=prec,
+                           compat=L.COMPAT_SKIP_ROW0, step_size=-1)
+          full = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)
+          part = full.slice_columns(c0, c1)
+          full.close()
+          m = L.Model(ctx, mc, c1 - c0, prec)
+          m.set(w0, w[c0:c1], v[c0:c1])
+          L.train_dev(ctx, m, part, sc)
+          mine = m.get()
+          m.close(); part.close()
+          parts = [None] * world
+          dist.all_gather_object(parts, mine)
+          if rank == 0:
+              gw0, gw, gv = multi.gather_model(parts)
+              solo = L.Context(local)                      # no communicator: the single-GPU path
+              d1 = L.Data.from_csr32(solo, n, p, rowptr, col, val, y)
+              m1 = L.Model(solo, mc, p, prec)
+              m1.set(w0, w, v)
+              L.train_dev(solo, m1, d1, sc)
+              sw0, sw, sv = m1.get()
+              m1.close(); d1.close(); solo.close()
+              err = max(abs(gw0 - sw0), float(np.max(np.abs(gw - sw) / np.maximum(1, np.abs(sw)))),
+                        float(np.max(np.abs(gv - sv) / np.maximum(1, np.abs(sv)))))
+              moved = float(np.max(np.abs(sv - v)))
+              print("exchange=%s solver=%d prec=%d world=%d max rel err vs single GPU = %.3e (params moved by %.3e)" % (exchange, solver, prec, world, err, moved), flush=True)
+              ok = ok and err < tol and moved > 1e-3
+              for q in parts[1:]:
+                  ok = ok and q[0] == parts[0][0]          # w0 is replicated bit for bit
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     ctx.comm_destroy(); ctx.close()

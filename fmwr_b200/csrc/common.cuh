@@ -194,6 +194,10 @@ struct fmwr_model {
 
 namespace fmwr {
 
+// NCCL all-reduces on the context's stream (comm.cu)
+void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
+void comm_allreduce_max_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count);
+
 // ---- device helpers ----------------------------------------------------------------------------
 #ifdef __CUDACC__
 template <class T>

@@ -328,6 +328,9 @@ void phases_build(fmwr_data* d)
   prev.alloc(p);
   prev.zero(ctx->stream);
   if (n > 0) FMWR_LAUNCH(ctx, phase_prev, ceil_div(n * 32, 256), 256, 0, d->rowptr.p, d->col.p, n, prev.p);
+  // row-sharded data (communicator initialised): the phases must come from the UNION of the shards' rows, or the ranks
+  // would disagree on the coordinate steps they all-reduce
+  if (ctx->nccl_comm && ctx->world > 1 && p > 0) comm_allreduce_max_u32(ctx, prev.p, (size_t)p);
   std::vector<uint32_t> h(p);
   FMWR_CUDA(cudaMemcpyAsync(h.data(), prev.p, sizeof(uint32_t) * p, cudaMemcpyDeviceToHost, ctx->stream));
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -29,6 +29,8 @@ template <class T> struct Vec2;
 template <> struct Vec2<float> { typedef float2 type; };
 template <> struct Vec2<double> { typedef double2 type; };
 
+void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
+
 constexpr int ALS_LONG = 4096;      // columns at least this long get a whole CTA
 
 // ---- forward: e = raw score, q[r][:] = S_f -----------------------------------------------------------
@@ -174,7 +176,7 @@ __device__ double trnorm_left_std(UnifStream& s, double left)
 // mode 0: regression e -= y; 1: ALS classification hazard table; 2: MCMC classification, truncated-normal draw
 template <class T>
 __global__ void als_error_kernel(T* __restrict__ e, const float* __restrict__ y, int64_t n, int mode,
-                                 const double* __restrict__ dpY, uint64_t seed, uint64_t sweep)
+                                 const double* __restrict__ dpY, uint64_t seed, uint64_t sweep, uint64_t row_offset)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -185,7 +187,7 @@ __global__ void als_error_kernel(T* __restrict__ e, const float* __restrict__ y,
   } else if (mode == 1) {
     e[i] = T(yi >= 0.0f ? -dev_fast_dpnorm(dpY, -s) : dev_fast_dpnorm(dpY, s));
   } else {
-    UnifStream us{nullptr, 0, nullptr, splitmix64(seed ^ (sweep * 0xD6E8FEB86659FD93ull) ^ (uint64_t)i), 0};
+    UnifStream us{nullptr, 0, nullptr, splitmix64(seed ^ (sweep * 0xD6E8FEB86659FD93ull) ^ (row_offset + (uint64_t)i)), 0};
     // as shipped: N(0,1) truncated at the score (reference :536-539)
     const double t = yi >= 0.0f ? trnorm_left_std(us, s) : -trnorm_left_std(us, -s);
     e[i] = T(s - t);
@@ -713,6 +715,7 @@ static void run_phases_rm(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, cons
       else if (a.n_hot > 0) FMWR_LAUNCH(ctx, (rm_stats_kernel<T, 2>), grid, 256, 0, a);
       else FMWR_LAUNCH(ctx, (rm_stats_kernel<T, 0>), grid, 256, 0, a);
     }
+    if (ctx->nccl_comm && ctx->world > 1) comm_allreduce_sum(ctx, a.AB, 2 * (size_t)a.ncols, sizeof(T) == 8);
     FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(a.ncols, 256), 256, 0, a);
     if (a.pe > a.pb) {
       const int grid = (int)std::min<int64_t>(grid_stream, ceil_div64(a.pe - a.pb, 256));
@@ -973,6 +976,31 @@ static int fused_replicas(uint32_t ncols, int grid)
 template <class T>
 static size_t fused_ab_elems(uint32_t max_cols) { return std::max<size_t>(2 * (size_t)max_cols, FUSED_AB_BYTES / sizeof(T)); }
 
+// row-sharded multi-GPU: sum the table's replicas into replica 0 (and clear the others) so that ONE all-reduce of
+// 2 * ncols values per coordinate step carries this rank's statistics
+template <class T>
+__global__ void ab_collapse_kernel(T* __restrict__ AB, uint32_t ncols, int n_rep)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;        // index into the interleaved [2 * ncols] table
+  if (i >= 2 * ncols) return;
+  T s = AB[i];
+  for (int r = 1; r < n_rep; ++r) { s += AB[(size_t)r * 2 * ncols + i]; AB[(size_t)r * 2 * ncols + i] = T(0); }
+  AB[i] = s;
+}
+
+// sum of a host double over the ranks (identical bits on every rank afterwards)
+static double allreduce_scalar(fmwr_ctx* ctx, double x)
+{
+  if (!(ctx->nccl_comm && ctx->world > 1)) return x;
+  ctx->red_scratch.ensure(1024);
+  FMWR_CUDA(cudaMemcpyAsync(ctx->red_scratch.p, &x, 8, cudaMemcpyHostToDevice, ctx->stream));
+  comm_allreduce_sum(ctx, ctx->red_scratch.p, 1, true);
+  double r = 0;
+  FMWR_CUDA(cudaMemcpyAsync(&r, ctx->red_scratch.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return r;
+}
+
 // one coordinate step of a fused sequence
 template <class T>
 struct Step { int phase; T* q; int f; T* theta; int64_t stride; double lambda, mu; int w_sd_is_var; long long normal_base; };
@@ -1028,6 +1056,11 @@ static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, co
     } else {
       if (dl.all_ones) FMWR_LAUNCH(ctx, (fused_kernel<T, 1, true>), grid, FUSED_THREADS, 0, fa);
       else FMWR_LAUNCH(ctx, (fused_kernel<T, 1, false>), grid, FUSED_THREADS, 0, fa);
+    }
+    if (t < T_ && ctx->nccl_comm && ctx->world > 1) {
+      // rows are sharded over the ranks: every rank holds partial (A, B); one all-reduce per coordinate step
+      if (ra.n_rep > 1) FMWR_LAUNCH(ctx, ab_collapse_kernel<T>, ceil_div(2 * (int64_t)ra.ncols, 256), 256, 0, ra.AB, ra.ncols, ra.n_rep);
+      comm_allreduce_sum(ctx, ra.AB, 2 * (size_t)ra.ncols, sizeof(T) == 8);
     }
     if (t < T_) {
       if (t + 1 < T_) {
@@ -1125,6 +1158,26 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   const bool enable_v = s->enable_v && k > 0;
   FMWR_REQUIRE(n < (1ll << 31) && p < (1ll << 31), FMWR_ERR_UNSUPPORTED, "dimension too large");
 
+  // Row-sharded multi-GPU (communicator initialised): the data handle is this rank's ROWS, the model is replicated.
+  // Every rank runs the same sweep; per-feature statistics and the two residual sums are all-reduced, so all ranks
+  // derive bit-identical parameters (and, for MCMC, identical draws: same seeds, same reduced inputs).
+  const bool multi = ctx->nccl_comm != nullptr && ctx->world > 1;
+  double n_glob = (double)n;
+  int64_t row_off = 0;
+  if (multi) {
+    FMWR_REQUIRE(s->step_size <= 0, FMWR_ERR_UNSUPPORTED, "the tracker is not available on row-sharded data (score the shards separately)");
+    FMWR_REQUIRE(!s->rands, FMWR_ERR_UNSUPPORTED, "an injected rand() stream is consumed in global row order: single GPU only");
+    ctx->red_scratch.ensure(1024);
+    std::vector<double> cnt(ctx->world, 0.0);
+    cnt[ctx->rank] = (double)n;
+    FMWR_CUDA(cudaMemcpyAsync(ctx->red_scratch.p, cnt.data(), 8 * ctx->world, cudaMemcpyHostToDevice, ctx->stream));
+    comm_allreduce_sum(ctx, ctx->red_scratch.p, ctx->world, true);
+    FMWR_CUDA(cudaMemcpyAsync(cnt.data(), ctx->red_scratch.p, 8 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    n_glob = 0;
+    for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) row_off += (int64_t)cnt[r]; n_glob += cnt[r]; }
+  }
+
   transpose_build(d);                                                    // src/FM.cpp:148-152
   struct AlsCache { PhaseInfo ph; RowMajor rm; DenseLayout dl; bool rm_tried = false; };
   if (d->als_cache && s->rands && static_cast<AlsCache*>(d->als_cache.get())->dl.permuted) d->als_cache.reset();
@@ -1141,6 +1194,7 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   RowMajor& rm = cache.rm;
   const int n_phases = (int)ph.begin.size() - 1;
   const bool use_rm = n_phases <= 256 && d->nnz > 0 && getenv("FMWR_ALS_COLUMN") == nullptr;
+  FMWR_REQUIRE(!multi || use_rm, FMWR_ERR_UNSUPPORTED, "row-sharded ALS/MCMC needs phase-decomposable (field-structured) data");
   DBuf<T> rm_th, rm_AB, rm_delta, rm_th2, rm_AB2, rm_delta2, rm_thd, rm_thd2;
   DenseLayout& dl = cache.dl;
   if (use_rm) {
@@ -1216,27 +1270,27 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
     dispatch_layout<T>(kp, fw);
     // calculate_error (:520-562)
     if (!cls) {
-      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 0, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 0, ctx->dp_table.p, s->seed, (uint64_t)sweep, (uint64_t)row_off);
     } else if (!do_sample) {
-      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 1, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 1, ctx->dp_table.p, s->seed, (uint64_t)sweep, (uint64_t)row_off);
     } else if (s->rands) {
       FMWR_LAUNCH(ctx, als_error_stream_kernel<T>, 1, 32, 0, e.p, d->y.p, n, rands_dev.p, (long long)s->n_rands, rand_pos.p);
     } else {
-      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 2, ctx->dp_table.p, s->seed, (uint64_t)sweep);
+      FMWR_LAUNCH(ctx, als_error_kernel<T>, ceil_div(n, 256), 256, 0, e.p, yp, n, 2, ctx->dp_table.p, s->seed, (uint64_t)sweep, (uint64_t)row_off);
     }
     // update_alpha (:360-380)
     if (!do_multilevel) alpha = alpha_0;
     else {
-      const double alpha_n = alpha_0 + (double)n;
-      const double gamma_n = gamma_0 + reduce<T>(ctx, e.p, n, 1, 1, 0.0);
+      const double alpha_n = alpha_0 + n_glob;
+      const double gamma_n = gamma_0 + allreduce_scalar(ctx, reduce<T>(ctx, e.p, n, 1, 1, 0.0));
       const double a = hs.gamma(alpha_n / 2.0, 2.0 / gamma_n);
       if (!hbad(a)) alpha = a;
     }
     // update_w0 (:162-188)
     if (m->cfg.keep_w0) {
       const double w0 = model_get_w0(m);
-      const double err = reduce<T>(ctx, e.p, n, 1, 0, 0.0) - (double)n * w0;
-      const double var = 1.0 / (m->cfg.l2_w0 + alpha * (double)n);
+      const double err = allreduce_scalar(ctx, reduce<T>(ctx, e.p, n, 1, 0, 0.0)) - n_glob * w0;
+      const double var = 1.0 / (m->cfg.l2_w0 + alpha * n_glob);
       const double mean = -(alpha * err - w0_mean_0 * m->cfg.l2_w0) * var;
       double nw = do_sample ? hs.normal(mean, std::sqrt(var)) : mean;
       if (hbad(nw)) nw = w0;

@@ -23,3 +23,11 @@ def test_feature_parallel_equals_single_gpu():
            "--master-port", "29611", os.path.join(ROOT, "tests", "multi_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_row_sharded_als_mcmc_equals_single_gpu():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29612", os.path.join(ROOT, "tests", "multi_worker_als.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "MULTI_ALS_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

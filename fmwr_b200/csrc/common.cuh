@@ -165,6 +165,11 @@ struct fmwr_data {
   fmwr::DBuf<uint32_t> mb_ent_row;   // [nnz'] global row index
   fmwr::DBuf<float> mb_ent_val;      // [nnz']
   std::vector<int64_t> mb_batch_seg;  // [n_batches+1] segment offsets per batch (host)
+  // one-shot training path: the value stream may still be uploading on the copy stream while the compute stream already
+  // sorts the (batch, feature) keys; val_ready marks its end (data.cu: data_wait_values)
+  cudaEvent_t val_ready = nullptr;
+  fmwr::DBuf<double> val_stage[2];
+  ~fmwr_data() { if (val_ready) { cudaEventSynchronize(val_ready); cudaEventDestroy(val_ready); } }
   // ALS/MCMC layouts (phases, row-major / dense copies), built on first use, dropped when the values change
   std::shared_ptr<void> als_cache;
   // last forward result

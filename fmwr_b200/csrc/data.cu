@@ -140,8 +140,56 @@ static void set_labels(fmwr_data* d, const float* y)
   FMWR_CUDA(cudaStreamSynchronize(d->ctx->stream));
 }
 
+// labels: f64 -> f32 on the device and Data::add_target's min / max (reference src/core/Data.h:80-84) by a device reduction
+__global__ void labels_narrow_minmax(const double* __restrict__ in, float* __restrict__ out, int64_t n, float* __restrict__ mm)
+{
+  __shared__ float smn[8], smx[8];
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float y = (float)in[i];
+    out[i] = y;
+    mn = fminf(mn, y); mx = fmaxf(mx, y);
+  }
+  for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    mm[2 * blockIdx.x] = mn; mm[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+static void set_labels_f64(fmwr_data* d, const double* labels)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t n = d->n;
+  d->has_labels = true;
+  d->y.alloc(n);
+  d->min_y = INFINITY; d->max_y = -INFINITY;
+  if (n == 0) return;
+  DBuf<double> stage;
+  stage.alloc(n);
+  const int nblk = (int)std::min<int64_t>(512, ceil_div64(n, 256));
+  DBuf<float> mm;
+  mm.alloc(2 * (size_t)nblk);
+  FMWR_CUDA(cudaMemcpyAsync(stage.p, labels, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+  FMWR_LAUNCH(ctx, labels_narrow_minmax, nblk, 256, 0, stage.p, d->y.p, n, mm.p);
+  std::vector<float> h(2 * (size_t)nblk);
+  FMWR_CUDA(cudaMemcpyAsync(h.data(), mm.p, 8 * (size_t)nblk, cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  float mn = INFINITY, mx = -INFINITY;
+  for (int b = 0; b < nblk; ++b) { mn = std::min(mn, h[2 * b]); mx = std::max(mx, h[2 * b + 1]); }
+  d->min_y = mn; d->max_y = mx;
+}
+
+// the compute stream waits for a deferred value upload (no-op otherwise)
+void data_wait_values(fmwr_data* d)
+{
+  if (d->val_ready) FMWR_CUDA(cudaStreamWaitEvent(d->ctx->stream, d->val_ready, 0));
+}
+
 fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, const int32_t* row_size,
-                           const int32_t* col_idx, const double* value, const double* labels)
+                           const int32_t* col_idx, const double* value, const double* labels, bool defer_values)
 {
   FMWR_REQUIRE(n >= 0 && p >= 0 && nnz >= 0, FMWR_ERR_ARG, "negative dimension");
   FMWR_REQUIRE(nnz < (int64_t)0xffffffffll && n < (int64_t)0xffffffffll && p < (int64_t)0xffffffffll, FMWR_ERR_UNSUPPORTED,
@@ -166,22 +214,35 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
     }
     if (nnz > 0) {
       FMWR_CUDA(cudaMemcpyAsync(d->col.p, col_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
-      // f64 -> f32 narrowing on the device, chunked so the f64 staging buffer stays small
-      const int64_t chunk = 32ll << 20;
-      DBuf<double> stage;
-      stage.alloc(std::min(chunk, nnz));
-      for (int64_t off = 0; off < nnz; off += chunk) {
+      // f64 -> f32 narrowing on the device, chunked through two staging buffers.  defer_values: the chunks travel on the
+      // copy stream and nobody waits here -- the one-shot training path sorts the (batch, feature) keys (which need only
+      // rowptr and col) while the 8-byte values are still crossing PCIe, and waits for val_ready before it reads them.
+      const int64_t chunk = 16ll << 20;
+      cudaStream_t vs = defer_values ? ctx->copy_stream : ctx->stream;
+      d->val_stage[0].alloc(std::min(chunk, nnz));
+      d->val_stage[1].alloc(nnz > chunk ? std::min(chunk, nnz - chunk) : 1);
+      cudaEvent_t free_ev[2] = {nullptr, nullptr};
+      int ci = 0;
+      for (int64_t off = 0; off < nnz; off += chunk, ci ^= 1) {
         const int64_t m = std::min(chunk, nnz - off);
-        FMWR_CUDA(cudaMemcpyAsync(stage.p, value + off, sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
-        FMWR_LAUNCH(ctx, f64_to_f32, ceil_div(m, 256), 256, 0, stage.p, d->val.p + off, m);
+        if (free_ev[ci]) FMWR_CUDA(cudaStreamWaitEvent(vs, free_ev[ci], 0));
+        FMWR_CUDA(cudaMemcpyAsync(d->val_stage[ci].p, value + off, sizeof(double) * m, cudaMemcpyHostToDevice, vs));
+        f64_to_f32<<<ceil_div(m, 256), 256, 0, vs>>>(d->val_stage[ci].p, d->val.p + off, m);
+        ctx->launches++;
+        FMWR_CUDA(cudaGetLastError());
+        if (!free_ev[ci]) FMWR_CUDA(cudaEventCreateWithFlags(&free_ev[ci], cudaEventDisableTiming));
+        FMWR_CUDA(cudaEventRecord(free_ev[ci], vs));
       }
-      FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int i = 0; i < 2; ++i) if (free_ev[i]) cudaEventDestroy(free_ev[i]);
+      if (defer_values) {
+        FMWR_CUDA(cudaEventCreateWithFlags(&d->val_ready, cudaEventDisableTiming));
+        FMWR_CUDA(cudaEventRecord(d->val_ready, vs));
+      } else {
+        FMWR_CUDA(cudaStreamSynchronize(vs));
+        d->val_stage[0].release(); d->val_stage[1].release();
+      }
     }
-    if (labels) {
-      std::vector<float> y(n);
-      for (int64_t i = 0; i < n; ++i) y[i] = (float)labels[i];
-      set_labels(d, y.data());
-    }
+    if (labels) set_labels_f64(d, labels);
     finish_create(d);
   } catch (...) { delete d; throw; }
   return d;
@@ -464,6 +525,7 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_CUDA(cudaMemcpy(&last_head, head.p + (m - 1), 4, cudaMemcpyDeviceToHost));
   const uint32_t n_seg = last_id + last_head;
   d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_rec.alloc(n_seg);
+  data_wait_values(d);
   FMWR_LAUNCH(ctx, mb_emit<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, idx_out.p, erow.p, d->val.p, e0, m,
               colbits, d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
   FMWR_LAUNCH(ctx, mb_seg_len, ceil_div(n_seg, 256), 256, 0, d->mb_seg_ptr.p, d->mb_seg_rec.p, n_seg);

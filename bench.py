@@ -223,6 +223,11 @@ def run_engine(args):
     k1 = prof_train.get("mb_forward_kernel")
     kernels = {name: {"launches": v[0], "ms": round(v[1], 3)} for name, v in prof_train.items()}
 
+    # ---- the other solvers of the north_star (secondary lines) ------------------------------------------------------
+    solvers = None
+    if not args.no_solvers:
+        solvers = run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B)
+
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -248,12 +253,66 @@ def run_engine(args):
         "kernels": kernels,
         "predict": {"value": round(pred_rps, 1), "unit": "rows/s", "ms_per_step": round(ms_pred / args.steps, 3),
                     "roofline": fwd_roof},
+        "solvers": solvers,
         "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(l1 - l0),
         "clocks": clk, "setup_s": round(t_gen, 2),
     }
     print(json.dumps(out), flush=True)
     data.close(); model.close(); ctx.close()
+
+
+def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B):
+    """the north_star's other training paths, same timing rules (3 warm-ups, CUDA events, data resident): SGD and TDAP
+    minibatch epochs on the configs[1] matrix already on the device; one ALS sweep on configs[2] and one MCMC sweep on
+    configs[3] (MovieLens-shaped 20M ratings, 3 one-hot fields).  Fractions are against SURVEY 8(d)'s algorithmic bytes."""
+    out = {}
+    steps = max(1, min(args.steps, 3))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ctx.sync(); ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        return ctx.timer_stop_ms() / steps
+
+    for name, solver in (("sgd", L.SGD), ("tdap", L.TDAP)):
+        mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=0.0 if name == "sgd" else 1e-3, l2_w1=1e-3,
+                        l1_v=0.0, l2_v=1e-3)
+        m = L.Model(ctx, mc, p, L.F32)
+        m.init_random(0.0, 0.01, 20240603)
+        sc = L.SolverCfg(solver=solver, max_iter=n - 1, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                         gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F32,
+                         compat=L.COMPAT_REFERENCE, step_size=-1)
+        ms = timed(lambda: L.train_dev(ctx, m, data, sc))
+        b = ALG_BYTES[name](F, k)
+        sps = (n - 1) / (ms * 1e-3)
+        out[name] = {"workload": "configs[1] matrix, %s minibatch epoch (batch %d)" % (name.upper(), B), "value": round(sps, 1), "unit": "samples/s",
+                     "ms_per_step": round(ms, 3), "alg_bytes_per_sample": b, "achieved_gbs": round(sps * b / 1e9, 1), "frac": round(sps * b / 1e9 / peak, 4)}
+        m.close()
+    if args.rows < 1_000_000:
+        return out                                  # reduced smoke runs: skip the 20M-rating sweeps
+    na = 20_000_000
+    fields = [138493, 26744, 2048]
+    pa, Na = sum(fields), 3 * na
+    da = L.Data.synth(ctx, na, fields, [0, 1, 0], 0, 3, 0.3, 20240601)
+    for name, solver, ka in (("als", L.ALS, 32), ("mcmc", L.MCMC, 64)):
+        mc = L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=ka)
+        m = L.Model(ctx, mc, pa, L.F32)
+        m.init_random(0.0, 0.01, 20240603)
+        sc = L.SolverCfg(solver=solver, max_iter=1, random_step=1, min_target=0.5, max_target=5.0, mode=L.MODE_EXACT, precision=L.F32,
+                         compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=5)
+        ms = timed(lambda: L.train_dev(ctx, m, da, sc))
+        bfwd = 8 + 3 * (12 + 4 * ka)
+        sweep_bytes = na * bfwd + 16 * na + 16 * Na + ka * (32 * Na + 4 * na + 8 * pa) + (8 * na if name == "mcmc" else 0)
+        out[name] = {"workload": "configs[%d]: %d ratings x 3 one-hot fields (138493 / 26744 skewed / 2048), k=%d, one %s sweep (w and V blocks)" % (
+                         2 if name == "als" else 3, na, ka, name.upper()),
+                     "value": round(na / (ms * 1e-3), 1), "unit": "ratings/s", "ms_per_step": round(ms, 3), "alg_bytes_per_sweep": sweep_bytes,
+                     "achieved_gbs": round(sweep_bytes / (ms * 1e-3) / 1e9, 1), "frac": round(sweep_bytes / (ms * 1e-3) / 1e9 / peak, 4)}
+        m.close()
+    da.close()
+    return out
 
 
 def run_e2e(L, lib, ctx, data, mcfg, sc, n, p, k, args):
@@ -516,6 +575,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-solvers", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)

@@ -91,3 +91,17 @@ def test_enum_values_are_the_references():
     assert (L.CLASSIFICATION, L.REGRESSION) == (10, 20)
     assert (L.MCMC, L.ALS, L.SGD, L.FTRL, L.TDAP) == (100, 200, 300, 500, 600)
     assert (L.LL, L.AUC, L.ACC, L.RMSE, L.MSE, L.MAE) == (0, 111, 222, 333, 444, 555)
+
+
+def test_peer_window_size_covers_its_regions():
+    # fmwr_comm_peer_bytes (host-only arithmetic): control block + world x ceil(B/world) partial rows + B total rows, any precision
+    for B, k, world in ((65536, 32, 2), (65536, 32, 8), (512, 8, 2), (1000, 100, 3), (1, 0, 2)):
+        got = L.Context.comm_peer_bytes(B, k, world)
+        kp = max(4, 1 << (max(k, 1) - 1).bit_length())              # padded factor count never exceeds the next power of two (>= 4)
+        stride = kp + 4
+        rpo = -(-B // world)
+        need = 4096 + 8 * (world * rpo * stride + B * stride) + 2 * 256
+        assert got >= need, (B, k, world, got, need)
+    assert L.Context.comm_peer_bytes(0, 8, 2) == 0 and L.Context.comm_peer_bytes(16, 8, 0) == 0
+    # a window cannot be allocated without a communicator
+    assert L.lib().fmwr_comm_peer_alloc(None, C.c_int64(1 << 20), None) != 0

@@ -185,7 +185,7 @@ __device__ __forceinline__ T team_sum(T x)
 #define FMWR_FWD_BLOCKS 4
 #endif
 // factor rows in flight per sub-group: long rows (warp team) take the experiment knobs, short rows 4
-template <int LPR, int TEAM = 32> struct GatherDepth { enum { U = LPR >= 16 ? 8 : (TEAM == 32 ? FMWR_FWD_U : 4) }; };
+template <int LPR, int TEAM = 32> struct GatherDepth { enum { U = TEAM != 32 ? 4 : (LPR >= 16 ? 8 : FMWR_FWD_U) }; };
 
 // score (no link) of the team's row, identical in every lane of the team
 template <class T, int LPR, int CH, int TEAM>

@@ -52,7 +52,8 @@ struct FwdLaunch {
   {
     const int block = 256, rpb = (block / 32) * (32 / TEAM);
     int64_t want = ceil_div64(d->n, rpb);
-    int64_t cap = (int64_t)ctx->sm_count * 8 * 4;   // 4 waves of 8 resident CTAs per SM, grid-stride beyond that
+    static const int fwd_ctas = getenv("FMWR_FWD_CTAS") ? atoi(getenv("FMWR_FWD_CTAS")) : 32;
+    int64_t cap = (int64_t)ctx->sm_count * fwd_ctas;   // CTAs per SM, grid-stride beyond that
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     // predictions are always kept in fp64 (8 of ~5.5 KB per row): the R side wants a NumericVector and the

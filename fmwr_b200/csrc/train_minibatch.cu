@@ -442,13 +442,16 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 && CH == 1) ? K2Tune<SOLV
   if (blockIdx.x == 0) { mb_intercept<T, SOLVER>(a); return; }
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, l = lane % LPR;
-  const uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g;
-  if (seg >= a.seg_end) return;
-  const uint4 rec = __ldg(a.seg_rec + seg);
-  const uint32_t eb = __ldg(a.seg_ptr + seg);
-  SegStage<T, CH, NST> sg;
-  seg_issue<T, LPR, CH, SOLVER, L1>(a, rec, eb, l, true, sg);
-  seg_finish<T, LPR, CH, SOLVER, L1>(a, g, l, sg);
+  // grid-stride over the batch's segments: with a grid of (resident CTAs) the warps stay on the SM for the whole launch
+  // instead of being re-created every 4 segments (FMWR_K2_ONESHOT=1 launches one group per segment as before)
+  const uint32_t stride = (gridDim.x - 1) * (blockDim.x >> 5) * G;
+  for (uint32_t seg = a.seg_begin + ((blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + g; seg < a.seg_end; seg += stride) {
+    const uint4 rec = __ldg(a.seg_rec + seg);
+    const uint32_t eb = __ldg(a.seg_ptr + seg);
+    SegStage<T, CH, NST> sg;
+    seg_issue<T, LPR, CH, SOLVER, L1>(a, rec, eb, l, true, sg);
+    seg_finish<T, LPR, CH, SOLVER, L1>(a, g, l, sg);
+  }
 }
 
 template <class T>
@@ -471,7 +474,12 @@ struct MbLaunch {
     } else {
       constexpr int G = 32 / LPR;
       const uint32_t nseg = ua.seg_end - ua.seg_begin;
-      const int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
+      int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
+      {
+        static const int persist = getenv("FMWR_K2_ONESHOT") ? 0 : (getenv("FMWR_K2_WAVES") ? atoi(getenv("FMWR_K2_WAVES")) : 1);
+        const int resident = (sizeof(TT) == 4 && CH == 1) ? (s->solver == FMWR_TDAP ? 3 : 6) : 2;
+        if (persist > 0) grid = std::min(grid, ctx->sm_count * resident * persist + 1);
+      }
       switch (s->solver) {
         case FMWR_SGD:
           if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, true>), grid, 256, 0, ua);
@@ -490,7 +498,8 @@ void MbLaunch<T>::k1()
 {
   const int rpb = 8 * (32 / TEAM);
   // peer mode: one release fence per CTA at the end (it waits for the CTA's NVLink stores), so few fat CTAs
-  const int fgrid = (int)std::min<int64_t>(ceil_div(rows, rpb), (int64_t)ctx->sm_count * (partial == 2 ? 4 : 16));
+  static const int k1_ctas = getenv("FMWR_K1_CTAS") ? atoi(getenv("FMWR_K1_CTAS")) : 4;      // resident CTAs per SM: measured best (persistent warps)
+  const int fgrid = (int)std::min<int64_t>(ceil_div(rows, rpb), (int64_t)ctx->sm_count * (partial == 2 ? 4 : k1_ctas));
   FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH, TEAM>), fgrid, 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
               (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
               m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial, pa);

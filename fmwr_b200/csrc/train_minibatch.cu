@@ -188,7 +188,13 @@ struct MbUpdArgs {
   PeerArgs pa;
 };
 
-template <int SOLVER> struct K2Tune { enum { BLOCKS = SOLVER == FMWR_TDAP ? 3 : 6, UE = SOLVER == FMWR_TDAP ? 4 : 2 }; };
+#ifndef FMWR_K2B
+#define FMWR_K2B 5
+#endif
+#ifndef FMWR_K2UE
+#define FMWR_K2UE 2
+#endif
+template <int SOLVER> struct K2Tune { enum { BLOCKS = SOLVER == FMWR_TDAP ? 3 : FMWR_K2B, UE = SOLVER == FMWR_TDAP ? 4 : FMWR_K2UE }; };
 
 // the intercept (dense coordinate): fixed-order reduction of the batch's multipliers by ONE block.  It is block 0 so
 // that its serial chain of loads overlaps the rest of the grid instead of forming the kernel's tail.
@@ -430,8 +436,9 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
 }
 
 // One lane group per segment.  Measured on B200 (profiles/r01_summary.md): occupancy beats per-warp depth here -- a
-// 40-register build (6 CTAs/SM, entries taken two at a time) is as fast as a persistent software-pipelined variant
-// with three segments in flight per group, and simpler.  TDAP carries 4 state rows and keeps 80 registers.
+// 48-register build (5 resident CTAs/SM walking the segments grid-stride, entries taken two at a time) beats both the
+// 40-register/6-CTA build (spills) and a software-pipelined variant with three segments in flight per group.
+// TDAP carries 4 state rows and keeps 80 registers.
 
 template <class T, int LPR, int CH, int SOLVER, bool L1>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 && CH == 1) ? K2Tune<SOLVER>::BLOCKS : 1) mb_update_kernel(MbUpdArgs<T> a)
@@ -477,7 +484,7 @@ struct MbLaunch {
       int grid = ceil_div((int64_t)nseg, 8 * G) + 1;       // +1: the intercept block
       {
         static const int persist = getenv("FMWR_K2_ONESHOT") ? 0 : (getenv("FMWR_K2_WAVES") ? atoi(getenv("FMWR_K2_WAVES")) : 1);
-        const int resident = (sizeof(TT) == 4 && CH == 1) ? (s->solver == FMWR_TDAP ? 3 : 6) : 2;
+        const int resident = (sizeof(TT) == 4 && CH == 1) ? (s->solver == FMWR_TDAP ? 3 : FMWR_K2B) : 2;
         if (persist > 0) grid = std::min(grid, ctx->sm_count * resident * persist + 1);
       }
       switch (s->solver) {

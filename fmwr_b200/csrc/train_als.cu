@@ -500,6 +500,7 @@ struct RmArgs {
 
 template <class T> __device__ __forceinline__ void rm_extract_one(const RmArgs<T>& a, uint32_t c);
 template <class T> __device__ __forceinline__ void rm_solve_one(const RmArgs<T>& a, uint32_t c);
+template <class T> __device__ __forceinline__ void rm_solve_finish(const RmArgs<T>& a, uint32_t c, double A, double Bm);
 
 template <class T>
 __global__ void rm_extract_kernel(RmArgs<T> a)
@@ -516,12 +517,41 @@ __global__ void rm_solve_kernel(RmArgs<T> a)
 }
 
 // solve of step t and extract of step t + 1 in one launch (they touch different features and different scratch)
+// 64 features x 4 replica slices per CTA: the replica sums / clears are latency chains, so they are spread over threads
+constexpr int SE_COLS = 64, SE_SLICES = 4;
 template <class T>
-__global__ void rm_solve_extract_kernel(RmArgs<T> a, RmArgs<T> b)
+__global__ void __launch_bounds__(SE_COLS * SE_SLICES) rm_solve_extract_kernel(RmArgs<T> a, RmArgs<T> b)
 {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < a.ncols) rm_solve_one(a, c);
-  if (c < b.ncols) rm_extract_one(b, c);
+  typedef typename Vec2<T>::type V2;
+  __shared__ double sA[SE_SLICES][SE_COLS], sB[SE_SLICES][SE_COLS];
+  const int tx = threadIdx.x % SE_COLS, ty = threadIdx.x / SE_COLS;
+  const uint32_t c = blockIdx.x * SE_COLS + tx;
+  double A = 0.0, Bm = 0.0;
+  if (c < a.ncols) {
+    const int R = a.n_rep > 1 ? a.n_rep : 1;
+#pragma unroll 4
+    for (int r = ty; r < R; r += SE_SLICES) {
+      const V2 ab = reinterpret_cast<const V2*>(a.AB)[(size_t)r * a.ncols + c];
+      A += (double)ab.x; Bm += (double)ab.y;
+    }
+  }
+  sA[ty][tx] = A; sB[ty][tx] = Bm;
+  __syncthreads();
+  if (ty == 0 && c < a.ncols) {
+#pragma unroll
+    for (int j = 1; j < SE_SLICES; ++j) { A += sA[j][tx]; Bm += sB[j][tx]; }
+    rm_solve_finish(a, c, A, Bm);
+  }
+  if (c < b.ncols) {
+    if (ty == 0) {
+      const T th = b.theta[(size_t)(b.cb + c) * b.theta_stride];
+      b.th[c] = th;
+      if (b.thd) b.thd[c].x = th;
+    }
+    const int R = b.n_rep > 1 ? b.n_rep : 1;
+    V2 z; z.x = T(0); z.y = T(0);
+    for (int r = ty; r < R; r += SE_SLICES) reinterpret_cast<V2*>(b.AB)[(size_t)r * b.ncols + c] = z;
+  }
 }
 
 template <class T>
@@ -606,6 +636,13 @@ __device__ __forceinline__ void rm_solve_one(const RmArgs<T>& a, uint32_t c)
       A += (double)ab.x; Bm += (double)ab.y;
     }
   }
+  rm_solve_finish(a, c, A, Bm);
+}
+
+template <class T>
+__device__ __forceinline__ void rm_solve_finish(const RmArgs<T>& a, uint32_t c, double A, double Bm)
+{
+  const double old = (double)a.th[c];
   if (a.q != nullptr) Bm -= old * A;                                    // reference :322
   const double var = 1.0 / (a.lambda + a.alpha * A);
   const double mean = -var * (a.alpha * Bm - a.mu * a.lambda);
@@ -742,6 +779,7 @@ struct FusedArgs {
   int has_prev; const uint32_t* pcol; const float* pval; const typename Vec2<T>::type* pthd; T* pq;
   int has_cur; const uint32_t* ccol; const float* cval; const T* cth; T* cAB; T* cq;
   uint32_t p_ncols, c_ncols; int n_rep;
+  int cur_sorted;      // the rows are sorted by the current field: equal features sit in consecutive rows
 };
 
 #ifndef FMWR_FUSED_BLOCKS
@@ -758,95 +796,134 @@ constexpr size_t FUSED_AB_BYTES = 8u << 20; // ... as many as fit this budget (L
 // keeps same-address serialisation negligible even for a 2048-feature field.  A thread owns VEC consecutive rows and first
 // combines the rows that share a feature -- with the rows sorted by the widest field that is one reduction per thread.
 // ONES: every value of the data is 1.0 (one-hot fields): the value streams are not read at all.
+// apply(step t-1) and the per-row statistics of step t for the VEC rows starting at `base`
+// (reference :251-253 / :338-349 for the apply, :225-230 / :313-321 for the statistics)
 template <class T, int VEC, bool ONES>
-__global__ void __launch_bounds__(FUSED_THREADS, FUSED_BLOCKS) fused_kernel(FusedArgs<T> a)
+__device__ __forceinline__ void fused_rows(const FusedArgs<T>& a, int64_t base, bool same_q, uint32_t (&cc)[VEC], T (&sa)[VEC], T (&sb)[VEC])
 {
   typedef typename Vec2<T>::type V2;
+  typedef typename Vec<T>::type V16;
   // (staging these lookup tables in shared memory was measured and does not pay: the pass is bound by the reductions)
   const V2* __restrict__ ptab = a.pthd;
   const T* __restrict__ ctab = a.cth;
-  const bool same_q = a.has_prev && a.has_cur && a.pq != nullptr && a.pq == a.cq;
-  T* AB = a.cAB + (a.has_cur ? 2 * (size_t)(blockIdx.x % (unsigned)a.n_rep) * a.c_ncols : 0);
-  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; base < a.n; base += (int64_t)gridDim.x * blockDim.x * VEC) {
-    T ev[VEC], qv[VEC];
-    uint32_t pc[VEC], cc[VEC];
-    float px[VEC], cx[VEC];
+  T ev[VEC], qv[VEC];
+  uint32_t pc[VEC];
+  float px[VEC], cx[VEC];
 #pragma unroll
-    for (int u = 0; u < VEC; ++u) { px[u] = 1.f; cx[u] = 1.f; pc[u] = 0u; cc[u] = 0u; }
-    if (VEC == 4) {
-      *reinterpret_cast<typename Vec<T>::type*>(ev) = *reinterpret_cast<const typename Vec<T>::type*>(a.e + base);
-      if (sizeof(T) == 8) *reinterpret_cast<typename Vec<T>::type*>(ev + 2) = *reinterpret_cast<const typename Vec<T>::type*>(a.e + base + 2);
-      if (a.has_prev) {
-        *reinterpret_cast<uint4*>(pc) = *reinterpret_cast<const uint4*>(a.pcol + base);
-        if (!ONES) *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(a.pval + base);
-      }
-      if (a.has_cur) {
-        *reinterpret_cast<uint4*>(cc) = *reinterpret_cast<const uint4*>(a.ccol + base);
-        if (!ONES) *reinterpret_cast<float4*>(cx) = *reinterpret_cast<const float4*>(a.cval + base);
-      }
-    } else {
-      ev[0] = a.e[base];
-      if (a.has_prev) { pc[0] = a.pcol[base]; if (!ONES) px[0] = a.pval[base]; }
-      if (a.has_cur) { cc[0] = a.ccol[base]; if (!ONES) cx[0] = a.cval[base]; }
-    }
-    // ---- apply the previous step (reference :251-253 for w, :338-349 for V)
+  for (int u = 0; u < VEC; ++u) { px[u] = 1.f; cx[u] = 1.f; pc[u] = 0u; cc[u] = 0u; }
+  if (VEC == 4) {
+    *reinterpret_cast<V16*>(ev) = *reinterpret_cast<const V16*>(a.e + base);
+    if (sizeof(T) == 8) *reinterpret_cast<V16*>(ev + 2) = *reinterpret_cast<const V16*>(a.e + base + 2);
     if (a.has_prev) {
-      if (a.pq != nullptr) {
-        if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(qv) = *reinterpret_cast<const typename Vec<T>::type*>(a.pq + base);
-        else {
-#pragma unroll
-          for (int u = 0; u < VEC; ++u) qv[u] = a.pq[base + u];
-        }
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) {
-          const V2 td = ptab[pc[u]];
-          const T d = td.y;
-          const T h = T(px[u]) * qv[u] - T(px[u] * px[u]) * td.x;
-          qv[u] -= T(px[u]) * d;
-          ev[u] -= h * d;
-        }
-        if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(a.pq + base) = *reinterpret_cast<const typename Vec<T>::type*>(qv);
-        else {
-#pragma unroll
-          for (int u = 0; u < VEC; ++u) a.pq[base + u] = qv[u];
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) ev[u] -= T(px[u]) * ptab[pc[u]].y;
-      }
-      if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(a.e + base) = *reinterpret_cast<const typename Vec<T>::type*>(ev);
+      *reinterpret_cast<uint4*>(pc) = *reinterpret_cast<const uint4*>(a.pcol + base);
+      if (!ONES) *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(a.pval + base);
+    }
+    if (a.has_cur) {
+      *reinterpret_cast<uint4*>(cc) = *reinterpret_cast<const uint4*>(a.ccol + base);
+      if (!ONES) *reinterpret_cast<float4*>(cx) = *reinterpret_cast<const float4*>(a.cval + base);
+    }
+  } else {
+    ev[0] = a.e[base];
+    if (a.has_prev) { pc[0] = a.pcol[base]; if (!ONES) px[0] = a.pval[base]; }
+    if (a.has_cur) { cc[0] = a.ccol[base]; if (!ONES) cx[0] = a.cval[base]; }
+  }
+  if (a.has_prev) {
+    if (a.pq != nullptr) {
+      if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<V16*>(qv) = *reinterpret_cast<const V16*>(a.pq + base);
       else {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) a.e[base + u] = ev[u];
+        for (int u = 0; u < VEC; ++u) qv[u] = a.pq[base + u];
       }
-    }
-    // ---- statistics of the current step (reference :225-230 for w, :313-321 for V)
-    if (a.has_cur) {
-      if (a.cq != nullptr && !same_q) {
-        if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<typename Vec<T>::type*>(qv) = *reinterpret_cast<const typename Vec<T>::type*>(a.cq + base);
-        else {
-#pragma unroll
-          for (int u = 0; u < VEC; ++u) qv[u] = a.cq[base + u];
-        }
-      }
-      T ra = T(0), rb = T(0);
-      uint32_t rc = cc[0];
 #pragma unroll
       for (int u = 0; u < VEC; ++u) {
-        const T old = ctab[cc[u]];
-        T sa, sb;
-        if (a.cq == nullptr) {
-          const T x = T(cx[u]);
-          sa = x * x;
-          sb = ev[u] * x - old * x * x;
-        } else {
-          const T h = T(cx[u]) * qv[u] - T(cx[u] * cx[u]) * old;
-          sa = h * h;
-          sb = h * ev[u];
-        }
-        if (u > 0 && cc[u] != rc) { atomic_add2(AB, rc, ra, rb); rc = cc[u]; ra = T(0); rb = T(0); }
-        ra += sa; rb += sb;
+        const V2 td = ptab[pc[u]];
+        const T d = td.y;
+        const T h = T(px[u]) * qv[u] - T(px[u] * px[u]) * td.x;
+        qv[u] -= T(px[u]) * d;
+        ev[u] -= h * d;
       }
+      if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<V16*>(a.pq + base) = *reinterpret_cast<const V16*>(qv);
+      else {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) a.pq[base + u] = qv[u];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) ev[u] -= T(px[u]) * ptab[pc[u]].y;
+    }
+    if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<V16*>(a.e + base) = *reinterpret_cast<const V16*>(ev);
+    else {
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) a.e[base + u] = ev[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) { sa[u] = T(0); sb[u] = T(0); }
+  if (a.has_cur) {
+    if (a.cq != nullptr && !same_q) {
+      if (VEC == 4 && sizeof(T) == 4) *reinterpret_cast<V16*>(qv) = *reinterpret_cast<const V16*>(a.cq + base);
+      else {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] = a.cq[base + u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) {
+      const T old = ctab[cc[u]];
+      if (a.cq == nullptr) {
+        const T x = T(cx[u]);
+        sa[u] = x * x;
+        sb[u] = ev[u] * x - old * x * x;
+      } else {
+        const T h = T(cx[u]) * qv[u] - T(cx[u] * cx[u]) * old;
+        sa[u] = h * h;
+        sb[u] = h * ev[u];
+      }
+    }
+  }
+}
+
+template <class T, int VEC, bool ONES>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_BLOCKS) fused_kernel(FusedArgs<T> a)
+{
+  const bool same_q = a.has_prev && a.has_cur && a.pq != nullptr && a.pq == a.cq;
+  T* AB = a.cAB + (a.has_cur ? 2 * (size_t)(blockIdx.x % (unsigned)a.n_rep) * a.c_ncols : 0);
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * VEC;
+  // the loop condition is warp-uniform (first lane's row), so every lane reaches the shuffles of the sorted-field path
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; base - (int64_t)lane * VEC < a.n; base += stride) {
+    const bool valid = base < a.n;
+    uint32_t cc[VEC];
+    T sa[VEC], sb[VEC];
+    if (valid) fused_rows<T, VEC, ONES>(a, base, same_q, cc, sa, sb);
+    if (!a.has_cur) continue;
+    T ra = T(0), rb = T(0);
+    uint32_t rc = valid ? cc[0] : 0u;
+    bool single = valid;
+    if (valid) {
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        if (u > 0 && cc[u] != rc) { atomic_add2(AB, rc, ra, rb); rc = cc[u]; ra = T(0); rb = T(0); single = false; }
+        ra += sa[u]; rb += sb[u];
+      }
+    }
+    if (a.cur_sorted) {
+      // Rows are sorted by this field, so the lanes whose rows all carry the previous lane's feature continue its run.
+      // A segmented shuffle reduction leaves each run's total in its first lane: ~2 reductions per warp instead of 32.
+      // (A thread that saw a feature change has already emitted its earlier runs and starts a new segment with its last.)
+      const uint32_t prev_rc = __shfl_up_sync(0xffffffffu, rc, 1);
+      const bool head = lane == 0 || !valid || !single || prev_rc != rc;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));          // heads at or below this lane
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const T ta = __shfl_down_sync(0xffffffffu, ra, o);
+        const T tb = __shfl_down_sync(0xffffffffu, rb, o);
+        const int ts = __shfl_down_sync(0xffffffffu, seg, o);
+        if (lane + o < 32 && ts == seg) { ra += ta; rb += tb; }
+      }
+      if (valid && head) atomic_add2(AB, rc, ra, rb);
+    } else if (valid) {
       atomic_add2(AB, rc, ra, rb);
     }
   }
@@ -1049,6 +1126,7 @@ static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, co
       fa.ccol = dl.col.p + (size_t)cs.phase * n; fa.cval = dl.val.p + (size_t)cs.phase * n;
       fa.cth = ra.th; fa.cAB = ra.AB; fa.cq = cs.q ? cs.q + (size_t)cs.f * n : nullptr;
       fa.c_ncols = ra.ncols; fa.n_rep = ra.n_rep;
+      fa.cur_sorted = (dl.permuted && dl.sorted_phase == cs.phase && getenv("FMWR_ALS_NO_WARPSEG") == nullptr) ? 1 : 0;
     }
     if (vec == 4) {
       if (dl.all_ones) FMWR_LAUNCH(ctx, (fused_kernel<T, 4, true>), grid, FUSED_THREADS, 0, fa);
@@ -1067,7 +1145,7 @@ static void run_steps_dense(fmwr_ctx* ctx, const std::vector<uint32_t>& pbeg, co
         // solve(t) and extract(t+1) share a launch: step t+1 is another (phase, factor), i.e. other features, and its
         // scratch (parity (t+1)&1) was last read by the fused pass that has just finished
         rnext = step_args(t + 1);
-        FMWR_LAUNCH(ctx, rm_solve_extract_kernel<T>, ceil_div(std::max(ra.ncols, rnext.ncols), 256), 256, 0, ra, rnext);
+        FMWR_LAUNCH(ctx, rm_solve_extract_kernel<T>, ceil_div(std::max(ra.ncols, rnext.ncols), SE_COLS), SE_COLS * SE_SLICES, 0, ra, rnext);
       } else FMWR_LAUNCH(ctx, rm_solve_kernel<T>, ceil_div(ra.ncols, 256), 256, 0, ra);
     }
   }
@@ -1343,14 +1421,18 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
           const double nl = do_sample ? hs.gamma(la / 2.0, 2.0 / g) : la / g;
           if (!hbad(nl)) v_lambda[f] = nl;
         }
+        // F7: the reference sums v(f, attr_group[i]) == v(f, 0), p times (:462).  The p-fold fp64 addition is reproduced
+        // exactly, but for all factors at once (k independent chains the CPU can pipeline) -- one factor at a time it
+        // was 3 ms of host time per sweep with the GPU idle.
+        std::vector<double> vrep(k, 0.0);
+        if (s->compat & FMWR_COMPAT_MCMC_VMU_IDX) {
+          std::vector<double> v0(k);
+          for (int f = 0; f < k; ++f) v0[f] = (double)T(vrow0[f]);
+          for (int64_t i = 0; i < p; ++i)
+            for (int f = 0; f < k; ++f) vrep[f] += v0[f];
+        }
         for (int f = 0; f < k; ++f) {
-          double mm;
-          if (s->compat & FMWR_COMPAT_MCMC_VMU_IDX) {
-            // F7: the reference sums v(f, attr_group[i]) == v(f, 0), p times (:462)
-            const T v0 = T(vrow0[f]);
-            mm = 0.0;
-            for (int64_t i = 0; i < p; ++i) mm += (double)v0;
-          } else mm = vsum[f];
+          double mm = (s->compat & FMWR_COMPAT_MCMC_VMU_IDX) ? vrep[f] : vsum[f];
           mm = (mm + beta_0 * mu_0) / ((double)p + beta_0);
           const double var = 1.0 / (((double)p + beta_0) * v_lambda[f]);
           const double nm = do_sample ? hs.normal(mm, std::sqrt(var)) : mm;

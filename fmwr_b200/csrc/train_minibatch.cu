@@ -308,7 +308,8 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
   constexpr int NST = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
   constexpr bool FAST = sizeof(T) == 4;
   // TDAP keeps the per-entry gradient form of the exact mode (see fm_grad: a rounding residue flips theta by +-alpha);
-  // SGD / FTRL sum  A_f = sum_r (m_r x_r) S_rf  and  b = sum_r m_r x_r^2  and form  G_f = A_f - v_f b  once
+  // SGD / FTRL sum  A_f = sum_r (m_r x_r) S_rf  and  b = sum_r m_r x_r^2  and form  G_f = A_f - v_f b  once (the same
+  // value up to rounding; at batch = 1 it differs from the exact mode's per-entry form by an ulp, not by a step)
   constexpr bool ENTRY_FORM = SOLVER == FMWR_TDAP;
   if (!sg.live) return;
   const SolverParams<T>& sp = a.sp;
@@ -320,7 +321,7 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
   uint32_t my_r = sg.my_r;
   float my_x = sg.my_x;
 
-  T th[CH][VN], Gv[CH][VN], G1[CH][VN];
+  T th[CH][VN], Gv[CH][VN];
   const T x0 = T(sg.x0), m0 = sg.m0;
   const T mx0 = m0 * x0;
   T Gw = mx0, bsum = mx0 * x0;
@@ -330,10 +331,7 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
     vec_to_arr(sg.th[ch], th[ch]);
     vec_to_arr(sg.s0[ch], s);
 #pragma unroll
-    for (int k2 = 0; k2 < VN; ++k2) {
-      G1[ch][k2] = m0 * fm_grad(s[k2], th[ch][k2], x0);            // the exact-mode form: what a one-entry segment uses
-      Gv[ch][k2] = ENTRY_FORM ? G1[ch][k2] : mx0 * s[k2];
-    }
+    for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = ENTRY_FORM ? m0 * fm_grad(s[k2], th[ch][k2], x0) : mx0 * s[k2];
   }
   for (uint32_t base = 1; base < len; base += LPR) {
     if (base > 1) {
@@ -378,7 +376,7 @@ __device__ __forceinline__ void seg_finish(const MbUpdArgs<T>& a, const int g, c
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-      for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = (len == 1u) ? G1[ch][k2] : Gv[ch][k2] - th[ch][k2] * bsum;
+      for (int k2 = 0; k2 < VN; ++k2) Gv[ch][k2] = Gv[ch][k2] - th[ch][k2] * bsum;
   }
 
   // ---- linear weight (lane 0 of the group)

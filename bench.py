@@ -519,9 +519,31 @@ def run_engine_multi(args, rank, world, local):
     for _ in range(args.warmup):
         L.predict_dev(ctx, pmodel, pdata, L.LINK_LOGISTIC)
     ms_pred = timed(lambda: L.predict_dev(ctx, pmodel, pdata, L.LINK_LOGISTIC), args.steps)
-    clk = clocks.stop() if rank == 0 else None
     pred_rps = n * args.steps / (ms_pred * 1e-3)
     pdata.close(); pmodel.close()
+
+    # ALS sweep, rows sharded: configs[2] split into `world` row ranges, one NCCL all-reduce of the field's
+    # statistics per coordinate step; every rank ends the sweep with the same model
+    als = None
+    if not args.no_solvers and args.rows >= 1_000_000:
+        na, fields, ka = 20_000_000, [138493, 26744, 2048], 32
+        a0, a1 = multi.row_partition(na, world)[rank]
+        ad = L.Data.synth_rows(ctx, a0, a1 - a0, fields, [0, 1, 0], 0, 3, 0.3, 20240601)
+        am = L.Model(ctx, L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=ka), sum(fields), L.F32)
+        am.init_random(0.0, 0.01, 20240603)
+        asc = L.SolverCfg(solver=L.ALS, max_iter=1, random_step=1, min_target=0.5, max_target=5.0, mode=L.MODE_EXACT, precision=L.F32,
+                          compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=5)
+        for _ in range(args.warmup):
+            L.train_dev(ctx, am, ad, asc)
+        ms_als = timed(lambda: L.train_dev(ctx, am, ad, asc), args.steps) / args.steps
+        pa_, Na_ = sum(fields), 3 * na
+        sweep_bytes = na * (8 + 3 * (12 + 4 * ka)) + 16 * na + 16 * Na_ + ka * (32 * Na_ + 4 * na + 8 * pa_)
+        als = {"workload": "configs[2]: 20000000 ratings x 3 one-hot fields, k=32, one ALS sweep, rows sharded over %d GPUs "
+                           "(one NCCL all-reduce of 2 x |field| f32 per coordinate step, 99 per sweep)" % world,
+               "value": round(na / (ms_als * 1e-3), 1), "unit": "ratings/s", "ms_per_step": round(ms_als, 3),
+               "frac_of_n_gpus_peak": round(sweep_bytes / (ms_als * 1e-3) / 1e9 / (peak * world), 4)}
+        ad.close(); am.close()
+    clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
         b_fwd, b_ftrl = ALG_BYTES["predict"](F, k), ALG_BYTES["ftrl"](F, k)
@@ -551,6 +573,7 @@ def run_engine_multi(args, rank, world, local):
             "predict": {"value": round(pred_rps, 1), "unit": "rows/s", "ms_per_step": round(ms_pred / args.steps, 3),
                         "roofline": {"bound": "hbm", "achieved": round(pred_rps * b_fwd / 1e9, 1), "unit": "GB/s",
                                      "frac_of_n_gpus_peak": round(pred_rps * b_fwd / 1e9 / (peak * world), 4)}},
+            "solvers": {"als": als} if als else None,
             "cpu_baseline": None,
             "e2e": None,
             "gpu_launches": int(l1 - l0),

@@ -135,7 +135,7 @@ struct fmwr_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   // peer window (CUDA IPC over NVLink): base[r] = rank r's window mapped into this process (base[rank] = our own)
-  struct PeerWin { void* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t bytes = 0; bool ready = false; } peer;
+  struct PeerWin { void* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t bytes = 0; bool ready = false; unsigned als_step = 0; } peer;
   fmwr::DBuf<double> red_scratch;  // reductions
   fmwr::HBuf<double> h_scalar;
 };

@@ -42,7 +42,7 @@ class SolverCfg(C.Structure):
                 ("normals", C.c_void_p), ("n_normals", C.c_int64),
                 ("gammas", C.c_void_p), ("n_gammas", C.c_int64),
                 ("rands", C.c_void_p), ("n_rands", C.c_int64),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("warm_state", C.c_int32)]
 
 
 class Trace(C.Structure):
@@ -300,6 +300,25 @@ class Model:
         v = np.zeros((self.p, self.k))
         check(lib().fmwr_model_get(self.h, C.byref(w0), ptr(w), ptr(v) if self.k > 0 else None))
         return w0.value, w, v
+
+    def state_info(self):
+        solver, ns = C.c_int32(), C.c_int32()
+        check(lib().fmwr_model_state_info(self.h, C.byref(solver), C.byref(ns)))
+        return solver.value, ns.value
+
+    def get_state(self):
+        """(solver, scal[8], sw[n_state][p], sv[n_state][p][k]) of the last training call on this handle"""
+        solver, ns = self.state_info()
+        scal = np.zeros(8)
+        sw = np.zeros((ns, self.p))
+        sv = np.zeros((ns, self.p, self.k))
+        check(lib().fmwr_model_get_state(self.h, ptr(scal), ptr(sw), ptr(sv)))
+        return dict(solver=solver, scal=scal, sw=sw, sv=sv)
+
+    def set_state(self, st):
+        sw = np.ascontiguousarray(st["sw"], np.float64); sv = np.ascontiguousarray(st["sv"], np.float64)
+        scal = np.ascontiguousarray(st["scal"], np.float64)
+        check(lib().fmwr_model_set_state(self.h, C.c_int32(int(st["solver"])), C.c_int32(sw.shape[0]), ptr(scal), ptr(sw), ptr(sv)))
 
     def init_random(self, mean=0.0, sd=0.01, seed=20240603):
         check(lib().fmwr_model_init_random(self.h, C.c_double(mean), C.c_double(sd), C.c_uint64(seed)))

@@ -23,7 +23,10 @@ import numpy as np
 from . import _lib as L
 
 _OPTIONS = {"FM.threads": 1, "FM.mode": "exact", "FM.batch": 65536, "FM.precision": "f32", "FM.compat": "reference",
-            "FM.enable_v": False, "FM.device": 0, "FM.seed": 1}
+            "FM.enable_v": False, "FM.device": 0, "FM.seed": 1,
+            # engine extension: keep the optimizer state (FTRL z/n, TDAP u/nu/delta/h, SGD-L1 q) in the FM object
+            # and continue from it in fm.update; False = the reference's behaviour (state dropped, FTRL_Learner.h:48-56)
+            "FM.keep_state": False}
 _CTX = {}
 
 
@@ -263,6 +266,11 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
             m.set(w0, w, v)
             s = solver_controls["solver"]
             name = s.solver
+            warm = 0
+            if (model_list is not None and _OPTIONS["FM.keep_state"] and model_list.get("State") is not None
+                    and model_list["State"]["solver"] == L.SOLVERS[name] and name in ("SGD", "FTRL", "TDAP")):
+                m.set_state(model_list["State"])
+                warm = 1
             sc = L.SolverCfg(solver=L.SOLVERS[name], max_iter=int(solver_controls["max_iter"]), random_step=int(s.get("random_step", 1)),
                              learn_rate=float(s.get("learn_rate", 0.01)), alpha_w=float(s.get("alpha_w", 0.1)),
                              alpha_v=float(s.get("alpha_v", 0.1)), beta_w=float(s.get("beta_w", 1.0)), beta_v=float(s.get("beta_v", 1.0)),
@@ -271,7 +279,7 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
                              batch_size=int(_OPTIONS["FM.batch"]), precision=prec, compat=_compat(),
                              enable_v=int(bool(_OPTIONS["FM.enable_v"])), step_size=int(track_controls["step_size"]),
                              metric=L.METRICS[track_controls["evaluate.metric"]], convergence=float(track_controls["convergence"]),
-                             seed=int(_OPTIONS["FM.seed"]))
+                             seed=int(_OPTIONS["FM.seed"]), warm_state=warm)
             keep = []
             if streams:
                 for fld, cnt, dt in (("normals", "n_normals", np.float64), ("gammas", "n_gammas", np.float64), ("rands", "n_rands", np.int32)):
@@ -286,6 +294,7 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
                 trace = L.TraceBuf(nrec, p, k, snapshots=True)
             L.train_dev(ctx, m, d, sc, trace, keep=keep)
             gw0, gw, gv = m.get()
+            state = m.get_state() if (_OPTIONS["FM.keep_state"] and name in ("SGD", "FTRL", "TDAP")) else None
         finally:
             m.close()
     finally:
@@ -295,6 +304,8 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
     model["solver.control"] = solver_controls
     model["track.control"] = track_controls
     res = FM(Model=model, Scales=scales)
+    if state is not None:
+        res["State"] = state
     if trace is not None:
         t = trace.result()
         model["convergence"] = t["convergent"]

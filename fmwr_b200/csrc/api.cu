@@ -235,9 +235,14 @@ void model_get_host(fmwr_model* m, double* w0, double* w, double* v)
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-void model_alloc_state(fmwr_model* m, int n_state)
+// returns true when the existing state was kept (warm start)
+bool model_alloc_state(fmwr_model* m, int n_state, int solver, bool warm)
 {
   FMWR_REQUIRE(n_state <= 5, FMWR_ERR_ARG, "too many optimizer state arrays");
+  bool have = m->n_state == n_state && m->state_solver == solver;
+  for (int i = 0; i < n_state && have; ++i)
+    have = m->sw[i].p && m->sv[i].p && m->sw[i].bytes() == (size_t)m->p * m->esz() && m->sv[i].bytes() == (size_t)m->p * m->kp * m->esz();
+  if (warm && have) return true;
   for (int i = 0; i < n_state; ++i) {
     m->sw[i].alloc((size_t)m->p * m->esz());
     m->sv[i].alloc((size_t)m->p * m->kp * m->esz());
@@ -245,7 +250,10 @@ void model_alloc_state(fmwr_model* m, int n_state)
     FMWR_CUDA(cudaMemsetAsync(m->sv[i].p, 0, m->sv[i].bytes(), m->ctx->stream));
   }
   for (int i = n_state; i < 5; ++i) { m->sw[i].release(); m->sv[i].release(); }
+  FMWR_CUDA(cudaMemsetAsync((double*)m->scal.p + 1, 0, 7 * sizeof(double), m->ctx->stream));     // Learner::init(): restart at zero
   m->n_state = n_state;
+  m->state_solver = solver;
+  return false;
 }
 
 fmwr_data* data_create_f64(fmwr_ctx*, int64_t, int64_t, int64_t, const int32_t*, const int32_t*, const double*, const double*, bool defer_values);
@@ -596,6 +604,69 @@ int fmwr_model_get(fmwr_model* m, double* w0, double* w, double* v)
     FMWR_REQUIRE(m, FMWR_ERR_ARG, "null model");
     FMWR_CUDA(cudaSetDevice(m->ctx->device));
     model_get_host(m, w0, w, v);
+  });
+}
+
+int fmwr_model_state_info(fmwr_model* m, int32_t* solver, int32_t* n_state)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(m, FMWR_ERR_ARG, "null model");
+    if (solver) *solver = m->state_solver;
+    if (n_state) *n_state = m->state_solver ? m->n_state : 0;
+  });
+}
+
+int fmwr_model_get_state(fmwr_model* m, double* scal8, double* sw, double* sv)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(m, FMWR_ERR_ARG, "null model");
+    fmwr_ctx* ctx = m->ctx;
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    const int64_t p = m->p;
+    if (scal8) FMWR_CUDA(cudaMemcpyAsync(scal8, m->scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const int ns = m->state_solver ? m->n_state : 0;
+    DBuf<double> stage;
+    stage.alloc(std::max<int64_t>(1, p * (int64_t)std::max(m->k, 1)));
+    for (int i = 0; i < ns && p > 0; ++i) {
+      if (sw) {
+        if (m->prec == FMWR_F64) FMWR_LAUNCH(ctx, cast_to_f64<double>, ceil_div(p, 256), 256, 0, (const double*)m->sw[i].p, stage.p, p);
+        else FMWR_LAUNCH(ctx, cast_to_f64<float>, ceil_div(p, 256), 256, 0, (const float*)m->sw[i].p, stage.p, p);
+        FMWR_CUDA(cudaMemcpyAsync(sw + (size_t)i * p, stage.p, 8 * p, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      if (sv && m->k > 0) {
+        if (m->prec == FMWR_F64) FMWR_LAUNCH(ctx, unpack_v<double>, ceil_div(p * m->k, 256), 256, 0, (const double*)m->sv[i].p, stage.p, p, m->k, m->kp);
+        else FMWR_LAUNCH(ctx, unpack_v<float>, ceil_div(p * m->k, 256), 256, 0, (const float*)m->sv[i].p, stage.p, p, m->k, m->kp);
+        FMWR_CUDA(cudaMemcpyAsync(sv + (size_t)i * p * m->k, stage.p, 8 * p * m->k, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int fmwr_model_set_state(fmwr_model* m, int32_t solver, int32_t n_state, const double* scal8, const double* sw, const double* sv)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(m && n_state >= 0 && n_state <= 5, FMWR_ERR_ARG, "bad argument");
+    FMWR_REQUIRE(n_state == 0 || (sw && (sv || m->k == 0)), FMWR_ERR_ARG, "null state arrays");
+    fmwr_ctx* ctx = m->ctx;
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    const int64_t p = m->p;
+    model_alloc_state(m, n_state, solver, false);
+    if (scal8) FMWR_CUDA(cudaMemcpyAsync((double*)m->scal.p + 1, scal8 + 1, 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // [0] = w0 stays
+    DBuf<double> stage;
+    stage.alloc(std::max<int64_t>(1, p * (int64_t)std::max(m->k, 1)));
+    for (int i = 0; i < n_state && p > 0; ++i) {
+      FMWR_CUDA(cudaMemcpyAsync(stage.p, sw + (size_t)i * p, 8 * p, cudaMemcpyHostToDevice, ctx->stream));
+      if (m->prec == FMWR_F64) FMWR_LAUNCH(ctx, cast_from_f64<double>, ceil_div(p, 256), 256, 0, stage.p, (double*)m->sw[i].p, p);
+      else FMWR_LAUNCH(ctx, cast_from_f64<float>, ceil_div(p, 256), 256, 0, stage.p, (float*)m->sw[i].p, p);
+      if (m->k > 0) {
+        FMWR_CUDA(cudaMemcpyAsync(stage.p, sv + (size_t)i * p * m->k, 8 * p * m->k, cudaMemcpyHostToDevice, ctx->stream));
+        if (m->prec == FMWR_F64) FMWR_LAUNCH(ctx, pack_v<double>, ceil_div(p * m->kp, 256), 256, 0, stage.p, (double*)m->sv[i].p, p, m->k, m->kp);
+        else FMWR_LAUNCH(ctx, pack_v<float>, ceil_div(p * m->kp, 256), 256, 0, stage.p, (float*)m->sv[i].p, p, m->k, m->kp);
+      }
+      FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
 

@@ -192,6 +192,7 @@ struct fmwr_model {
   fmwr::DBuf<char> v;        // [p][kp] real
   // optimizer state, allocated by the trainer on demand (n_state arrays shaped like w / v)
   int n_state = 0;
+  int state_solver = 0;      // solver the state arrays belong to (0: none)
   fmwr::DBuf<char> sw[5];    // per-solver state for w
   fmwr::DBuf<char> sv[5];    // per-solver state for V
   size_t esz() const { return prec == FMWR_F64 ? 8 : 4; }
@@ -314,7 +315,7 @@ void train_exact(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_c
 void train_minibatch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);
 void train_als_mcmc(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);
 double evaluate_dev(fmwr_ctx* ctx, fmwr_data* d, int task, int metric);
-void model_alloc_state(fmwr_model* m, int n_state);
+bool model_alloc_state(fmwr_model* m, int n_state, int solver, bool warm);
 void model_get_host(fmwr_model* m, double* w0, double* w, double* v);
 void model_set_host(fmwr_model* m, double w0, const double* w, const double* v);
 double model_get_w0(fmwr_model* m);

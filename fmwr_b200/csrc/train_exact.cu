@@ -334,8 +334,7 @@ template <class T>
 static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
 {
   const SolverParams<double> spd = make_params<double>(m, s);
-  model_alloc_state(m, solver_state_count(spd));              // Learner::init(): optimizer state restarts at zero
-  FMWR_CUDA(cudaMemsetAsync((double*)m->scal.p + 1, 0, 7 * sizeof(double), ctx->stream));
+  model_alloc_state(m, solver_state_count(spd), s->solver, s->warm_state != 0);   // Learner::init(): the state restarts at zero unless warm
 
   ExactArgs<T> a;
   memset(&a, 0, sizeof a);

@@ -530,8 +530,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   FMWR_REQUIRE(s->random_step <= 1 && !s->visit_order, FMWR_ERR_UNSUPPORTED,
                "minibatch mode scans rows in storage order (random_step must be 1)");
   const SolverParams<double> spd = make_params_f64(m, s);
-  model_alloc_state(m, solver_state_count(spd));
-  FMWR_CUDA(cudaMemsetAsync((double*)m->scal.p + 1, 0, 7 * sizeof(double), ctx->stream));
+  const bool kept_state = model_alloc_state(m, solver_state_count(spd), s->solver, s->warm_state != 0);
 
   const int64_t row0 = (s->compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0;     // F5: the reference scan starts at row 1
   const int64_t B = s->batch_size;
@@ -585,6 +584,13 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   int64_t iter = 0, next_track = 0;
   int n_rec = 0, conv_times = 0, convergent = 0;
   double old_score = 0.0, u_w = 0.0, u_v = 0.0;
+  const bool sgd_l1 = spd.solver == FMWR_SGD && spd.l1;
+  if (sgd_l1 && kept_state) {                // cumulative-L1 totals live in the scalar block ([1], [2]) like in the exact mode
+    double h[2] = {0, 0};
+    FMWR_CUDA(cudaMemcpyAsync(h, (double*)m->scal.p + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    u_w = h[0]; u_v = h[1];
+  }
   // The per-batch launches are recorded into CUDA graphs (chunks of GRAPH_CHUNK batches) and replayed by the device,
   // so the epoch does not depend on host launch latency / host jitter.  Per-kernel profiling, the tracker and the
   // NCCL path use plain launches.
@@ -642,6 +648,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
     }
   }
   flush_graph();
+  if (sgd_l1) { const double h[2] = {u_w, u_v}; FMWR_CUDA(cudaMemcpyAsync((double*)m->scal.p + 1, h, 16, cudaMemcpyHostToDevice, ctx->stream)); }
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   if (peer) {
     uint32_t err = 0;

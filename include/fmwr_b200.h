@@ -87,6 +87,10 @@ typedef struct {
   const double* gammas;  int64_t n_gammas;      /* unit-scale gammas  (stand in for Rf_rgamma) */
   const int32_t* rands;  int64_t n_rands;       /* glibc rand() ints  (truncated-normal draws) */
   uint64_t seed;
+  /* SGD/FTRL/TDAP: 1 = continue from the optimizer state the model handle already holds for this solver (z/n, u/nu/delta/h,
+   * cumulative-L1 q and totals) instead of restarting it at zero.  The reference's fm.update drops the state
+   * (FTRL_Learner.h:48-56); 0 reproduces that. */
+  int32_t warm_state;
 } fmwr_solver_cfg;
 
 /* train-metric trace (Tracker::save, src/core/Tracker.h:96-119) -- caller allocates */
@@ -186,6 +190,12 @@ int fmwr_model_get(fmwr_model* m, double* w0, double* w /*[p]*/, double* v /*[p]
 /* device-side init: w = 0, V ~ N(mean, sd) from the counter-based generator (benchmarks only; the R glue
  * draws V with Rf_rnorm itself so set.seed() reproducibility survives, src/core/Model.h:63-72) */
 int fmwr_model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);
+/* Optimizer state of the last fmwr_train_dev on this handle, so that a stateless host (R keeps the model in a list) can carry
+ * it from fm.train to fm.update: n_state arrays shaped like w and like V (V-shaped ones as [n_state][p][k]) plus the 8-double
+ * scalar block (w0 and its state).  fmwr_model_state_info reports which solver the state belongs to (0: none). */
+int fmwr_model_state_info(fmwr_model* m, int32_t* solver, int32_t* n_state);
+int fmwr_model_get_state(fmwr_model* m, double* scal8, double* sw /*[n_state][p]*/, double* sv /*[n_state][p][k]*/);
+int fmwr_model_set_state(fmwr_model* m, int32_t solver, int32_t n_state, const double* scal8, const double* sw, const double* sv);
 
 /* ---- forward: replaces Model::predict_batch / predict_prob (src/core/Model.h:106-180) ----
  * link: FMWR_LINK_NONE raw score; LOGISTIC 1/(1+exp(-s)); PROBIT_TABLE the reference's fast_pnorm table

@@ -120,3 +120,45 @@ def test_minibatch_hot_feature_segments(gpu_ctx, port):
     ll_r = -port.evaluate(O.CLASSIFICATION, O.LL, rp, y) / 20000
     ll_g = -port.evaluate(O.CLASSIFICATION, O.LL, gp, y) / 20000
     assert abs(ll_g - ll_r) / ll_r < 0.05, (ll_g, ll_r)
+
+
+@pytest.mark.parametrize("solver,regs", [(O.FTRL, dict(l1_w1=1e-3, l2_w1=1e-3, l2_v=1e-3)), (O.TDAP, dict(l1_w1=1e-3, l2_v=1e-3)),
+                                         (O.SGD, dict(l1_w1=1e-3, l1_v=1e-4))])
+@pytest.mark.parametrize("mode", [L.MODE_MINIBATCH, L.MODE_EXACT])
+def test_warm_state_continues_the_optimizer(gpu_ctx, solver, regs, mode):
+    """two calls of one epoch with warm_state = one call of two epochs, bit for bit -- also when the state
+    travels through host arrays into a fresh model handle (what the R glue does between fm.train and fm.update).
+    Without warm_state the second call restarts the state (the reference's fm.update) and ends elsewhere."""
+    ctx = gpu_ctx
+    rowptr, col, val, p = synth.fields_csr(3000, [40] * 6, None, 1, 5)
+    n = rowptr.size - 1
+    score = synth.planted_scores_fast(rowptr, col, val, p, seed=6)
+    y = synth.labels_from_scores(score, "classification", seed=7)
+    rng = np.random.default_rng(8)
+    k = 8
+    w = rng.normal(0, 0.05, p); v = rng.normal(0, 0.05, (p, k)); w0 = 0.05
+    d = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, **regs)
+    epoch = n - 1
+
+    def cfg(iters, warm):
+        return L.SolverCfg(solver=solver, max_iter=iters, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                           gamma=1e-4, min_target=-1.0, max_target=1.0, mode=mode, batch_size=256, precision=L.F64,
+                           compat=L.COMPAT_REFERENCE, step_size=-1, warm_state=warm)
+
+    def fresh():
+        m = L.Model(ctx, mc, p, L.F64)
+        m.set(w0, w, v)
+        return m
+
+    m = fresh(); L.train_dev(ctx, m, d, cfg(2 * epoch, 0)); both = m.get(); m.close()
+    m = fresh(); L.train_dev(ctx, m, d, cfg(epoch, 0)); L.train_dev(ctx, m, d, cfg(epoch, 1)); warm = m.get()
+    assert m.state_info()[0] == solver
+    m.close()
+    m = fresh(); L.train_dev(ctx, m, d, cfg(epoch, 0)); half = m.get(); st = m.get_state(); m.close()
+    m2 = L.Model(ctx, mc, p, L.F64); m2.set(*half); m2.set_state(st); L.train_dev(ctx, m2, d, cfg(epoch, 1)); moved = m2.get(); m2.close()
+    m = fresh(); L.train_dev(ctx, m, d, cfg(epoch, 0)); L.train_dev(ctx, m, d, cfg(epoch, 0)); cold = m.get(); m.close()
+    for a, b in ((both, warm), (both, moved)):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert not np.array_equal(both[2], cold[2])
+    d.close()

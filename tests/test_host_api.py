@@ -148,3 +148,28 @@ def test_normalize_update_and_regression_clamp(port):
     with pytest.raises(ValueError, match="not the same"):
         A.fm_update(fit, A.fm_matrix(X, y, feature_names=["x%d" % i for i in range(p)]))
     A.options(**{"FM.precision": "f32"})
+
+
+@pytest.mark.gpu
+def test_fm_update_with_kept_optimizer_state_equals_one_long_run():
+    """engine extension: options(FM.keep_state=TRUE) stores the FTRL state in the FM object and fm.update
+    continues from it -- train(epoch) + update(epoch) == train(2 epochs); the default drops the state like the reference"""
+    rng = np.random.default_rng(4)
+    n, p, k = 500, 25, 3
+    X = rng.uniform(0.5, 1.5, (n, p)) * (rng.random((n, p)) < 0.25)
+    X[X.sum(1) == 0, 0] = 1.0
+    y01 = (rng.random(n) < 0.5).astype(float)
+    data = A.fm_matrix(X, y01)
+    A.options(**{"FM.precision": "f64", "FM.seed": 9, "FM.mode": "exact", "FM.keep_state": True})
+    try:
+        mk = lambda it: [A.model_control(factor_number=k, L1_w1=1e-3, L2_v=1e-3), A.solver_control(max_iter=it, solver=A.FTRL_solver())]
+        long = A.fm_train(data, normalize=False, control=mk(2 * (n - 1)))
+        half = A.fm_train(data, normalize=False, control=mk(n - 1))
+        assert "State" in half and half["State"]["sw"].shape == (2, p) and half["State"]["sv"].shape == (2, p, k)
+        cont = A.fm_update(half, data)
+        assert np.array_equal(cont["Model"]["w"], long["Model"]["w"]) and np.array_equal(cont["Model"]["v"], long["Model"]["v"])
+        A.options(**{"FM.keep_state": False})
+        cold = A.fm_update(half, data)                           # the reference's fm.update: optimizer state restarts
+        assert "State" not in cold and not np.array_equal(cold["Model"]["v"], long["Model"]["v"])
+    finally:
+        A.options(**{"FM.precision": "f32", "FM.keep_state": False})

@@ -31,6 +31,14 @@ template <> struct Vec2<double> { typedef double2 type; };
 
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
+// rows a warp contributes to a forward tile (tile = 8 warps x RW rows): as many as keep the staging buffer within 40 KB --
+// longer runs of consecutive rows per factor in the transposed q stores (measured 1.9 -> 1.6 ms at k = 32 from 4 to 16)
+template <class T, int KP, int TPW>
+struct AlsTile {
+  static constexpr int fit(int rw) { return (size_t)(KP + 1) * 8 * rw * sizeof(T) <= 40 * 1024; }
+  static constexpr int BASE = fit(16) ? 16 : (fit(8) ? 8 : 4);
+  static constexpr int RW = TPW > BASE ? TPW : BASE;
+};
 constexpr int ALS_LONG = 4096;      // columns at least this long get a whole CTA
 
 // ---- forward: e = raw score, q[r][:] = S_f -----------------------------------------------------------
@@ -46,7 +54,7 @@ als_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restri
   constexpr int VN = Vec<T>::N;
   constexpr int KP = LPR * CH * VN;
   constexpr int TPW = 32 / TEAM;
-  constexpr int RW = TPW > 4 ? TPW : 4;
+  constexpr int RW = AlsTile<T, KP, TPW>::RW;
   constexpr int TILE = 8 * RW;
   constexpr bool STAGE = (size_t)(KP + 1) * TILE * sizeof(T) <= 40 * 1024;
   __shared__ T sS[STAGE ? TILE : 1][STAGE ? KP + 1 : 1];
@@ -100,7 +108,7 @@ struct AlsFwd {
   void go()
   {
     constexpr int TPW = 32 / TEAM;
-    constexpr int TILE = 8 * (TPW > 4 ? TPW : 4);
+    constexpr int TILE = 8 * AlsTile<TT, LPR * CH * Vec<TT>::N, TPW>::RW;
     int64_t want = ceil_div64(d->n, TILE);
     int64_t cap = (int64_t)ctx->sm_count * 32;
     int grid = (int)std::max<int64_t>(1, std::min(want, cap));

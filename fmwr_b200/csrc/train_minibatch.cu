@@ -483,7 +483,8 @@ struct MbLaunch {
       {
         static const int persist = getenv("FMWR_K2_ONESHOT") ? 0 : (getenv("FMWR_K2_WAVES") ? atoi(getenv("FMWR_K2_WAVES")) : 1);
         const int resident = (sizeof(TT) == 4 && CH == 1) ? (s->solver == FMWR_TDAP ? 3 : FMWR_K2B) : 2;
-        if (persist > 0) grid = std::min(grid, ctx->sm_count * resident * persist + 1);
+        // feature-parallel ranks hold a fraction of the segments: there the one-shot grid measured faster (N = 2/4/8)
+        if (persist > 0 && !(ctx->nccl_comm && ctx->world > 1)) grid = std::min(grid, ctx->sm_count * resident * persist + 1);
       }
       switch (s->solver) {
         case FMWR_SGD:

@@ -786,7 +786,7 @@ int fmwr_train(const fmwr_model_cfg* cfg, const fmwr_solver_cfg* s, int64_t n, i
       minibatch_build(dg.d, (s->compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0, s->batch_size);
       pt.lap("per-batch CSC build");
     }
-    data_wait_values(dg.d);
+    if (!dg.d->mb_vals_pending) data_wait_values(dg.d);
     train_dispatch(ctx, mg.m, dg.d, s, trace);
     pt.lap("train");
     model_get_host(mg.m, w0, w, v);

@@ -168,8 +168,20 @@ struct fmwr_data {
   // one-shot training path: the value stream may still be uploading on the copy stream while the compute stream already
   // sorts the (batch, feature) keys; val_ready marks its end (data.cu: data_wait_values)
   cudaEvent_t val_ready = nullptr;
+  std::vector<cudaEvent_t> val_ev;     // one per uploaded chunk of val_chunk entries (deferred upload only)
+  int64_t val_chunk = 0;
   fmwr::DBuf<double> val_stage[2];
-  ~fmwr_data() { if (val_ready) { cudaEventSynchronize(val_ready); cudaEventDestroy(val_ready); } }
+  // per-batch CSC built while the values were still in flight: ent_val / seg_rec.w of batch b are filled right before
+  // batch b trains, as soon as the value chunks covering its rows have arrived (train_minibatch.cu)
+  bool mb_vals_pending = false;
+  fmwr::DBuf<uint32_t> mb_perm;        // sorted position -> original entry (relative to mb_e0)
+  uint32_t mb_e0 = 0;
+  std::vector<int64_t> mb_batch_ent;   // [n_batches+1] entries before batch b (== offsets into the sorted entry arrays)
+  ~fmwr_data()
+  {
+    if (val_ready) { cudaEventSynchronize(val_ready); cudaEventDestroy(val_ready); }
+    for (cudaEvent_t e : val_ev) cudaEventDestroy(e);
+  }
   // ALS/MCMC layouts (phases, row-major / dense copies), built on first use, dropped when the values change
   std::shared_ptr<void> als_cache;
   // last forward result

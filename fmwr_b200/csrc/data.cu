@@ -232,7 +232,14 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
         FMWR_CUDA(cudaGetLastError());
         if (!free_ev[ci]) FMWR_CUDA(cudaEventCreateWithFlags(&free_ev[ci], cudaEventDisableTiming));
         FMWR_CUDA(cudaEventRecord(free_ev[ci], vs));
+        if (defer_values) {
+          cudaEvent_t ce = nullptr;
+          FMWR_CUDA(cudaEventCreateWithFlags(&ce, cudaEventDisableTiming));
+          FMWR_CUDA(cudaEventRecord(ce, vs));
+          d->val_ev.push_back(ce);
+        }
       }
+      d->val_chunk = chunk;
       for (int i = 0; i < 2; ++i) if (free_ev[i]) cudaEventDestroy(free_ev[i]);
       if (defer_values) {
         FMWR_CUDA(cudaEventCreateWithFlags(&d->val_ready, cudaEventDisableTiming));
@@ -442,7 +449,7 @@ __global__ void mb_emit(const K* __restrict__ keys, const uint32_t* __restrict__
   if (i >= m) return;
   const uint32_t e = perm[i];
   const uint32_t r = erow[e];
-  const float x = val[e0 + e];
+  const float x = val ? val[e0 + e] : 0.f;           // deferred upload: filled per batch by mb_fill_values
   ent_row[i] = r;
   ent_val[i] = x;
   if (head[i]) {
@@ -453,6 +460,33 @@ __global__ void mb_emit(const K* __restrict__ keys, const uint32_t* __restrict__
     seg_rec[s] = make_uint4((uint32_t)((uint64_t)keys[i] & ((1ull << colbits) - 1ull)), 0u, r, __float_as_uint(x));
   }
   if (i == m - 1) seg_ptr[n_seg] = (uint32_t)m;
+}
+
+// values of the segments [seg_lo, seg_hi) (one batch) once their upload has arrived: ent_val and the record's first value
+__global__ void mb_fill_values(const uint32_t* __restrict__ seg_ptr, uint4* __restrict__ seg_rec, const uint32_t* __restrict__ perm,
+                               const float* __restrict__ val, uint32_t e0, uint32_t seg_lo, uint32_t seg_hi, float* __restrict__ ent_val)
+{
+  const uint32_t s = seg_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= seg_hi) return;
+  const uint32_t i0 = seg_ptr[s], i1 = seg_ptr[s + 1];
+  for (uint32_t i = i0; i < i1; ++i) {
+    const float x = val[e0 + perm[i]];
+    ent_val[i] = x;
+    if (i == i0) seg_rec[s].w = __float_as_uint(x);
+  }
+}
+
+__global__ void gather_u32(const uint32_t* __restrict__ src, const int64_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+void minibatch_fill_values(fmwr_data* d, uint32_t seg_lo, uint32_t seg_hi)
+{
+  if (seg_hi <= seg_lo) return;
+  FMWR_LAUNCH(d->ctx, mb_fill_values, ceil_div((int64_t)seg_hi - seg_lo, 256), 256, 0, d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_perm.p, d->val.p,
+              d->mb_e0, seg_lo, seg_hi, d->mb_ent_val.p);
 }
 
 __global__ void mb_seg_len(const uint32_t* __restrict__ seg_ptr, uint4* __restrict__ seg_rec, uint32_t n_seg)
@@ -506,16 +540,20 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   }
   DBuf<K> keys_in, keys_out;
   DBuf<uint32_t> erow, idx_in, idx_out, head, segid;
-  keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); idx_in.alloc(m); idx_out.alloc(m); head.alloc(m); segid.alloc(m);
+  // values still uploading (one-shot training path): build the structure from rowptr / col alone and keep the permutation
+  const bool deferred = d->val_ready != nullptr && !d->val_ev.empty() && cudaEventQuery(d->val_ready) != cudaSuccess;
+  keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); idx_in.alloc(m); head.alloc(m); segid.alloc(m);
+  if (deferred) d->mb_perm.alloc(m); else idx_out.alloc(m);
+  uint32_t* perm_p = deferred ? d->mb_perm.p : idx_out.p;
   FMWR_LAUNCH(ctx, mb_keys<K>, ceil_div(rows * 32, 256), 256, 0, d->rowptr.p, d->col.p, row0, d->n, (uint32_t)batch, colbits,
               keys_in.p, erow.p);
   FMWR_LAUNCH(ctx, iota_u32, ceil_div(m, 256), 256, 0, idx_in.p, m);
   size_t tmp_bytes = 0;
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, idx_out.p, (int)m, 0,
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, perm_p, (int)m, 0,
                                             colbits + batchbits, ctx->stream));
   DBuf<char> tmp;
   tmp.alloc(tmp_bytes);
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, idx_out.p, (int)m, 0,
+  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, perm_p, (int)m, 0,
                                             colbits + batchbits, ctx->stream));
   ctx->launches += 1;
   FMWR_LAUNCH(ctx, mb_heads<K>, ceil_div(m, 256), 256, 0, keys_out.p, m, head.p);
@@ -525,8 +563,8 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_CUDA(cudaMemcpy(&last_head, head.p + (m - 1), 4, cudaMemcpyDeviceToHost));
   const uint32_t n_seg = last_id + last_head;
   d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_rec.alloc(n_seg);
-  data_wait_values(d);
-  FMWR_LAUNCH(ctx, mb_emit<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, idx_out.p, erow.p, d->val.p, e0, m,
+  if (!deferred) data_wait_values(d);
+  FMWR_LAUNCH(ctx, mb_emit<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, perm_p, erow.p, deferred ? (const float*)nullptr : d->val.p, e0, m,
               colbits, d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
   FMWR_LAUNCH(ctx, mb_seg_len, ceil_div(n_seg, 256), 256, 0, d->mb_seg_ptr.p, d->mb_seg_rec.p, n_seg);
   DBuf<uint32_t> bseg;
@@ -544,6 +582,23 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   d->mb_batch_seg[n_batches] = n_seg;
   for (int64_t b = n_batches - 1; b >= 0; --b) if (d->mb_batch_seg[b] > d->mb_batch_seg[b + 1]) d->mb_batch_seg[b] = d->mb_batch_seg[b + 1];
   d->mb_batch = batch; d->mb_row0 = row0;
+  d->mb_vals_pending = false;
+  if (deferred) {
+    // entries before each batch (rows of a batch are consecutive, so this is also the batch's offset in the sorted arrays)
+    std::vector<int64_t> rows_at(n_batches + 1);
+    for (int64_t b = 0; b <= n_batches; ++b) rows_at[b] = std::min<int64_t>(row0 + b * batch, d->n);
+    DBuf<int64_t> idx; DBuf<uint32_t> out;
+    idx.alloc(n_batches + 1); out.alloc(n_batches + 1);
+    FMWR_CUDA(cudaMemcpyAsync(idx.p, rows_at.data(), 8 * (n_batches + 1), cudaMemcpyHostToDevice, ctx->stream));
+    FMWR_LAUNCH(ctx, gather_u32, ceil_div(n_batches + 1, 256), 256, 0, d->rowptr.p, idx.p, n_batches + 1, out.p);
+    std::vector<uint32_t> ho(n_batches + 1);
+    FMWR_CUDA(cudaMemcpyAsync(ho.data(), out.p, 4 * (n_batches + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    d->mb_batch_ent.resize(n_batches + 1);
+    for (int64_t b = 0; b <= n_batches; ++b) d->mb_batch_ent[b] = (int64_t)ho[b] - (int64_t)e0;
+    d->mb_e0 = e0;
+    d->mb_vals_pending = true;
+  }
 }
 
 void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)

@@ -25,6 +25,8 @@ namespace fmwr {
 int solver_state_count(const SolverParams<double>& sp);
 double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s);
 void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
+void minibatch_fill_values(fmwr_data* d, uint32_t seg_lo, uint32_t seg_hi);
+void data_wait_values(fmwr_data* d);
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
@@ -595,7 +597,9 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   // The per-batch launches are recorded into CUDA graphs (chunks of GRAPH_CHUNK batches) and replayed by the device,
   // so the epoch does not depend on host launch latency / host jitter.  Per-kernel profiling, the tracker and the
   // NCCL path use plain launches.
-  const bool use_graph = !ctx->profile && step <= 0 && (!multi || peer) && getenv("FMWR_NO_GRAPH") == nullptr;
+  // one-shot path: the values of batch b may still be crossing PCIe; each batch waits for its chunk and fills its CSC values
+  const bool pending0 = d->mb_vals_pending;
+  const bool use_graph = !ctx->profile && step <= 0 && (!multi || peer) && !pending0 && getenv("FMWR_NO_GRAPH") == nullptr;
   constexpr int GRAPH_CHUNK = 2048;
   std::vector<cudaGraphExec_t> execs;
   std::vector<cudaGraph_t> graphs;
@@ -614,6 +618,15 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
     for (int64_t b = 0; b < n_batches && iter < max_iter; ++b) {
       if (use_graph && captured == 0) FMWR_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
       const int64_t rb = row0 + b * B;
+      if (d->mb_vals_pending) {
+        const int64_t last_entry = (int64_t)d->mb_e0 + d->mb_batch_ent[b + 1] - 1;
+        if (last_entry >= 0 && d->val_chunk > 0) {
+          const size_t ci = std::min<size_t>(d->val_ev.size() - 1, (size_t)(last_entry / d->val_chunk));
+          FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->val_ev[ci], 0));
+        }
+        minibatch_fill_values(d, (uint32_t)d->mb_batch_seg[b], (uint32_t)d->mb_batch_seg[b + 1]);
+        if (b == n_batches - 1) d->mb_vals_pending = false;      // every batch has its values now
+      }
       int64_t rows = std::min<int64_t>(B, d->n - rb);
       rows = std::min<int64_t>(rows, max_iter - iter);
       L.row_begin = rb; L.rows = (int)rows;
@@ -647,6 +660,11 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
         if (conv_times >= 3) { convergent = 1; break; }
       }
     }
+  }
+  if (d->mb_vals_pending) {                      // a truncated first epoch: finish the value fill for later calls
+    data_wait_values(d);
+    minibatch_fill_values(d, 0u, (uint32_t)d->mb_batch_seg[n_batches]);
+    d->mb_vals_pending = false;
   }
   flush_graph();
   if (sgd_l1) { const double h[2] = {u_w, u_v}; FMWR_CUDA(cudaMemcpyAsync((double*)m->scal.p + 1, h, 16, cudaMemcpyHostToDevice, ctx->stream)); }

@@ -162,3 +162,34 @@ def test_warm_state_continues_the_optimizer(gpu_ctx, solver, regs, mode):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert not np.array_equal(both[2], cold[2])
     d.close()
+
+
+@pytest.mark.parametrize("solver", [O.FTRL, O.SGD])
+def test_one_shot_train_equals_handle_path(gpu_ctx, solver):
+    """fmwr_train (host fm.matrix lists in, host model out; the values upload on the copy stream while the per-batch CSC is
+    sorted, and every batch waits only for its own chunk) must give the parameters of the handle path bit for bit --
+    also over two epochs, when the second pass finds every value in place."""
+    import ctypes as C
+    ctx = gpu_ctx
+    lib = L.lib()
+    n, fields, k = 700_000, [997] * 13, 8               # 9.1M entries: several upload chunks' worth is not needed for the check
+    rowptr, col, val, p = synth.fields_csr(n, fields, None, 1, 21)
+    score = synth.planted_scores_fast(rowptr, col, val, p, seed=22)
+    y = synth.labels_from_scores(score, "classification", seed=23)
+    rng = np.random.default_rng(24)
+    w = rng.normal(0, 0.02, p); v = rng.normal(0, 0.02, (p, k)); w0 = 0.01
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l1_w1=1e-4, l2_w1=1e-3, l2_v=1e-3)
+    for iters in (n - 1, 2 * (n - 1) - 12345):
+        sc = L.SolverCfg(solver=solver, max_iter=iters, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                         min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=16384, precision=L.F32,
+                         compat=L.COMPAT_REFERENCE, step_size=-1)
+        d = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)
+        m = L.Model(ctx, mc, p, L.F32); m.set(w0, w, v)
+        L.train_dev(ctx, m, d, sc)
+        a = m.get(); m.close(); d.close()
+        rs = np.diff(rowptr.astype(np.int64)).astype(np.int32)
+        ci = col.astype(np.int32); v64 = val.astype(np.float64); y64 = y.astype(np.float64)
+        bw0 = C.c_double(w0); bw = w.copy(); bv = v.copy()
+        L.check(lib.fmwr_train(C.byref(mc), C.byref(sc), C.c_int64(n), C.c_int64(p), C.c_int64(ci.size), L.ptr(rs), L.ptr(ci), L.ptr(v64),
+                               L.ptr(y64), C.byref(bw0), L.ptr(bw), L.ptr(bv), None))
+        assert a[0] == bw0.value and np.array_equal(a[1], bw) and np.array_equal(a[2], bv)

@@ -321,8 +321,15 @@ int fmwr_ctx_create(int device, fmwr_ctx** out)
       c->device = device;
       c->sm_count = prop.multiProcessorCount;
       if (prop.sharedMemPerBlockOptin > 0) c->smem_optin = (int)prop.sharedMemPerBlockOptin;
-      FMWR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-      FMWR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      {
+        // the staging stream carries upload chunks and their tiny f64 -> f32 narrowing kernels, one after the other; if such a
+        // kernel waits for SM slots behind the compute stream's large grids the whole upload pauses (measured: the key sort
+        // delayed the value upload by its own 25 ms).  High priority lets its CTAs in as soon as any CTA retires.
+        int prio_lo = 0, prio_hi = 0;
+        FMWR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        FMWR_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+        FMWR_CUDA(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi));
+      }
       FMWR_CUDA(cudaEventCreate(&c->ev0));
       FMWR_CUDA(cudaEventCreate(&c->ev1));
       for (int i = 0; i < 2; ++i) {
@@ -732,11 +739,19 @@ static fmwr_ctx* default_ctx()
 }
 
 // FMWR_TRACE=1: wall-clock of the phases of the one-shot entry points (stderr)
+// FMWR_TRACE=2: host-side laps only (no device synchronisation: the pipelined one-shot path stays pipelined)
 struct PhaseTimer {
-  bool on; std::chrono::steady_clock::time_point t;
-  PhaseTimer() : on(getenv("FMWR_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  bool on, host_only; std::chrono::steady_clock::time_point t;
+  PhaseTimer() : on(getenv("FMWR_TRACE") != nullptr && atoi(getenv("FMWR_TRACE")) == 1),
+                 host_only(getenv("FMWR_TRACE") != nullptr && atoi(getenv("FMWR_TRACE")) == 2), t(std::chrono::steady_clock::now()) {}
   void lap(const char* what)
   {
+    if (host_only) {
+      auto n = std::chrono::steady_clock::now();
+      fprintf(stderr, "[fmwr host ] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+      t = n;
+      return;
+    }
     if (!on) return;
     cudaDeviceSynchronize();
     auto n = std::chrono::steady_clock::now();
@@ -777,11 +792,12 @@ int fmwr_train(const fmwr_model_cfg* cfg, const fmwr_solver_cfg* s, int64_t n, i
     // minibatch path: the f64 values (60 % of the bytes) keep uploading on the copy stream while the compute stream
     // builds the per-batch CSC keys; every reader of the values waits for the upload's event
     const bool mb = s->mode == FMWR_MODE_MINIBATCH && s->solver >= FMWR_SGD && s->solver <= FMWR_TDAP;
-    dg.d = data_create_f64(ctx, n, p, nnz, row_size, col_idx, value, labels, mb && !pt.on);
-    pt.lap("data_create (H2D + narrow)");
+    // the model goes up first: once the value chunks are queued on the copy engine nothing else gets through until they are done
     if (fmwr_model_create(ctx, cfg, p, s->precision, &mg.m)) throw Error(FMWR_ERR_ARG, g_last_error);
     model_set_host(mg.m, *w0, w, v);
     pt.lap("model create + set");
+    dg.d = data_create_f64(ctx, n, p, nnz, row_size, col_idx, value, labels, mb && !pt.on);
+    pt.lap("data_create (H2D + narrow)");
     if (mb) {
       minibatch_build(dg.d, (s->compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0, s->batch_size);
       pt.lap("per-batch CSC build");

@@ -138,6 +138,7 @@ struct fmwr_ctx {
   struct PeerWin { void* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t bytes = 0; bool ready = false; unsigned als_step = 0; } peer;
   fmwr::DBuf<double> red_scratch;  // reductions
   fmwr::HBuf<double> h_scalar;
+  fmwr::HBuf<uint32_t> h_u32;      // pinned landing zone for small device -> host reads (pageable targets serialise with in-flight uploads)
 };
 
 struct fmwr_data {
@@ -171,6 +172,8 @@ struct fmwr_data {
   std::vector<cudaEvent_t> val_ev;     // one per uploaded chunk of val_chunk entries (deferred upload only)
   int64_t val_chunk = 0;
   fmwr::DBuf<double> val_stage[2];
+  fmwr::DBuf<double> val64;            // deferred upload: the raw f64 values; narrowed into `val` range by range on the compute stream
+  bool val_all_narrowed = true;
   // per-batch CSC built while the values were still in flight: ent_val / seg_rec.w of batch b are filled right before
   // batch b trains, as soon as the value chunks covering its rows have arrived (train_minibatch.cu)
   bool mb_vals_pending = false;

@@ -183,9 +183,18 @@ static void set_labels_f64(fmwr_data* d, const double* labels)
 }
 
 // the compute stream waits for a deferred value upload (no-op otherwise)
+void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi)
+{
+  if (!d->val64.p || hi <= lo) return;
+  f64_to_f32<<<ceil_div(hi - lo, 256), 256, 0, d->ctx->stream>>>(d->val64.p + lo, d->val.p + lo, hi - lo);
+  d->ctx->launches++;
+  FMWR_CUDA(cudaGetLastError());
+}
+
 void data_wait_values(fmwr_data* d)
 {
   if (d->val_ready) FMWR_CUDA(cudaStreamWaitEvent(d->ctx->stream, d->val_ready, 0));
+  if (!d->val_all_narrowed) { data_narrow_values(d, 0, d->nnz); d->val_all_narrowed = true; }
 }
 
 fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, const int32_t* row_size,
@@ -217,35 +226,45 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
       // f64 -> f32 narrowing on the device, chunked through two staging buffers.  defer_values: the chunks travel on the
       // copy stream and nobody waits here -- the one-shot training path sorts the (batch, feature) keys (which need only
       // rowptr and col) while the 8-byte values are still crossing PCIe, and waits for val_ready before it reads them.
-      const int64_t chunk = 16ll << 20;
-      cudaStream_t vs = defer_values ? ctx->copy_stream : ctx->stream;
-      d->val_stage[0].alloc(std::min(chunk, nnz));
-      d->val_stage[1].alloc(nnz > chunk ? std::min(chunk, nnz - chunk) : 1);
-      cudaEvent_t free_ev[2] = {nullptr, nullptr};
-      int ci = 0;
-      for (int64_t off = 0; off < nnz; off += chunk, ci ^= 1) {
-        const int64_t m = std::min(chunk, nnz - off);
-        if (free_ev[ci]) FMWR_CUDA(cudaStreamWaitEvent(vs, free_ev[ci], 0));
-        FMWR_CUDA(cudaMemcpyAsync(d->val_stage[ci].p, value + off, sizeof(double) * m, cudaMemcpyHostToDevice, vs));
-        f64_to_f32<<<ceil_div(m, 256), 256, 0, vs>>>(d->val_stage[ci].p, d->val.p + off, m);
-        ctx->launches++;
-        FMWR_CUDA(cudaGetLastError());
-        if (!free_ev[ci]) FMWR_CUDA(cudaEventCreateWithFlags(&free_ev[ci], cudaEventDisableTiming));
-        FMWR_CUDA(cudaEventRecord(free_ev[ci], vs));
-        if (defer_values) {
+      static const int64_t chunk_env = getenv("FMWR_VAL_CHUNK") ? atoll(getenv("FMWR_VAL_CHUNK")) : 0;
+      const int64_t chunk = chunk_env > 0 ? chunk_env : (16ll << 20);
+      if (defer_values) {
+        // the copy stream carries nothing but copies (a narrowing kernel between two chunks would stall the upload whenever it
+        // has to wait for SM slots behind the compute stream's sort): raw f64 into a full-size staging buffer, one event per chunk;
+        // the compute stream narrows exactly the range a batch needs once that batch's chunk has arrived
+        cudaStream_t vs = ctx->copy_stream;
+        FMWR_CUDA(cudaEventRecord(ctx->ev_copy[0], ctx->stream));        // the column ids go first: the key sort needs all of them
+        FMWR_CUDA(cudaStreamWaitEvent(vs, ctx->ev_copy[0], 0));
+        d->val64.alloc(nnz);
+        for (int64_t off = 0; off < nnz; off += chunk) {
+          const int64_t m = std::min(chunk, nnz - off);
+          FMWR_CUDA(cudaMemcpyAsync(d->val64.p + off, value + off, sizeof(double) * m, cudaMemcpyHostToDevice, vs));
           cudaEvent_t ce = nullptr;
           FMWR_CUDA(cudaEventCreateWithFlags(&ce, cudaEventDisableTiming));
           FMWR_CUDA(cudaEventRecord(ce, vs));
           d->val_ev.push_back(ce);
         }
-      }
-      d->val_chunk = chunk;
-      for (int i = 0; i < 2; ++i) if (free_ev[i]) cudaEventDestroy(free_ev[i]);
-      if (defer_values) {
+        d->val_chunk = chunk;
+        d->val_all_narrowed = false;
         FMWR_CUDA(cudaEventCreateWithFlags(&d->val_ready, cudaEventDisableTiming));
         FMWR_CUDA(cudaEventRecord(d->val_ready, vs));
       } else {
-        FMWR_CUDA(cudaStreamSynchronize(vs));
+        d->val_stage[0].alloc(std::min(chunk, nnz));
+        d->val_stage[1].alloc(nnz > chunk ? std::min(chunk, nnz - chunk) : 1);
+        cudaEvent_t free_ev[2] = {nullptr, nullptr};
+        int ci = 0;
+        for (int64_t off = 0; off < nnz; off += chunk, ci ^= 1) {
+          const int64_t m = std::min(chunk, nnz - off);
+          if (free_ev[ci]) FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, free_ev[ci], 0));
+          FMWR_CUDA(cudaMemcpyAsync(d->val_stage[ci].p, value + off, sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
+          f64_to_f32<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(d->val_stage[ci].p, d->val.p + off, m);
+          ctx->launches++;
+          FMWR_CUDA(cudaGetLastError());
+          if (!free_ev[ci]) FMWR_CUDA(cudaEventCreateWithFlags(&free_ev[ci], cudaEventDisableTiming));
+          FMWR_CUDA(cudaEventRecord(free_ev[ci], ctx->stream));
+        }
+        for (int i = 0; i < 2; ++i) if (free_ev[i]) cudaEventDestroy(free_ev[i]);
+        FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
         d->val_stage[0].release(); d->val_stage[1].release();
       }
     }
@@ -476,10 +495,30 @@ __global__ void mb_fill_values(const uint32_t* __restrict__ seg_ptr, uint4* __re
   }
 }
 
-__global__ void gather_u32(const uint32_t* __restrict__ src, const int64_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ out)
+// device -> pinned host memory by a kernel (zero-copy store over PCIe): no copy engine, so it cannot queue behind uploads
+__global__ void peek_u32(const uint32_t* __restrict__ src, int64_t n, uint32_t* __restrict__ host_dst)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = src[idx[i]];
+  if (i < n) host_dst[i] = src[i];
+}
+__global__ void peek2_u32(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ host_dst)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) { host_dst[0] = *a; host_dst[1] = *b; }
+}
+
+__global__ void fill_u32(uint32_t* __restrict__ a, int64_t n, uint32_t v)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// out[b] = rowptr[min(row0 + b * batch, n)]: the first entry of batch b
+__global__ void batch_row_ptr(const uint32_t* __restrict__ rowptr, int64_t row0, int64_t batch, int64_t n, int64_t count, uint32_t* __restrict__ out)
+{
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= count) return;
+  const int64_t r = row0 + b * batch;
+  out[b] = rowptr[r < n ? r : n];
 }
 
 void minibatch_fill_values(fmwr_data* d, uint32_t seg_lo, uint32_t seg_hi)
@@ -525,9 +564,24 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   const int64_t n_batches = rows > 0 ? ceil_div64(rows, batch) : 0;
   d->mb_batch_seg.assign(n_batches + 1, 0);
   if (rows <= 0) { d->mb_batch = batch; d->mb_row0 = row0; return; }
-  uint32_t e0 = 0, e1 = 0;
-  FMWR_CUDA(cudaMemcpy(&e0, d->rowptr.p + row0, 4, cudaMemcpyDeviceToHost));
-  FMWR_CUDA(cudaMemcpy(&e1, d->rowptr.p + d->n, 4, cudaMemcpyDeviceToHost));
+  // small device -> host reads are zero-copy stores of a kernel into pinned memory: a cudaMemcpy of 4 bytes would queue behind
+  // the upload chunks on the copy engine (measured: the build then ends when the upload ends)
+  ctx->h_u32.ensure(2 * (size_t)n_batches + 32);
+  uint32_t* hp = ctx->h_u32.p;
+  FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, d->rowptr.p + row0, d->rowptr.p + d->n, hp);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint32_t e0 = hp[0], e1 = hp[1];
+  {
+    // entries before each batch (rows of a batch are consecutive, so this is also the batch's offset in the sorted arrays);
+    // used by the deferred-value path of the one-shot trainer
+    DBuf<uint32_t> bp;
+    bp.alloc(n_batches + 1);
+    FMWR_LAUNCH(ctx, batch_row_ptr, ceil_div(n_batches + 1, 256), 256, 0, d->rowptr.p, row0, batch, d->n, n_batches + 1, bp.p);
+    FMWR_LAUNCH(ctx, peek_u32, ceil_div(n_batches + 1, 256), 256, 0, bp.p, n_batches + 1, hp + 8);
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    d->mb_batch_ent.resize(n_batches + 1);
+    for (int64_t b = 0; b <= n_batches; ++b) d->mb_batch_ent[b] = (int64_t)hp[8 + b] - (int64_t)e0;
+  }
   const int64_t m = (int64_t)e1 - e0;
   const int colbits = bits_for((uint64_t)(d->p > 0 ? d->p - 1 : 0));
   const int batchbits = bits_for((uint64_t)(n_batches > 0 ? n_batches - 1 : 0));
@@ -558,10 +612,9 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   ctx->launches += 1;
   FMWR_LAUNCH(ctx, mb_heads<K>, ceil_div(m, 256), 256, 0, keys_out.p, m, head.p);
   exclusive_scan_u32(ctx, head.p, segid.p, m);
-  uint32_t last_id = 0, last_head = 0;
-  FMWR_CUDA(cudaMemcpy(&last_id, segid.p + (m - 1), 4, cudaMemcpyDeviceToHost));
-  FMWR_CUDA(cudaMemcpy(&last_head, head.p + (m - 1), 4, cudaMemcpyDeviceToHost));
-  const uint32_t n_seg = last_id + last_head;
+  FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, segid.p + (m - 1), head.p + (m - 1), hp);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint32_t n_seg = hp[0] + hp[1];
   d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_rec.alloc(n_seg);
   if (!deferred) data_wait_values(d);
   FMWR_LAUNCH(ctx, mb_emit<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, perm_p, erow.p, deferred ? (const float*)nullptr : d->val.p, e0, m,
@@ -569,36 +622,21 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_LAUNCH(ctx, mb_seg_len, ceil_div(n_seg, 256), 256, 0, d->mb_seg_ptr.p, d->mb_seg_rec.p, n_seg);
   DBuf<uint32_t> bseg;
   bseg.alloc(n_batches + 1);
-  // default every batch offset to n_seg (covers trailing empty batches), then fill real starts
-  std::vector<uint32_t> fill(n_batches + 1, n_seg);
-  FMWR_CUDA(cudaMemcpyAsync(bseg.p, fill.data(), 4 * (n_batches + 1), cudaMemcpyHostToDevice, ctx->stream));
+  // default every batch offset to n_seg (covers trailing empty batches), then fill real starts.  (A kernel, not a host ->
+  // device copy: a copy would queue behind every value chunk still waiting for the H2D engine.)
+  FMWR_LAUNCH(ctx, fill_u32, ceil_div(n_batches + 1, 256), 256, 0, bseg.p, n_batches + 1, n_seg);
   FMWR_LAUNCH(ctx, mb_batch_bounds<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, m, colbits, n_batches, n_seg,
               bseg.p);
-  std::vector<uint32_t> hb(n_batches + 1);
-  FMWR_CUDA(cudaMemcpyAsync(hb.data(), bseg.p, 4 * (n_batches + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_LAUNCH(ctx, peek_u32, ceil_div(n_batches + 1, 256), 256, 0, bseg.p, n_batches + 1, hp);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> hb(hp, hp + n_batches + 1);
   // empty batches in the middle were filled by the next non-empty one; trailing ones keep n_seg
   for (int64_t b = 0; b <= n_batches; ++b) d->mb_batch_seg[b] = hb[b];
   d->mb_batch_seg[n_batches] = n_seg;
   for (int64_t b = n_batches - 1; b >= 0; --b) if (d->mb_batch_seg[b] > d->mb_batch_seg[b + 1]) d->mb_batch_seg[b] = d->mb_batch_seg[b + 1];
   d->mb_batch = batch; d->mb_row0 = row0;
   d->mb_vals_pending = false;
-  if (deferred) {
-    // entries before each batch (rows of a batch are consecutive, so this is also the batch's offset in the sorted arrays)
-    std::vector<int64_t> rows_at(n_batches + 1);
-    for (int64_t b = 0; b <= n_batches; ++b) rows_at[b] = std::min<int64_t>(row0 + b * batch, d->n);
-    DBuf<int64_t> idx; DBuf<uint32_t> out;
-    idx.alloc(n_batches + 1); out.alloc(n_batches + 1);
-    FMWR_CUDA(cudaMemcpyAsync(idx.p, rows_at.data(), 8 * (n_batches + 1), cudaMemcpyHostToDevice, ctx->stream));
-    FMWR_LAUNCH(ctx, gather_u32, ceil_div(n_batches + 1, 256), 256, 0, d->rowptr.p, idx.p, n_batches + 1, out.p);
-    std::vector<uint32_t> ho(n_batches + 1);
-    FMWR_CUDA(cudaMemcpyAsync(ho.data(), out.p, 4 * (n_batches + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-    d->mb_batch_ent.resize(n_batches + 1);
-    for (int64_t b = 0; b <= n_batches; ++b) d->mb_batch_ent[b] = (int64_t)ho[b] - (int64_t)e0;
-    d->mb_e0 = e0;
-    d->mb_vals_pending = true;
-  }
+  if (deferred) { d->mb_e0 = e0; d->mb_vals_pending = true; }
 }
 
 void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)

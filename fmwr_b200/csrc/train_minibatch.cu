@@ -27,6 +27,7 @@ double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solv
 void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
 void minibatch_fill_values(fmwr_data* d, uint32_t seg_lo, uint32_t seg_hi);
 void data_wait_values(fmwr_data* d);
+void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi);
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
@@ -624,8 +625,9 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
           const size_t ci = std::min<size_t>(d->val_ev.size() - 1, (size_t)(last_entry / d->val_chunk));
           FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->val_ev[ci], 0));
         }
+        data_narrow_values(d, b == 0 ? 0 : (int64_t)d->mb_e0 + d->mb_batch_ent[b], (int64_t)d->mb_e0 + d->mb_batch_ent[b + 1]);
         minibatch_fill_values(d, (uint32_t)d->mb_batch_seg[b], (uint32_t)d->mb_batch_seg[b + 1]);
-        if (b == n_batches - 1) d->mb_vals_pending = false;      // every batch has its values now
+        if (b == n_batches - 1) { d->mb_vals_pending = false; d->val_all_narrowed = true; }      // every batch has its values now
       }
       int64_t rows = std::min<int64_t>(B, d->n - rb);
       rows = std::min<int64_t>(rows, max_iter - iter);

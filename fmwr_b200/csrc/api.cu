@@ -796,7 +796,8 @@ int fmwr_train(const fmwr_model_cfg* cfg, const fmwr_solver_cfg* s, int64_t n, i
     if (fmwr_model_create(ctx, cfg, p, s->precision, &mg.m)) throw Error(FMWR_ERR_ARG, g_last_error);
     model_set_host(mg.m, *w0, w, v);
     pt.lap("model create + set");
-    dg.d = data_create_f64(ctx, n, p, nnz, row_size, col_idx, value, labels, mb && !pt.on);
+    // (not with the tracker: its mid-epoch scoring pass reads every row's values)
+    dg.d = data_create_f64(ctx, n, p, nnz, row_size, col_idx, value, labels, mb && !pt.on && s->step_size <= 0);
     pt.lap("data_create (H2D + narrow)");
     if (mb) {
       minibatch_build(dg.d, (s->compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0, s->batch_size);

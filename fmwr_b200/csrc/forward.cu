@@ -44,7 +44,9 @@ struct FwdLaunch {
   template <class T, int LPR, int CH>
   void run()
   {
-    if (short_rows(d->nnz, d->n, LPR)) go<T, LPR, CH, LPR>();
+    const int tm = team_mode(d->nnz, d->n, LPR);
+    if (tm == 1) go<T, LPR, CH, LPR>();
+    else if (tm == 2) go<T, LPR, CH, (LPR <= 8 ? 16 : 32)>();
     else go<T, LPR, CH, 32>();
   }
   template <class T, int LPR, int CH, int TEAM>

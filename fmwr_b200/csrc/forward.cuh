@@ -210,6 +210,19 @@ __device__ __forceinline__ T team_forward_partial(const uint32_t* __restrict__ c
 
 // rows with at most this many non-zeros per LPR-lane group on average go one row per group
 __host__ __device__ inline bool short_rows(int64_t nnz, int64_t n, int lpr) { return lpr < 32 && n > 0 && nnz <= n * 4 * (32 / lpr); }
+// 1: one row per LPR-lane group; 2: one row per half warp (two sub-groups; the per-row fixed cost -- bounds, linear sweep,
+// combine, team sum, stores -- is shared by two rows per warp); 0: one row per warp.  FMWR_TEAM=8|16|32 forces a choice.
+inline int team_mode(int64_t nnz, int64_t n, int lpr)
+{
+  static const int forced = getenv("FMWR_TEAM") ? atoi(getenv("FMWR_TEAM")) : 0;
+  if (forced == 32) return 0;
+  if (forced == 16) return lpr <= 8 ? 2 : (lpr == 16 ? 1 : 0);
+  if (forced == 8) return lpr < 32 ? 1 : 0;
+  if (short_rows(nnz, n, lpr)) return 1;
+  // long rows: half-warp teams measured best for every k <= 32 (predict 8.4 -> 6.6 ms at k = 32, 4.8 -> 3.7 ms at k = 8); k = 64 is
+  // DRAM-bound either way and keeps one row per 16-lane group
+  return lpr <= 8 ? 2 : (lpr == 16 ? 1 : 0);
+}
 
 // table-exact fast_pnorm (reference src/util/Random.h:95-111; Y table regenerated, see link_tables.cu)
 __device__ __forceinline__ double dev_fast_pnorm(const double* __restrict__ Y, double x)

@@ -477,7 +477,9 @@ struct MbLaunch {
       FMWR_LAUNCH(ctx, (mb_exchange_kernel<TT, LPR, CH>), xgrid, 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
                   m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, s_stride, pa);
     } else if (phase == 0) {
-      if (short_rows(d->nnz, d->n, LPR)) k1<TT, LPR, CH, LPR>();
+      const int tm = team_mode(d->nnz, d->n, LPR);
+      if (tm == 1) k1<TT, LPR, CH, LPR>();
+      else if (tm == 2) k1<TT, LPR, CH, (LPR <= 8 ? 16 : 32)>();
       else k1<TT, LPR, CH, 32>();
     } else {
       constexpr int G = 32 / LPR;

@@ -160,3 +160,39 @@ def test_als_converges_on_planted_fm(gpu_ctx):
     rmse_v = float(np.sqrt(np.mean((p_v - y) ** 2)))
     rmse_nov = float(np.sqrt(np.mean((p_nov - y) ** 2)))
     assert rmse_v < 0.2 and rmse_v < 0.6 * rmse_nov, (rmse_v, rmse_nov)
+
+
+def test_als_paths_agree_on_the_same_data(gpu_ctx):
+    """the fused field-structured passes (default), the same without the warp-segmented reduction, without the row
+    permutation, the row-major streaming passes and the column-parallel kernels are five implementations of one
+    Gauss-Seidel sweep: on the same data they must end at the same parameters"""
+    import os
+    ctx = gpu_ctx
+    fields = [900, 260, 24]
+    n, k = 20000, 8
+    rowptr, col, val, p = synth.fields_csr(n, fields, [0, 1, 0], 0, 51)
+    y = synth.labels_from_scores(synth.planted_scores_fast(rowptr, col, val, p, seed=52), "regression", seed=53)
+    rng = np.random.default_rng(54)
+    v = rng.normal(0, 0.05, (p, k))
+    sc = L.SolverCfg(solver=L.ALS, max_iter=3, random_step=1, min_target=float(y.min()), max_target=float(y.max()), mode=L.MODE_EXACT,
+                     precision=L.F64, compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=1)
+    mc = L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=k)
+    out = {}
+    for tag, env in (("default", None), ("no_warpseg", "FMWR_ALS_NO_WARPSEG"), ("no_perm", "FMWR_ALS_NO_PERM"),
+                     ("row_major", "FMWR_ALS_NO_DENSE"), ("column", "FMWR_ALS_COLUMN")):
+        if env:
+            os.environ[env] = "1"
+        try:
+            d = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)          # a fresh handle: the layouts are cached per handle
+            m = L.Model(ctx, mc, p, L.F64)
+            m.set(0.0, np.zeros(p), v)
+            L.train_dev(ctx, m, d, sc)
+            out[tag] = m.get()
+            m.close(); d.close()
+        finally:
+            if env:
+                os.environ.pop(env, None)
+    ref = out["default"]
+    assert float(np.max(np.abs(ref[2] - v))) > 1e-3
+    for tag, got in out.items():
+        assert relerr(got[0], ref[0]) < 1e-8 and relerr(got[1], ref[1]) < 1e-8 and relerr(got[2], ref[2]) < 1e-8, tag

@@ -193,3 +193,39 @@ def test_one_shot_train_equals_handle_path(gpu_ctx, solver):
         L.check(lib.fmwr_train(C.byref(mc), C.byref(sc), C.c_int64(n), C.c_int64(p), C.c_int64(ci.size), L.ptr(rs), L.ptr(ci), L.ptr(v64),
                                L.ptr(y64), C.byref(bw0), L.ptr(bw), L.ptr(bv), None))
         assert a[0] == bw0.value and np.array_equal(a[1], bw) and np.array_equal(a[2], bv)
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL])
+def test_minibatch_ragged_rows_with_empty_rows_and_wide_rows(gpu_ctx, solver):
+    """edge cases of the data: empty rows (score = w0 only, no segment), rows wider than one gather chunk (> 64 non-zeros),
+    a batch size that does not divide the row count, k that needs padding -- batch = 1 must still equal the exact mode,
+    and a larger batch must be deterministic and finite"""
+    rng = np.random.default_rng(11)
+    n, p, k = 500, 400, 5
+    rowptr, col, val = synth.random_csr(n, p, 30, seed=12, empty_rows=True)
+    # make a few rows very wide
+    counts = np.diff(rowptr.astype(np.int64))
+    assert (counts == 0).any()
+    wide = [3, 250, 499]
+    rows = []
+    for r in range(n):
+        if r in wide:
+            c = np.sort(rng.choice(p, 150, replace=False)).astype(np.uint32)
+            rows.append((c, rng.uniform(0.5, 1.5, c.size).astype(np.float32)))
+        else:
+            rows.append((col[rowptr[r]:rowptr[r + 1]], val[rowptr[r]:rowptr[r + 1]]))
+    rowptr2 = np.concatenate([[0], np.cumsum([c.size for c, _ in rows])]).astype(np.uint32)
+    col2 = np.concatenate([c for c, _ in rows]).astype(np.uint32)
+    val2 = np.concatenate([x for _, x in rows]).astype(np.float32)
+    ds = dict(n=n, p=p, rowptr=rowptr2, col=col2, val=val2)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.05, p); v = rng.normal(0, 0.05, (p, k))
+    iters = 2 * (n - 1) + 3
+    regs = dict(l2_w=0.01, l2_v=0.01)
+    a, _, _ = mb_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, SOLV[solver], k, 0.1, w, v, iters, 1, regs=regs, compat=L.COMPAT_SKIP_ROW0)
+    b, _, _ = mb_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, SOLV[solver], k, 0.1, w, v, iters, 1, mode=L.MODE_EXACT, regs=regs, compat=L.COMPAT_SKIP_ROW0)
+    assert relerr(a[0], b[0]) < 1e-10 and relerr(a[1], b[1]) < 1e-10 and relerr(a[2], b[2]) < 1e-10
+    c1, p1, _ = mb_train(gpu_ctx, L.F32, ds, y, L.CLASSIFICATION, SOLV[solver], k, 0.1, w, v, iters, 37, regs=regs)
+    c2, p2, _ = mb_train(gpu_ctx, L.F32, ds, y, L.CLASSIFICATION, SOLV[solver], k, 0.1, w, v, iters, 37, regs=regs)
+    assert c1[0] == c2[0] and np.array_equal(c1[1], c2[1]) and np.array_equal(c1[2], c2[2])
+    assert np.isfinite(c1[2]).all() and np.isfinite(p1).all() and np.array_equal(p1, p2)

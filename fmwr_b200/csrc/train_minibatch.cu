@@ -31,7 +31,7 @@ void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi);
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
-template <class T, int LPR, int CH, int TEAM>
+template <class T, int LPR, int CH, int TEAM, bool PEERK>
 __global__ void __launch_bounds__(256, FMWR_FWD_BLOCKS)
 mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val,
                   const float* __restrict__ y, const T* __restrict__ w, const T* __restrict__ v,
@@ -58,7 +58,7 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
       // feature-parallel: this rank holds a column slice, so the row's score is not known yet.  Emit the partials:
       // S_f of the slice and its additive scalar (see team_gather); 1/2 sum S_f^2 is formed after the exchange
       const T addend = team_forward_partial<T, LPR, CH, TEAM>(col, val, b, e, w, v, kp, k1, S);
-      if (partial == 2) {
+      if (PEERK) {
         // peer window: the partial goes straight into the memory of the rank that finalises this row (NVLink stores)
         if (r < rows) {
           const int owner = r / pa.rows_per_owner;
@@ -85,7 +85,7 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
       for (int ch = 0; ch < CH; ++ch) dst[ch * LPR + tl] = arr_to_vec(S[ch]);
     }
   }
-  if (partial == 2) peer_signal(pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1);
+  if (PEERK) peer_signal(pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1);
 }
 
 // ---- peer exchange: the rank that owns a row sums the world's partials IN RANK ORDER (deterministic), forms the
@@ -511,9 +511,15 @@ void MbLaunch<T>::k1()
   // peer mode: one release fence per CTA at the end (it waits for the CTA's NVLink stores), so few fat CTAs
   static const int k1_ctas = getenv("FMWR_K1_CTAS") ? atoi(getenv("FMWR_K1_CTAS")) : 4;      // resident CTAs per SM: measured best (persistent warps)
   const int fgrid = (int)std::min<int64_t>(ceil_div(rows, rpb), (int64_t)ctx->sm_count * (partial == 2 ? 4 : k1_ctas));
-  FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH, TEAM>), fgrid, 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
-              (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
-              m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial, pa);
+  // (the peer-window variant is a separate instantiation: indexing the window table by owner costs every thread a stack frame)
+  if (partial == 2)
+    FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH, TEAM, true>), fgrid, 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
+                (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
+                m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial, pa);
+  else
+    FMWR_LAUNCH(ctx, (mb_forward_kernel<TT, LPR, CH, TEAM, false>), fgrid, 256, 0, d->rowptr.p, d->col.p, d->val.p, d->y.p,
+                (const TT*)m->w.p, (const TT*)m->v.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, m->cfg.keep_w1,
+                m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, mult, Scache, s_stride, partial, pa);
 }
 
 template <class T>

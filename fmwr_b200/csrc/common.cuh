@@ -243,6 +243,16 @@ struct PeerArgs {
   size_t off_P, off_S, off_mult;   // byte offsets of the partial slabs [world][rows_per_owner][stride], S cache [B][stride], mult [B]
 };
 
+// pa.base[i] with a run-time i, as a chain of selects: indexing a kernel parameter array dynamically makes the compiler copy
+// the whole struct to a per-thread stack frame
+__device__ __forceinline__ char* peer_base(const PeerArgs& pa, int i)
+{
+  char* p = pa.base[0];
+#pragma unroll
+  for (int h = 1; h < 8; ++h) p = (h == i) ? pa.base[h] : p;
+  return p;
+}
+
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
@@ -252,7 +262,7 @@ __device__ __forceinline__ void peer_signal(const PeerArgs& pa, int flag_base, i
 {
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t* ctl = reinterpret_cast<uint32_t*>(pa.base[pa.rank]);
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
     __threadfence_system();                                   // this CTA's (peer) stores before the count
     const unsigned done = atomicAdd(ctl + count_word, 1u);
     if (done == gridDim.x - 1) {
@@ -260,7 +270,9 @@ __device__ __forceinline__ void peer_signal(const PeerArgs& pa, int flag_base, i
       const uint32_t ep = ctl[epoch_word] + 1u;
       ctl[epoch_word] = ep;
       __threadfence_system();
-      for (int h = 0; h < pa.world; ++h) st_release_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < pa.world) st_release_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
     }
   }
 }
@@ -270,7 +282,7 @@ __device__ __forceinline__ void peer_signal(const PeerArgs& pa, int flag_base, i
 __device__ __forceinline__ void peer_wait(const PeerArgs& pa, int flag_base, int epoch_word)
 {
   if ((int)threadIdx.x < pa.world) {
-    uint32_t* ctl = reinterpret_cast<uint32_t*>(pa.base[pa.rank]);
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
     const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(ctl + epoch_word);
     const uint32_t* f = ctl + flag_base + 32 * threadIdx.x;
     const long long t0 = clock64();

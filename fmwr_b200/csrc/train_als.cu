@@ -1089,7 +1089,9 @@ __global__ void __launch_bounds__(256) ab_push_kernel(const T* __restrict__ AB, 
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
     T s = AB[i];
     for (int r = 1; r < n_rep; ++r) s += AB[(size_t)r * n2 + i];
-    for (int h = 0; h < pa.world; ++h) reinterpret_cast<T*>(pa.base[h] + buf_off + (size_t)pa.rank * slot_bytes)[i] = s;
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < pa.world) reinterpret_cast<T*>(pa.base[h] + buf_off + (size_t)pa.rank * slot_bytes)[i] = s;
   }
   peer_signal(pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1);
 }

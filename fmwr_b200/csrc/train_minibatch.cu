@@ -62,7 +62,7 @@ mb_forward_kernel(const uint32_t* __restrict__ rowptr, const uint32_t* __restric
         // peer window: the partial goes straight into the memory of the rank that finalises this row (NVLink stores)
         if (r < rows) {
           const int owner = r / pa.rows_per_owner;
-          T* dst = reinterpret_cast<T*>(pa.base[owner] + pa.off_P) + ((size_t)pa.rank * pa.rows_per_owner + (r - owner * pa.rows_per_owner)) * s_stride;
+          T* dst = reinterpret_cast<T*>(peer_base(pa, owner) + pa.off_P) + ((size_t)pa.rank * pa.rows_per_owner + (r - owner * pa.rows_per_owner)) * s_stride;
           if (tl == 0) {                      // a whole 16-byte vector {addend, 0..}: no partial-sector write over NVLink
             T pad[Vec<T>::N];
 #pragma unroll
@@ -107,7 +107,7 @@ mb_exchange_kernel(const float* __restrict__ y, const double* __restrict__ scal,
   const int r_lo = pa.rank * pa.rows_per_owner;
   const int r_hi = min(rows, r_lo + pa.rows_per_owner);
   const int n_local = max(0, r_hi - r_lo);
-  const T* P = reinterpret_cast<const T*>(pa.base[pa.rank] + pa.off_P);
+  const T* P = reinterpret_cast<const T*>(peer_base(pa, pa.rank) + pa.off_P);
   const T w0 = k0 ? T(scal[0]) : T(0);
   for (int base = 0; base < n_local; base += ngrp) {             // warp-uniform trip count: the shuffles below need every lane
     const int rl = base + grp0;
@@ -144,7 +144,9 @@ mb_exchange_kernel(const float* __restrict__ y, const double* __restrict__ scal,
 #pragma unroll
       for (int i = 0; i < VN; ++i) tail[i] = T(0);
       tail[0] = m;
-      for (int h = 0; h < pa.world; ++h) {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h >= pa.world) break;
         T* dst = reinterpret_cast<T*>(pa.base[h] + pa.off_S) + (size_t)r * s_stride;
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) reinterpret_cast<V16*>(dst)[ch * LPR + l] = arr_to_vec(S[ch]);

@@ -4,10 +4,26 @@
 // calculate_param (reference src/solver/SGD_Learner.h:79-178, FTRL_Learner.h:64-202,
 // TDAP_Learner.h:79-233).  Samples are strictly serial (w0 is read by every forward and written
 // by every update), so the parallelism is INSIDE a sample: one persistent CTA walks the visit
-// sequence; thread (slot, l) owns non-zero `slot` of the row and the 16-byte vector l of that
-// feature's factor row.  Within one sample every coordinate update is independent given `mult`
-// and the frozen S_f (each (f, j) is touched once), which is exactly what the reference's
-// f-outer / nnz-inner loops compute.
+// sequence.  Within one sample every coordinate update is independent given `mult` and the
+// frozen S_f (each (f, j) is touched once), which is exactly what the reference's f-outer /
+// nnz-inner loops compute.
+//
+// The sample time is a chain of latencies (DRAM ~1000 cycles, shared memory ~30, IEEE div/sqrt
+// sequences that end basic blocks), measured with clock64() per role (profiles/r01_summary.md).
+// The CTA is therefore warp-specialised, and each role runs only its own short program:
+//   * factor warps (0 .. FW-1): thread (slot, l) owns non-zero `slot` of the row and the 16-byte
+//     vector l of that feature's factor row; warps without a non-zero only hit the barriers;
+//   * the linear warp: lane = non-zero (two per lane in registers), owns w_j and its state;
+//   * the pipeline warp: runs ahead of the sample being processed -- visit index (t+4), row bounds
+//     and label (t+3), the row's first SLOTS column/value entries (t+2) into shared-memory rings,
+//     and an L2 prefetch of every parameter / state line sample t+1 will touch -- and owns w0 and
+//     the scalar optimizer state (fp64, double-buffered by sample parity so it is updated while
+//     the other warps still read it).  The CSR arrays are read-only and L2 is the coherence point,
+//     so running ahead cannot observe stale data.
+// Rows that fit one round (nnz <= SLOTS) read theta and its state once, with the forward gather,
+// and keep them in registers for the update.  Two barriers per sample.
+// fp32 FTRL/TDAP use the branch-free MUFU sqrt/rcp forms (<= 2 ulp, the same order as fp32 rounding
+// itself; lets the four elements of a vector interleave); fp64 keeps IEEE operations throughout.
 #include "forward.cuh"
 #include "coord.cuh"
 
@@ -18,6 +34,8 @@ namespace fmwr {
 
 constexpr int EX_THREADS = 512;
 constexpr int EX_WARPS = EX_THREADS / 32;
+constexpr int EX_FW = EX_WARPS - 2;          // factor warps
+constexpr int EX_NL = 2;                     // non-zeros per lane the linear warp keeps in registers
 
 template <class T>
 struct ExactArgs {
@@ -31,239 +49,415 @@ struct ExactArgs {
   int skip_row0;             // F5: scan rows 1..n-1
   int64_t t_begin, t_end;    // sample counters of this launch
   int tdap_zw_index;         // F6
+  int prefetch;              // L2 run-ahead of parameter lines (FMWR_EXACT_PREFETCH=0 disables)
   SolverParams<T> sp;
   double lo, hi;
 };
 
-template <class T, int LPR, int CH>
+// CTA barrier reached from role-specific code (every warp arrives whole, the same number of times per sample)
+__device__ __forceinline__ void ex_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// one coordinate step; LIN selects the linear-weight hyper-parameters
+template <class T, int SOLVER, bool LIN, bool FAST>
+__device__ __forceinline__ T exact_step(T th, T g, T (&st)[4], const SolverParams<T>& sp, T u)
+{
+  if (SOLVER == FMWR_SGD) {
+    T q = sp.l1 ? st[0] : T(0);
+    th = sgd_step(th, g, sp.lr, LIN ? sp.reg_w : sp.reg_v, sp.l1, u, q);
+    st[0] = q;
+    return th;
+  }
+  if (SOLVER == FMWR_FTRL)
+    return ftrl_step<T, FAST>(th, g, st[0], st[1], LIN ? sp.alpha_w : sp.alpha_v, LIN ? sp.beta_w : sp.beta_v,
+                              LIN ? sp.l1_w : sp.l1_v, LIN ? sp.l2_w : sp.l2_v);
+  const T z = tdap_state<T, FAST>(th, g, st[0], st[1], st[2], st[3], LIN ? sp.alpha_w : sp.alpha_v, sp.egamma);
+  return tdap_refresh<T, FAST>(z, st[2], LIN ? sp.l1_w : sp.l1_v, LIN ? sp.l2_w : sp.l2_v);
+}
+
+template <class T, int LPR, int CH, int SOLVER>
 __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
 {
   typedef typename Vec<T>::type V16;
   constexpr int VN = Vec<T>::N;
-  constexpr int KP = LPR * CH * VN;
-  constexpr int SLOTS = EX_THREADS / LPR;
-  constexpr int SPW = 32 / LPR;            // slots per warp
-  __shared__ T sS[EX_WARPS][KP];
-  __shared__ T sPart[EX_WARPS];
-  __shared__ T sFin[KP];
-  __shared__ T sScore;
-  __shared__ double sc[8];                  // w0 and the scalar optimizer state
+  constexpr int SLOTS = EX_FW * 32 / LPR;
+  constexpr int SPW = 32 / LPR;             // slots per factor warp
+  constexpr int NS = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);   // state arrays (SGD: only with L1)
+  constexpr bool KEEP = (CH == 1);          // registers for theta + state only at one vector per lane
+  constexpr bool FAST = (sizeof(T) == 4) && (SOLVER != FMWR_SGD);
+  constexpr int RING = 8, CRING = 4;
+  constexpr int NC = (SLOTS + 31) / 32;     // ring entries per pipeline lane
+  constexpr int NL = EX_NL;
+  constexpr int W_PIPE = EX_FW, W_LIN = EX_FW + 1;
+  constexpr int LINE = 128 / (int)sizeof(T);
+  __shared__ V16 sS[EX_FW][LPR * CH];
+  __shared__ T sPart[EX_FW];
+  __shared__ T sLin;
+  __shared__ double sc[2][8];               // w0 and the scalar optimizer state, by sample parity
+  __shared__ uint32_t rRow[RING], rB[RING], rE[RING];
+  __shared__ float rY[RING];
+  __shared__ uint32_t rCol[CRING][SLOTS];
+  __shared__ float rVal[CRING][SLOTS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = tid / LPR, l = tid % LPR;
+  const int slot = tid / LPR, l = tid % LPR;          // factor warps only
   const int kp = a.kp;
   const SolverParams<T> sp = a.sp;
-  if (tid < 8) sc[tid] = a.scal[tid];
-  __syncthreads();
+  const bool sgd_l1 = (SOLVER == FMWR_SGD) && sp.l1;
+  const bool has_state = (SOLVER != FMWR_SGD) || sp.l1;
+  if (a.t_begin >= a.t_end) return;
+  if (tid < 8) sc[a.t_begin & 1][tid] = a.scal[tid];
 
-  for (int64_t t = a.t_begin; t < a.t_end; ++t) {
-    int64_t row;
-    if (a.order) row = a.order[t % a.order_len];
-    else if (a.skip_row0) row = 1 + (t % (a.n - 1));
-    else row = t % a.n;
-    const uint32_t b = a.rowptr[row], e = a.rowptr[row + 1];
-
-    // ---- pass A: S_f, sum Q, linear term (Model::predict, reference src/core/Model.h:75-103)
-    T S[CH][VN];
-    T qsum = T(0), lin = T(0);
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-      for (int i = 0; i < VN; ++i) S[ch][i] = T(0);
-    for (uint32_t j0 = b; j0 < e; j0 += SLOTS) {
-      const uint32_t j = j0 + slot;
-      if (j < e) {
-        const uint32_t c = a.col[j];
-        const T x = T(a.val[j]);
-        const V16* vr = reinterpret_cast<const V16*>(a.v + (size_t)c * kp);
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          T arr[VN];
-          vec_to_arr(vr[ch * LPR + l], arr);
-#pragma unroll
-          for (int i = 0; i < VN; ++i) {
-            const T tt = arr[i] * x;
-            S[ch][i] += tt;
-            qsum += tt * tt;
-          }
-        }
-        if (a.k1 && l == 0) lin += a.w[c] * x;
-      }
-    }
-    // slots of this warp -> lanes < LPR hold the warp's S
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-        for (int i = 0; i < VN; ++i) S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
-    const T part = warp_sum(lin - T(0.5) * qsum);
-    if (lane < LPR) {
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-        for (int i = 0; i < VN; ++i) sS[warp][(ch * LPR + l) * VN + i] = S[ch][i];
-    }
-    if (lane == 0) sPart[warp] = part;
-    __syncthreads();
-    if (warp == 0) {
-      T acc = T(0);
-      for (int f = lane; f < KP; f += 32) {
-        T sf = T(0);
-#pragma unroll
-        for (int w2 = 0; w2 < EX_WARPS; ++w2) sf += sS[w2][f];
-        sFin[f] = sf;
-        acc += T(0.5) * sf * sf;
-      }
-      if (lane < EX_WARPS) acc += sPart[lane];
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        sScore = (a.k0 ? T(sc[0]) : T(0)) + acc;
-        // SGD cumulative-L1 totals advance once per sample, before the updates (SGD_Learner.h:92-97)
-        if (sp.solver == FMWR_SGD && sp.l1) { sc[1] += (double)sp.lr * (double)sp.reg_w; sc[2] += (double)sp.lr * (double)sp.reg_v; }
-      }
-    }
-    __syncthreads();
-
-    // ---- multiplier (calculate_grad_mult)
-    const T yv = T(a.y[row]);
-    const T mult = grad_mult<T>(a.task, sScore, yv, T(a.lo), T(a.hi));
-    T Sf[CH][VN];
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-      for (int i = 0; i < VN; ++i) Sf[ch][i] = sFin[(ch * LPR + l) * VN + i];
-
-    const bool sgd_l1 = (sp.solver == FMWR_SGD) && sp.l1;
-    const T u_w = sgd_l1 ? T(sc[1]) : T(0), u_v = sgd_l1 ? T(sc[2]) : T(0);
-
-    // ---- pass B: coordinate updates
-    for (uint32_t j0 = b; j0 < e; j0 += SLOTS) {
-      const uint32_t j = j0 + slot;
-      if (j < e) {
-        const uint32_t c = a.col[j];
-        const T x = T(a.val[j]);
-        // linear weight
-        if (a.k1 && l == 0) {
-          const T g = mult * x;
-          T th = a.w[c];
-          if (sp.solver == FMWR_SGD) {
-            T q = sp.l1 ? a.sw[0][c] : T(0);
-            th = sgd_step(th, g, sp.lr, sp.reg_w, sp.l1, u_w, q);
-            if (sp.l1) a.sw[0][c] = q;
-            a.w[c] = th;
-          } else if (sp.solver == FMWR_FTRL) {
-            T z = a.sw[0][c], nn = a.sw[1][c];
-            th = ftrl_step(th, g, z, nn, sp.alpha_w, sp.beta_w, sp.l1_w, sp.l2_w);
-            a.sw[0][c] = z; a.sw[1][c] = nn;
-            a.w[c] = th;
-          } else {
-            T u = a.sw[0][c], nu = a.sw[1][c], dl = a.sw[2][c], h = a.sw[3][c];
-            const T z = tdap_state(th, g, u, nu, dl, h, sp.alpha_w, sp.egamma);
-            a.sw[0][c] = u; a.sw[1][c] = nu; a.sw[2][c] = dl; a.sw[3][c] = h;
-            if (!a.tdap_zw_index) a.w[c] = tdap_refresh(z, dl, sp.l1_w, sp.l2_w);
-          }
-        }
-        // factors
-        V16* vr = reinterpret_cast<V16*>(a.v + (size_t)c * kp);
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          const int vi = ch * LPR + l;
-          T th[VN];
-          vec_to_arr(vr[vi], th);
-          if (sp.solver == FMWR_SGD) {
-            T q[VN];
-            V16* qr = sp.l1 ? reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp) : nullptr;
-            if (sp.l1) vec_to_arr(qr[vi], q);
-#pragma unroll
-            for (int i = 0; i < VN; ++i) {
-              const T grad = fm_grad(Sf[ch][i], th[i], x);
-              T qq = sp.l1 ? q[i] : T(0);
-              th[i] = sgd_step(th[i], mult * grad, sp.lr, sp.reg_v, sp.l1, u_v, qq);
-              if (sp.l1) q[i] = qq;
-            }
-            if (sp.l1) qr[vi] = arr_to_vec(q);
-          } else if (sp.solver == FMWR_FTRL) {
-            V16* zr = reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp);
-            V16* nr = reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp);
-            T z[VN], nn[VN];
-            vec_to_arr(zr[vi], z); vec_to_arr(nr[vi], nn);
-#pragma unroll
-            for (int i = 0; i < VN; ++i) {
-              const T g = mult * fm_grad(Sf[ch][i], th[i], x);
-              th[i] = ftrl_step(th[i], g, z[i], nn[i], sp.alpha_v, sp.beta_v, sp.l1_v, sp.l2_v);
-            }
-            zr[vi] = arr_to_vec(z); nr[vi] = arr_to_vec(nn);
-          } else {
-            V16* ur = reinterpret_cast<V16*>(a.sv[0] + (size_t)c * kp);
-            V16* nur = reinterpret_cast<V16*>(a.sv[1] + (size_t)c * kp);
-            V16* dr = reinterpret_cast<V16*>(a.sv[2] + (size_t)c * kp);
-            V16* hr = reinterpret_cast<V16*>(a.sv[3] + (size_t)c * kp);
-            T u[VN], nu[VN], dl[VN], h[VN];
-            vec_to_arr(ur[vi], u); vec_to_arr(nur[vi], nu); vec_to_arr(dr[vi], dl); vec_to_arr(hr[vi], h);
-#pragma unroll
-            for (int i = 0; i < VN; ++i) {
-              const T g = mult * fm_grad(Sf[ch][i], th[i], x);
-              const T z = tdap_state(th[i], g, u[i], nu[i], dl[i], h[i], sp.alpha_v, sp.egamma);
-              th[i] = tdap_refresh(z, dl[i], sp.l1_v, sp.l2_v);
-            }
-            ur[vi] = arr_to_vec(u); nur[vi] = arr_to_vec(nu); dr[vi] = arr_to_vec(dl); hr[vi] = arr_to_vec(h);
-          }
-          vr[vi] = arr_to_vec(th);
-        }
-      }
-    }
-
-    // ---- scalars: w0 and its optimizer state (thread 0)
-    if (tid == 0) {
-      const double g = (double)mult;
-      if (sp.solver == FMWR_SGD) {
-        if (a.k0) sc[0] -= (double)sp.lr * (g + (double)sp.reg_w0 * sc[0]);       // SGD_Learner.h:106-109
-      } else if (sp.solver == FMWR_FTRL) {
-        if (a.k0) {                                                              // FTRL_Learner.h:80-86
-          const double old = sc[2];
-          sc[2] += g * g;
-          const double delta = (sqrt(sc[2]) - sqrt(old)) / (double)sp.alpha_w;
-          sc[1] += g - delta * sc[0];
-        }
-        sc[0] = -sc[1] * (double)sp.alpha_w / ((double)sp.beta_w + sqrt(sc[2]));  // :161, unconditional
-      } else {
-        if (a.k0) {                                                              // TDAP_Learner.h:96-105
-          const double old = sc[1];
-          sc[1] += g * g; sc[2] += g;
-          const double sigma = (sqrt(sc[1]) - sqrt(old)) / (double)sp.alpha_w;
-          sc[3] = (double)sp.egamma * (sc[3] + sigma);
-          sc[4] = (double)sp.egamma * (sc[4] + sigma * sc[0]);
-          sc[5] = sc[2] - sc[4];
-        }
-        sc[0] = -sc[5] / sc[3];                                                  // :192 (0/0 = NaN when keep.w0 is false)
-      }
-    }
-    __syncthreads();
-
-    // ---- F6: TDAP linear refresh reads z_w[position in row], not z_w[column] (TDAP_Learner.h:207)
-    if (sp.solver == FMWR_TDAP && a.tdap_zw_index && a.k1) {
-      for (uint32_t j0 = b; j0 < e; j0 += SLOTS) {
-        const uint32_t j = j0 + slot;
-        if (j < e && l == 0) {
-          const uint32_t c = a.col[j];
-          const uint32_t pos = j - b;                       // pos < nnz(row) <= p
-          const T z = a.sw[1][pos] - a.sw[3][pos];           // z_w[pos] = nu_w[pos] - h_w[pos]
-          a.w[c] = tdap_refresh(z, a.sw[2][c], sp.l1_w, sp.l2_w);
-        }
-      }
-      __syncthreads();
+  // ---- pipeline prologue: rings for the first samples
+  const int64_t period = a.order ? a.order_len : (a.skip_row0 ? a.n - 1 : a.n);
+  int64_t pos = 0;                          // visit cursor (pipeline warp, lane 0)
+  auto row_at = [&](int64_t q) -> uint32_t { return a.order ? a.order[q] : (uint32_t)(a.skip_row0 ? q + 1 : q); };
+  if (tid == W_PIPE * 32) {
+    pos = a.t_begin % period;
+    for (int i = 0; i < 4 && a.t_begin + i < a.t_end; ++i) {
+      rRow[(a.t_begin + i) & (RING - 1)] = row_at(pos);
+      if (++pos == period) pos = 0;
     }
   }
-  if (tid < 8) a.scal[tid] = sc[tid];
-  (void)SPW;
+  __syncthreads();
+  if (tid < 3 && a.t_begin + tid < a.t_end) {
+    const int s = (int)((a.t_begin + tid) & (RING - 1));
+    const uint32_t r = rRow[s];
+    rB[s] = a.rowptr[r]; rE[s] = a.rowptr[r + 1]; rY[s] = a.y[r];
+  }
+  __syncthreads();
+  for (int i = 0; i < 2; ++i) {
+    const int64_t s = a.t_begin + i;
+    if (s < a.t_end && tid < SLOTS) {
+      const uint32_t j = rB[s & (RING - 1)] + tid;
+      if (j < rE[s & (RING - 1)]) { rCol[s & (CRING - 1)][tid] = a.col[j]; rVal[s & (CRING - 1)][tid] = a.val[j]; }
+    }
+  }
+  __syncthreads();
+  // sqrt of the w0 accumulator (FTRL n, TDAP u) is carried between samples by its owner
+  double sq_acc = 0.0;
+  if (tid == W_PIPE * 32) sq_acc = sqrt(SOLVER == FMWR_FTRL ? sc[a.t_begin & 1][2] : sc[a.t_begin & 1][1]);
+
+  for (int64_t t = a.t_begin; t < a.t_end; ++t) {
+    double* const scur = sc[t & 1];
+    double* const snext = sc[(t + 1) & 1];
+    const uint32_t b = rB[t & (RING - 1)], e = rE[t & (RING - 1)];
+    const uint32_t nnz = e - b;
+    const T yv = T(rY[t & (RING - 1)]);
+    const uint32_t* const ccol = rCol[t & (CRING - 1)];
+    const float* const cval = rVal[t & (CRING - 1)];
+    const uint32_t used = min(nnz, (uint32_t)SLOTS);
+    const int nwA = (int)((used + SPW - 1) / SPW);      // factor warps holding entries
+
+    // S_f of this lane's vector(s), the score and the multiplier; identical arithmetic in every warp.
+    // Fully unrolled and predicated: the shared-memory reads issue back to back instead of one per loop trip.
+    T Sf[CH][VN];
+    auto compute_mult = [&](int ll) -> T {
+      T acc = T(0);
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+#pragma unroll
+        for (int i = 0; i < VN; ++i) Sf[ch][i] = T(0);
+#pragma unroll
+        for (int w2 = 0; w2 < EX_FW; ++w2)
+          if (w2 < nwA) {
+            T arr[VN];
+            vec_to_arr(sS[w2][ch * LPR + ll], arr);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) Sf[ch][i] += arr[i];
+          }
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc += T(0.5) * Sf[ch][i] * Sf[ch][i];
+      }
+#pragma unroll
+      for (int o = 1; o < LPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+#pragma unroll
+      for (int w2 = 0; w2 < EX_FW; ++w2)
+        if (w2 < nwA) acc += sPart[w2];
+      acc += sLin;
+      const T score = (a.k0 ? T(scur[0]) : T(0)) + acc;          // Model::predict, reference src/core/Model.h:75-103
+      // calculate_grad_mult
+      return FAST ? grad_mult_fast(a.task, score, yv, T(a.lo), T(a.hi)) : grad_mult<T>(a.task, score, yv, T(a.lo), T(a.hi));
+    };
+
+    if (warp < EX_FW) {
+      // =========================== factor warps ===========================
+      const bool act = warp < nwA;
+      const bool single = KEEP && nnz <= (uint32_t)SLOTS;
+      T kth[VN], kst[4][VN];
+      uint32_t c0 = 0; T x0 = T(0);
+      if (act) {
+        T S[CH][VN];
+        T qsum = T(0);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int i = 0; i < VN; ++i) S[ch][i] = T(0);
+        for (uint32_t j0 = b; j0 < e; j0 += SLOTS) {
+          const uint32_t j = j0 + slot;
+          if (j < e) {
+            uint32_t c; T x;
+            if (j0 == b) { c = ccol[slot]; x = T(cval[slot]); c0 = c; x0 = x; }
+            else { c = a.col[j]; x = T(a.val[j]); }
+            const size_t off = (size_t)c * kp;
+            const V16* vr = reinterpret_cast<const V16*>(a.v + off);
+            if (single && has_state) {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) vec_to_arr(reinterpret_cast<const V16*>(a.sv[s] + off)[l], kst[s]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+              T arr[VN];
+              vec_to_arr(vr[ch * LPR + l], arr);
+#pragma unroll
+              for (int i = 0; i < VN; ++i) {
+                const T tt = arr[i] * x;
+                S[ch][i] += tt;
+                qsum += tt * tt;
+                if (KEEP) kth[i] = arr[i];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
+        const T part = warp_sum(T(-0.5) * qsum);
+        if (lane < LPR) {
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) sS[warp][ch * LPR + l] = arr_to_vec(S[ch]);
+        }
+        if (lane == 0) sPart[warp] = part;
+      }
+      ex_bar();
+      if (act) {
+        const T mult = compute_mult(l);
+        const T u_v = sgd_l1 ? T(scur[2]) : T(0);
+        for (uint32_t j0 = b; j0 < e; j0 += SLOTS) {
+          const uint32_t j = j0 + slot;
+          if (j < e) {
+            uint32_t c; T x;
+            if (j0 == b) { c = c0; x = x0; } else { c = a.col[j]; x = T(a.val[j]); }
+            const size_t off = (size_t)c * kp;
+            V16* vr = reinterpret_cast<V16*>(a.v + off);
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+              const int vi = ch * LPR + l;
+              T th[VN], st[4][VN];
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int i = 0; i < VN; ++i) st[s][i] = T(0);
+              if (single) {
+#pragma unroll
+                for (int i = 0; i < VN; ++i) th[i] = kth[i];
+                if (has_state) {
+#pragma unroll
+                  for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int i = 0; i < VN; ++i) st[s][i] = kst[s][i];
+                }
+              } else {
+                vec_to_arr(vr[vi], th);
+                if (has_state) {
+#pragma unroll
+                  for (int s = 0; s < NS; ++s) vec_to_arr(reinterpret_cast<const V16*>(a.sv[s] + off)[vi], st[s]);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < VN; ++i) {
+                T s4[4] = {st[0][i], st[1][i], st[2][i], st[3][i]};
+                th[i] = exact_step<T, SOLVER, false, FAST>(th[i], mult * fm_grad(Sf[ch][i], th[i], x), s4, sp, u_v);
+                st[0][i] = s4[0]; st[1][i] = s4[1]; st[2][i] = s4[2]; st[3][i] = s4[3];
+              }
+              if (has_state) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) reinterpret_cast<V16*>(a.sv[s] + off)[vi] = arr_to_vec(st[s]);
+              }
+              vr[vi] = arr_to_vec(th);
+            }
+          }
+        }
+      }
+      ex_bar();
+    } else if (warp == W_LIN) {
+      // =========================== linear warp: lane = non-zero ===========================
+      const bool lsingle = nnz <= 32u * NL;      // all of the row's w_j (and state) stay in registers
+      uint32_t kc[NL]; T kx[NL], kw[NL], ksw[NL][4];
+      T lin = T(0);
+      auto entry = [&](uint32_t i, uint32_t& c, T& x) {
+        if (i < (uint32_t)SLOTS) { c = ccol[i]; x = T(cval[i]); } else { c = a.col[b + i]; x = T(a.val[b + i]); }
+      };
+      if (a.k1) {
+        if (lsingle) {
+#pragma unroll
+          for (int q = 0; q < NL; ++q) {
+            const uint32_t i = q * 32 + lane;
+            kc[q] = 0; kx[q] = T(0); kw[q] = T(0);
+            ksw[q][0] = ksw[q][1] = ksw[q][2] = ksw[q][3] = T(0);
+            if (i < nnz) {
+              entry(i, kc[q], kx[q]);
+              kw[q] = a.w[kc[q]];
+              if (has_state) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) ksw[q][s] = a.sw[s][kc[q]];
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < NL; ++q) lin += kw[q] * kx[q];
+        } else {
+          for (uint32_t i = lane; i < nnz; i += 32) {
+            uint32_t c; T x;
+            entry(i, c, x);
+            lin += a.w[c] * x;
+          }
+        }
+        lin = warp_sum(lin);
+      }
+      if (lane == 0) sLin = lin;
+      ex_bar();
+      const T mult = compute_mult(lane % LPR);
+      if (a.k1) {
+        const T u_w = sgd_l1 ? T(scur[1]) : T(0);
+        auto update = [&](uint32_t c, T x, T th, T (&st)[4]) {
+          const T g = mult * x;
+          bool store_w = true;
+          if (SOLVER == FMWR_TDAP && a.tdap_zw_index) {
+            (void)tdap_state<T, FAST>(th, g, st[0], st[1], st[2], st[3], sp.alpha_w, sp.egamma);   // refreshed below (F6)
+            store_w = false;
+          } else {
+            th = exact_step<T, SOLVER, true, FAST>(th, g, st, sp, u_w);
+          }
+          if (has_state) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) a.sw[s][c] = st[s];
+          }
+          if (store_w) a.w[c] = th;
+        };
+        if (lsingle) {
+#pragma unroll
+          for (int q = 0; q < NL; ++q)
+            if ((uint32_t)(q * 32 + lane) < nnz) update(kc[q], kx[q], kw[q], ksw[q]);
+        } else {
+          for (uint32_t i = lane; i < nnz; i += 32) {
+            uint32_t c; T x, st[4] = {T(0), T(0), T(0), T(0)};
+            entry(i, c, x);
+            const T th = a.w[c];
+            if (has_state) {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) st[s] = a.sw[s][c];
+            }
+            update(c, x, th, st);
+          }
+        }
+      }
+      ex_bar();
+      // F6: TDAP linear refresh reads z_w[position in row], not z_w[column] (TDAP_Learner.h:207)
+      if (SOLVER == FMWR_TDAP && a.tdap_zw_index && a.k1) {
+        for (uint32_t i = lane; i < nnz; i += 32) {     // i < nnz(row) <= p
+          const uint32_t c = a.col[b + i];
+          const T z = a.sw[1][i] - a.sw[3][i];          // z_w[pos] = nu_w[pos] - h_w[pos]
+          a.w[c] = tdap_refresh<T, FAST>(z, a.sw[2][c], sp.l1_w, sp.l2_w);
+        }
+      }
+    } else {
+      // =========================== pipeline warp ===========================
+      // SGD cumulative-L1 totals advance once per sample, before the updates (SGD_Learner.h:92-97)
+      if (lane == 0 && sgd_l1) { scur[1] += (double)sp.lr * (double)sp.reg_w; scur[2] += (double)sp.lr * (double)sp.reg_v; }
+      uint32_t pa_row = 0, pb_b = 0, pb_e = 0, pc_col[NC];
+      float pb_y = 0.f, pc_val[NC];
+      if (lane == 0 && t + 4 < a.t_end) { pa_row = row_at(pos); if (++pos == period) pos = 0; }
+      if (lane == 1 && t + 3 < a.t_end) {
+        const uint32_t r = rRow[(t + 3) & (RING - 1)];
+        pb_b = a.rowptr[r]; pb_e = a.rowptr[r + 1]; pb_y = a.y[r];
+      }
+      if (t + 2 < a.t_end) {
+        const uint32_t b2 = rB[(t + 2) & (RING - 1)], e2 = rE[(t + 2) & (RING - 1)];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          const uint32_t idx = q * 32 + lane, j = b2 + idx;
+          pc_col[q] = 0; pc_val[q] = 0.f;
+          if (idx < (uint32_t)SLOTS && j < e2) { pc_col[q] = a.col[j]; pc_val[q] = a.val[j]; }
+        }
+      }
+      if (a.prefetch && t + 1 < a.t_end) {
+        const uint32_t n1 = min(rE[(t + 1) & (RING - 1)] - rB[(t + 1) & (RING - 1)], (uint32_t)SLOTS);
+        for (uint32_t i = lane; i < n1; i += 32) {
+          const uint32_t c = rCol[(t + 1) & (CRING - 1)][i];
+          const size_t off = (size_t)c * kp;
+          for (int q = 0; q < kp; q += LINE) {
+            prefetch_l2(a.v + off + q);
+            if (has_state) {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) prefetch_l2(a.sv[s] + off + q);
+            }
+          }
+          if (a.k1) {
+            prefetch_l2(a.w + c);
+            if (has_state) {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) prefetch_l2(a.sw[s] + c);
+            }
+          }
+        }
+      }
+      ex_bar();
+      const T mult = compute_mult(lane % LPR);
+      if (lane == 0) {
+        // scalars: w0 and its optimizer state, written to the other parity
+        const double g = (double)mult;
+        double s0 = scur[0], s1 = scur[1], s2 = scur[2], s3 = scur[3], s4 = scur[4], s5 = scur[5];
+        if (SOLVER == FMWR_SGD) {
+          if (a.k0) s0 -= (double)sp.lr * (g + (double)sp.reg_w0 * s0);           // SGD_Learner.h:106-109
+        } else if (SOLVER == FMWR_FTRL) {
+          if (a.k0) {                                                            // FTRL_Learner.h:80-86
+            s2 += g * g;
+            const double sq = sqrt(s2);
+            const double delta = (sq - sq_acc) / (double)sp.alpha_w;
+            sq_acc = sq;
+            s1 += g - delta * s0;
+          }
+          s0 = -s1 * (double)sp.alpha_w / ((double)sp.beta_w + sq_acc);           // :161, unconditional
+        } else {
+          if (a.k0) {                                                            // TDAP_Learner.h:96-105
+            s1 += g * g; s2 += g;
+            const double sq = sqrt(s1);
+            const double sigma = (sq - sq_acc) / (double)sp.alpha_w;
+            sq_acc = sq;
+            s3 = (double)sp.egamma * (s3 + sigma);
+            s4 = (double)sp.egamma * (s4 + sigma * s0);
+            s5 = s2 - s4;
+          }
+          s0 = -s5 / s3;                                                         // :192 (0/0 = NaN when keep.w0 is false)
+        }
+        snext[0] = s0; snext[1] = s1; snext[2] = s2; snext[3] = s3; snext[4] = s4; snext[5] = s5;
+        snext[6] = scur[6]; snext[7] = scur[7];
+      }
+      // run-ahead results into the rings
+      if (lane == 0 && t + 4 < a.t_end) rRow[(t + 4) & (RING - 1)] = pa_row;
+      if (lane == 1 && t + 3 < a.t_end) { rB[(t + 3) & (RING - 1)] = pb_b; rE[(t + 3) & (RING - 1)] = pb_e; rY[(t + 3) & (RING - 1)] = pb_y; }
+      if (t + 2 < a.t_end) {
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          const uint32_t idx = q * 32 + lane;
+          if (idx < (uint32_t)SLOTS) { rCol[(t + 2) & (CRING - 1)][idx] = pc_col[q]; rVal[(t + 2) & (CRING - 1)][idx] = pc_val[q]; }
+        }
+      }
+      ex_bar();
+    }
+    if (SOLVER == FMWR_TDAP && a.tdap_zw_index && a.k1) ex_bar();   // F6 refresh done before the next forward
+  }
+  if (tid < 8) a.scal[tid] = sc[a.t_end & 1][tid];
 }
 
-template <class T>
+template <class T, int SOLVER>
 struct ExactLaunch {
   fmwr_ctx* ctx; ExactArgs<T> args;
   template <class TT, int LPR, int CH>
-  void run() { FMWR_LAUNCH(ctx, (exact_kernel<TT, LPR, CH>), 1, EX_THREADS, 0, args); }
+  void run() { FMWR_LAUNCH(ctx, (exact_kernel<TT, LPR, CH, SOLVER>), 1, EX_THREADS, 0, args); }
 };
 
 template <class T>
@@ -347,6 +541,7 @@ static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr
   a.tdap_zw_index = (s->compat & FMWR_COMPAT_TDAP_ZW_INDEX) ? 1 : 0;
   a.sp = make_params<T>(m, s);
   a.lo = s->min_target; a.hi = s->max_target;
+  { const char* pf = std::getenv("FMWR_EXACT_PREFETCH"); a.prefetch = (pf && pf[0] == '0') ? 0 : 1; }
 
   // visit order.  random_step == 1: the reference scans i = 1 .. n-1 (F5).  random_step > 1: strides of
   // 1 + floor(U * random_step) from glibc rand() (reference src/util/Random.h:126-132); the caller may pass
@@ -388,8 +583,9 @@ static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr
       next = std::min<int64_t>(cand, max_iter);
     }
     a.t_begin = iter; a.t_end = next;
-    ExactLaunch<T> L{ctx, a};
-    dispatch_layout<T>(m->kp, L);
+    if (s->solver == FMWR_SGD) { ExactLaunch<T, FMWR_SGD> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
+    else if (s->solver == FMWR_FTRL) { ExactLaunch<T, FMWR_FTRL> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
+    else { ExactLaunch<T, FMWR_TDAP> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
     iter = next;
     if (step > 0) {
       const int64_t last = iter - 1;     // index of the sample just processed

@@ -21,7 +21,8 @@
 //     the other warps still read it).  The CSR arrays are read-only and L2 is the coherence point,
 //     so running ahead cannot observe stale data.
 // Rows that fit one round (nnz <= SLOTS) read theta and its state once, with the forward gather,
-// and keep them in registers for the update.  Two barriers per sample.
+// and keep them in registers for the update.  Three barriers per sample: partials ready, S_f and the
+// multiplier published (summed by the pipeline warp alone), updates done.
 // fp32 FTRL/TDAP use the branch-free MUFU sqrt/rcp forms (<= 2 ulp, the same order as fp32 rounding
 // itself; lets the four elements of a vector interleave); fp64 keeps IEEE operations throughout.
 #include "forward.cuh"
@@ -92,6 +93,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   __shared__ V16 sS[EX_FW][LPR * CH];
   __shared__ T sPart[EX_FW];
   __shared__ T sLin;
+  __shared__ V16 sSf[LPR * CH];             // S_f of the sample, summed over the factor warps by the pipeline warp
+  __shared__ T sMult;
   __shared__ double sc[2][8];               // w0 and the scalar optimizer state, by sample parity
   __shared__ uint32_t rRow[RING], rB[RING], rE[RING];
   __shared__ float rY[RING];
@@ -148,35 +151,27 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
     const uint32_t used = min(nnz, (uint32_t)SLOTS);
     const int nwA = (int)((used + SPW - 1) / SPW);      // factor warps holding entries
 
-    // S_f of this lane's vector(s), the score and the multiplier; identical arithmetic in every warp.
-    // Fully unrolled and predicated: the shared-memory reads issue back to back instead of one per loop trip.
-    T Sf[CH][VN];
-    auto compute_mult = [&](int ll) -> T {
+    // pipeline warp, between the two mid-sample barriers: S_f over the factor warps (lane = factor), the score
+    // and the multiplier, published through shared memory -- one warp's ~60 instructions instead of every warp's
+    auto reduce_mult = [&]() -> T {
       T acc = T(0);
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-#pragma unroll
-        for (int i = 0; i < VN; ++i) Sf[ch][i] = T(0);
+      T* const sf_out = reinterpret_cast<T*>(sSf);
+      for (int f = lane; f < LPR * CH * VN; f += 32) {
+        T sf = T(0);
 #pragma unroll
         for (int w2 = 0; w2 < EX_FW; ++w2)
-          if (w2 < nwA) {
-            T arr[VN];
-            vec_to_arr(sS[w2][ch * LPR + ll], arr);
-#pragma unroll
-            for (int i = 0; i < VN; ++i) Sf[ch][i] += arr[i];
-          }
-#pragma unroll
-        for (int i = 0; i < VN; ++i) acc += T(0.5) * Sf[ch][i] * Sf[ch][i];
+          if (w2 < nwA) sf += reinterpret_cast<const T*>(sS[w2])[f];
+        sf_out[f] = sf;
+        acc += T(0.5) * sf * sf;
       }
-#pragma unroll
-      for (int o = 1; o < LPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-#pragma unroll
-      for (int w2 = 0; w2 < EX_FW; ++w2)
-        if (w2 < nwA) acc += sPart[w2];
+      if (lane < nwA) acc += sPart[lane];
+      acc = warp_sum(acc);
       acc += sLin;
       const T score = (a.k0 ? T(scur[0]) : T(0)) + acc;          // Model::predict, reference src/core/Model.h:75-103
       // calculate_grad_mult
-      return FAST ? grad_mult_fast(a.task, score, yv, T(a.lo), T(a.hi)) : grad_mult<T>(a.task, score, yv, T(a.lo), T(a.hi));
+      const T mult = FAST ? grad_mult_fast(a.task, score, yv, T(a.lo), T(a.hi)) : grad_mult<T>(a.task, score, yv, T(a.lo), T(a.hi));
+      if (lane == 0) sMult = mult;
+      return mult;
     };
 
     if (warp < EX_FW) {
@@ -232,8 +227,12 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
         if (lane == 0) sPart[warp] = part;
       }
       ex_bar();
+      ex_bar();
       if (act) {
-        const T mult = compute_mult(l);
+        const T mult = sMult;
+        T Sf[CH][VN];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) vec_to_arr(sSf[ch * LPR + l], Sf[ch]);
         const T u_v = sgd_l1 ? T(scur[2]) : T(0);
         for (uint32_t j0 = b; j0 < e; j0 += SLOTS) {
           const uint32_t j = j0 + slot;
@@ -319,7 +318,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
       }
       if (lane == 0) sLin = lin;
       ex_bar();
-      const T mult = compute_mult(lane % LPR);
+      ex_bar();
+      const T mult = sMult;
       if (a.k1) {
         const T u_w = sgd_l1 ? T(scur[1]) : T(0);
         auto update = [&](uint32_t c, T x, T th, T (&st)[4]) {
@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
         }
       }
       ex_bar();
-      const T mult = compute_mult(lane % LPR);
+      const T mult = reduce_mult();
+      ex_bar();
       if (lane == 0) {
         // scalars: w0 and its optimizer state, written to the other parity
         const double g = (double)mult;

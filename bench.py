@@ -294,6 +294,25 @@ def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B):
         out[name] = {"workload": "configs[1] matrix, %s minibatch epoch (batch %d)" % (name.upper(), B), "value": round(sps, 1), "unit": "samples/s",
                      "ms_per_step": round(ms, 3), "alg_bytes_per_sample": b, "achieved_gbs": round(sps * b / 1e9, 1), "frac": round(sps * b / 1e9 / peak, 4)}
         m.close()
+    # exact mode (batch = 1, the reference's own sample order and arithmetic): one persistent CTA, latency-bound by
+    # construction (every sample reads w0 written by the previous one), so it is reported in samples/s on a bounded
+    # sample of the same matrix, next to the reference's single-thread rate in cpu_baseline -- no HBM fraction.
+    it = int(min(n - 1, 200_000))
+    ex = {}
+    for name, solver in (("sgd", L.SGD), ("ftrl", L.FTRL), ("tdap", L.TDAP)):
+        mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+        m = L.Model(ctx, mc, p, L.F32)
+        m.init_random(0.0, 0.01, 20240603)
+        sc = L.SolverCfg(solver=solver, max_iter=it, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                         gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_EXACT, batch_size=1, precision=L.F32,
+                         compat=L.COMPAT_REFERENCE, step_size=-1)
+        L.train_dev(ctx, m, data, sc)
+        ctx.sync(); ctx.timer_start()
+        L.train_dev(ctx, m, data, sc)
+        ms = ctx.timer_stop_ms()
+        ex[name] = {"value": round(it / (ms * 1e-3), 1), "unit": "samples/s", "us_per_sample": round(ms * 1e3 / it, 3)}
+        m.close()
+    out["exact"] = {"workload": "configs[1] matrix, batch=1 reference-order updates, first %d samples, fp32" % it, **ex}
     if args.rows < 1_000_000:
         return out                                  # reduced smoke runs: skip the 20M-rating sweeps
     na = 20_000_000

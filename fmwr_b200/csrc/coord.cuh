@@ -52,8 +52,9 @@ __device__ __forceinline__ T sgd_step(T theta, T g, T lr, T reg, int l1, T u, T&
 }
 
 // Throughput-mode arithmetic: MUFU approximations (sqrt.approx / rcp.approx, <= 2 ulp) instead of the IEEE
-// sequences (~10 instructions each) -- the minibatch update kernel is issue-bound on them.  FAST is only ever
-// set for the fp32 minibatch kernels; the exact (batch = 1) kernels and every fp64 instantiation keep IEEE ops.
+// sequences (~10 instructions each, and each ends a basic block) -- the minibatch update kernel is issue-bound on
+// them and the exact (batch = 1) kernel serialises a vector's elements behind them.  FAST is only ever set for
+// fp32 FTRL / TDAP kernels; SGD has no sqrt / div, and every fp64 instantiation keeps IEEE operations.
 template <bool FAST> __device__ __forceinline__ float m_sqrt(float x)
 {
   if (FAST) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

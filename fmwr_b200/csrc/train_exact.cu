@@ -140,7 +140,17 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   double sq_acc = 0.0;
   if (tid == W_PIPE * 32) sq_acc = sqrt(SOLVER == FMWR_FTRL ? sc[a.t_begin & 1][2] : sc[a.t_begin & 1][1]);
 
+#ifdef FMWR_EXACT_PROF
+  // per-role timeline (cycles per sample); a barrier's wait shows up in the section AFTER it (deferred blocking)
+  long long pt[4] = {0, 0, 0, 0};
+#define PROF(i) { const long long c_ = clock64(); pt[i] += c_ - p0; p0 = c_; }
+#else
+#define PROF(i)
+#endif
   for (int64_t t = a.t_begin; t < a.t_end; ++t) {
+#ifdef FMWR_EXACT_PROF
+    long long p0 = clock64();
+#endif
     double* const scur = sc[t & 1];
     double* const snext = sc[(t + 1) & 1];
     const uint32_t b = rB[t & (RING - 1)], e = rE[t & (RING - 1)];
@@ -219,6 +229,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
             for (int i = 0; i < VN; ++i) S[ch][i] += __shfl_xor_sync(0xffffffffu, S[ch][i], o);
+        PROF(0)
         const T part = warp_sum(T(-0.5) * qsum);
         if (lane < LPR) {
 #pragma unroll
@@ -226,10 +237,12 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
         }
         if (lane == 0) sPart[warp] = part;
       }
+      PROF(1)
       ex_bar();
       ex_bar();
       if (act) {
         const T mult = sMult;
+        PROF(2)
         T Sf[CH][VN];
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) vec_to_arr(sSf[ch * LPR + l], Sf[ch]);
@@ -280,6 +293,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           }
         }
       }
+      PROF(3)
       ex_bar();
     } else if (warp == W_LIN) {
       // =========================== linear warp: lane = non-zero ===========================
@@ -317,9 +331,11 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
         lin = warp_sum(lin);
       }
       if (lane == 0) sLin = lin;
+      PROF(1)
       ex_bar();
       ex_bar();
       const T mult = sMult;
+      PROF(2)
       if (a.k1) {
         const T u_w = sgd_l1 ? T(scur[1]) : T(0);
         auto update = [&](uint32_t c, T x, T th, T (&st)[4]) {
@@ -354,15 +370,29 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           }
         }
       }
-      ex_bar();
-      // F6: TDAP linear refresh reads z_w[position in row], not z_w[column] (TDAP_Learner.h:207)
+      // F6: TDAP linear refresh reads z_w[position in row], not z_w[column] (TDAP_Learner.h:207).  nu_w / h_w / w are
+      // written by this warp only, so a warp-level sync orders the refresh after the state updates above.
       if (SOLVER == FMWR_TDAP && a.tdap_zw_index && a.k1) {
-        for (uint32_t i = lane; i < nnz; i += 32) {     // i < nnz(row) <= p
-          const uint32_t c = a.col[b + i];
-          const T z = a.sw[1][i] - a.sw[3][i];          // z_w[pos] = nu_w[pos] - h_w[pos]
-          a.w[c] = tdap_refresh<T, FAST>(z, a.sw[2][c], sp.l1_w, sp.l2_w);
+        __syncwarp();
+        if (lsingle) {                                  // column and the fresh delta_w[column] are still in registers
+#pragma unroll
+          for (int q = 0; q < NL; ++q) {
+            const uint32_t i = q * 32 + lane;           // i < nnz(row) <= p
+            if (i < nnz) {
+              const T z = a.sw[1][i] - a.sw[3][i];        // z_w[pos] = nu_w[pos] - h_w[pos]
+              a.w[kc[q]] = tdap_refresh<T, FAST>(z, ksw[q][2], sp.l1_w, sp.l2_w);
+            }
+          }
+        } else {
+          for (uint32_t i = lane; i < nnz; i += 32) {
+            const uint32_t c = a.col[b + i];
+            const T z = a.sw[1][i] - a.sw[3][i];
+            a.w[c] = tdap_refresh<T, FAST>(z, a.sw[2][c], sp.l1_w, sp.l2_w);
+          }
         }
       }
+      PROF(3)
+      ex_bar();
     } else {
       // =========================== pipeline warp ===========================
       // SGD cumulative-L1 totals advance once per sample, before the updates (SGD_Learner.h:92-97)
@@ -404,8 +434,10 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           }
         }
       }
+      PROF(1)
       ex_bar();
       const T mult = reduce_mult();
+      PROF(2)
       ex_bar();
       if (lane == 0) {
         // scalars: w0 and its optimizer state, written to the other parity
@@ -447,10 +479,17 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           if (idx < (uint32_t)SLOTS) { rCol[(t + 2) & (CRING - 1)][idx] = pc_col[q]; rVal[(t + 2) & (CRING - 1)][idx] = pc_val[q]; }
         }
       }
+      PROF(3)
       ex_bar();
     }
-    if (SOLVER == FMWR_TDAP && a.tdap_zw_index && a.k1) ex_bar();   // F6 refresh done before the next forward
   }
+#ifdef FMWR_EXACT_PROF
+  if (lane == 0 && (warp == 0 || warp >= EX_FW)) {
+    const long long N = a.t_end - a.t_begin;
+    printf("exact prof %s: gather %lld reduce %lld [bar] mult %lld update %lld [bar]\n",
+           warp == 0 ? "factor warp 0" : (warp == W_LIN ? "linear warp  " : "pipeline warp"), pt[0] / N, pt[1] / N, pt[2] / N, pt[3] / N);
+  }
+#endif
   if (tid < 8) a.scal[tid] = sc[a.t_end & 1][tid];
 }
 

@@ -99,6 +99,27 @@ def test_exact_wide_rows_and_large_k(gpu_ctx, port, solver):
     assert relerr(gw0, rw0) < 1e-9 and relerr(gw, rw) < 1e-9 and relerr(gv, rv) < 1e-9
 
 
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL, O.TDAP])
+@pytest.mark.parametrize("k,max_nnz,prec", [(4, 70, "f64"), (128, 45, "f64"), (32, 100, "f32"), (128, 45, "f32")])
+def test_exact_row_shapes_and_layouts(gpu_ctx, port, solver, k, max_nnz, prec):
+    # ragged rows from empty to wider than the shared-memory ring (64) and than the factor warps' slot count
+    # (56 at k=32 fp32, 14 at k=128 fp32, 7 at k=128 fp64): every gather/update path of the kernel -- registers kept,
+    # second round from global memory, the linear warp's two-per-lane and looped forms, TDAP's position refresh (F6)
+    rng = np.random.default_rng(11)
+    n, p = 90, 300
+    rowptr, col, val = synth.random_csr(n, p, max_nnz, seed=21, empty_rows=True)
+    ds = dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.05, p); v = rng.normal(0, 0.05, (p, k)); w0 = 0.1
+    iters = 2 * (n - 1) + 7
+    regs = dict(l1_w=0.001, l2_w=0.001, l2_v=0.002)
+    cfg = O.make_cfg(solver=solver, k=k, max_iter=iters, **regs)
+    rw0, rw, rv, _ = port.train(cfg, n, p, rowptr, col, val, y, w0, w, v)
+    (gw0, gw, gv), _ = gpu_train(gpu_ctx, L.F64 if prec == "f64" else L.F32, ds, y, L.CLASSIFICATION, SOLV[solver], k, w0, w, v, iters, regs)
+    tol = 1e-9 if prec == "f64" else (5e-2 if solver == O.TDAP else 1e-4)
+    assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol
+
+
 def test_exact_tracker_and_convergence(gpu_ctx, port):
     rng = np.random.default_rng(5)
     ds = small(n=300, p=40, seed=6)

@@ -15,7 +15,7 @@
 //     vector l of that feature's factor row; warps without a non-zero only hit the barriers;
 //   * the linear warp: lane = non-zero (two per lane in registers), owns w_j and its state;
 //   * the pipeline warp: runs ahead of the sample being processed -- visit index (t+4), row bounds
-//     and label (t+3), the row's first SLOTS column/value entries (t+2) into shared-memory rings,
+//     and label (t+3), the row's first column/value entries (t+2) into shared-memory rings,
 //     and an L2 prefetch of every parameter / state line sample t+1 will touch -- and owns w0 and
 //     the scalar optimizer state (fp64, double-buffered by sample parity so it is updated while
 //     the other warps still read it).  The CSR arrays are read-only and L2 is the coherence point,
@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   constexpr bool KEEP = (CH == 1);          // registers for theta + state only at one vector per lane
   constexpr bool FAST = (sizeof(T) == 4) && (SOLVER != FMWR_SGD);
   constexpr int RING = 8, CRING = 4;
-  constexpr int NC = (SLOTS + 31) / 32;     // ring entries per pipeline lane
+  constexpr int RN = SLOTS > 32 * EX_NL ? SLOTS : 32 * EX_NL;   // non-zeros of a row staged in the shared-memory ring
+  constexpr int NC = (RN + 31) / 32;        // ring entries per pipeline lane
   constexpr int NL = EX_NL;
   constexpr int W_PIPE = EX_FW, W_LIN = EX_FW + 1;
   constexpr int LINE = 128 / (int)sizeof(T);
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   __shared__ double sc[2][8];               // w0 and the scalar optimizer state, by sample parity
   __shared__ uint32_t rRow[RING], rB[RING], rE[RING];
   __shared__ float rY[RING];
-  __shared__ uint32_t rCol[CRING][SLOTS];
-  __shared__ float rVal[CRING][SLOTS];
+  __shared__ uint32_t rCol[CRING][RN];
+  __shared__ float rVal[CRING][RN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = tid / LPR, l = tid % LPR;          // factor warps only
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   __syncthreads();
   for (int i = 0; i < 2; ++i) {
     const int64_t s = a.t_begin + i;
-    if (s < a.t_end && tid < SLOTS) {
+    if (s < a.t_end && tid < RN) {
       const uint32_t j = rB[s & (RING - 1)] + tid;
       if (j < rE[s & (RING - 1)]) { rCol[s & (CRING - 1)][tid] = a.col[j]; rVal[s & (CRING - 1)][tid] = a.val[j]; }
     }
@@ -301,22 +302,28 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
       uint32_t kc[NL]; T kx[NL], kw[NL], ksw[NL][4];
       T lin = T(0);
       auto entry = [&](uint32_t i, uint32_t& c, T& x) {
-        if (i < (uint32_t)SLOTS) { c = ccol[i]; x = T(cval[i]); } else { c = a.col[b + i]; x = T(a.val[b + i]); }
+        if (i < (uint32_t)RN) { c = ccol[i]; x = T(cval[i]); } else { c = a.col[b + i]; x = T(a.val[b + i]); }
       };
       if (a.k1) {
         if (lsingle) {
+          // branch-free on purpose: all shared-memory reads, then all global reads.  With a branch per non-zero the
+          // second non-zero's address arithmetic waited on the scoreboard of the first one's loads (ncu source page:
+          // two serialised DRAM round trips); lanes past the row's end read element 0 and are masked by x = 0.
 #pragma unroll
           for (int q = 0; q < NL; ++q) {
-            const uint32_t i = q * 32 + lane;
-            kc[q] = 0; kx[q] = T(0); kw[q] = T(0);
+            const uint32_t i = q * 32 + lane;            // < 32 * NL <= RN
+            const bool ok = i < nnz;
+            const uint32_t c = ccol[i];
+            const T x = T(cval[i]);
+            kc[q] = ok ? c : 0u; kx[q] = ok ? x : T(0);
             ksw[q][0] = ksw[q][1] = ksw[q][2] = ksw[q][3] = T(0);
-            if (i < nnz) {
-              entry(i, kc[q], kx[q]);
-              kw[q] = a.w[kc[q]];
-              if (has_state) {
+          }
 #pragma unroll
-                for (int s = 0; s < NS; ++s) ksw[q][s] = a.sw[s][kc[q]];
-              }
+          for (int q = 0; q < NL; ++q) {
+            kw[q] = a.w[kc[q]];
+            if (has_state) {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) ksw[q][s] = a.sw[s][kc[q]];
             }
           }
 #pragma unroll
@@ -410,11 +417,11 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
         for (int q = 0; q < NC; ++q) {
           const uint32_t idx = q * 32 + lane, j = b2 + idx;
           pc_col[q] = 0; pc_val[q] = 0.f;
-          if (idx < (uint32_t)SLOTS && j < e2) { pc_col[q] = a.col[j]; pc_val[q] = a.val[j]; }
+          if (idx < (uint32_t)RN && j < e2) { pc_col[q] = a.col[j]; pc_val[q] = a.val[j]; }
         }
       }
       if (a.prefetch && t + 1 < a.t_end) {
-        const uint32_t n1 = min(rE[(t + 1) & (RING - 1)] - rB[(t + 1) & (RING - 1)], (uint32_t)SLOTS);
+        const uint32_t n1 = min(rE[(t + 1) & (RING - 1)] - rB[(t + 1) & (RING - 1)], (uint32_t)RN);
         for (uint32_t i = lane; i < n1; i += 32) {
           const uint32_t c = rCol[(t + 1) & (CRING - 1)][i];
           const size_t off = (size_t)c * kp;
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
           const uint32_t idx = q * 32 + lane;
-          if (idx < (uint32_t)SLOTS) { rCol[(t + 2) & (CRING - 1)][idx] = pc_col[q]; rVal[(t + 2) & (CRING - 1)][idx] = pc_val[q]; }
+          if (idx < (uint32_t)RN) { rCol[(t + 2) & (CRING - 1)][idx] = pc_col[q]; rVal[(t + 2) & (CRING - 1)][idx] = pc_val[q]; }
         }
       }
       PROF(3)

@@ -65,7 +65,9 @@ template <bool FAST> __device__ __forceinline__ float m_div(float a, float b) { 
 template <bool FAST> __device__ __forceinline__ double m_div(double a, double b) { return a / b; }
 
 // FTRL-Proximal: state (z, n) in/out, returns refreshed theta
-template <class T, bool FAST = false>
+// SEL: compute the closed form unconditionally and select (same value; no branch, so the elements of a vector
+// interleave in the latency-bound exact kernel)
+template <class T, bool FAST = false, bool SEL = false>
 __device__ __forceinline__ T ftrl_step(T theta, T g, T& z, T& n, T alpha, T beta, T l1, T l2)
 {
   const T n_old = n;
@@ -73,9 +75,10 @@ __device__ __forceinline__ T ftrl_step(T theta, T g, T& z, T& n, T alpha, T beta
   const T sq = m_sqrt<FAST>(n);
   const T sigma = m_div<FAST>(sq - m_sqrt<FAST>(n_old), alpha);
   z += g - sigma * theta;
-  if (fabs(z) <= l1) return T(0);
+  if (!SEL && fabs(z) <= l1) return T(0);
   const T sign = z < T(0) ? T(-1) : T(1);
-  return -m_div<FAST>(z - sign * l1, m_div<FAST>(beta + sq, alpha) + l2);
+  const T r = -m_div<FAST>(z - sign * l1, m_div<FAST>(beta + sq, alpha) + l2);
+  return (SEL && fabs(z) <= l1) ? T(0) : r;
 }
 
 // TDAP state update: (u, nu, delta, h) in/out; returns z = nu - h
@@ -91,12 +94,13 @@ __device__ __forceinline__ T tdap_state(T theta, T g, T& u, T& nu, T& delta, T& 
   return nu - h;
 }
 
-template <class T, bool FAST = false>
+template <class T, bool FAST = false, bool SEL = false>
 __device__ __forceinline__ T tdap_refresh(T z, T delta, T l1, T l2)
 {
-  if (fabs(z) <= l1) return T(0);
+  if (!SEL && fabs(z) <= l1) return T(0);
   const T sign = z < T(0) ? T(-1) : T(1);
-  return -m_div<FAST>(z - sign * l1, delta + l2);
+  const T r = -m_div<FAST>(z - sign * l1, delta + l2);
+  return (SEL && fabs(z) <= l1) ? T(0) : r;
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -69,10 +69,10 @@ __device__ __forceinline__ T exact_step(T th, T g, T (&st)[4], const SolverParam
     return th;
   }
   if (SOLVER == FMWR_FTRL)
-    return ftrl_step<T, FAST>(th, g, st[0], st[1], LIN ? sp.alpha_w : sp.alpha_v, LIN ? sp.beta_w : sp.beta_v,
-                              LIN ? sp.l1_w : sp.l1_v, LIN ? sp.l2_w : sp.l2_v);
+    return ftrl_step<T, FAST, FAST>(th, g, st[0], st[1], LIN ? sp.alpha_w : sp.alpha_v, LIN ? sp.beta_w : sp.beta_v,
+                                    LIN ? sp.l1_w : sp.l1_v, LIN ? sp.l2_w : sp.l2_v);
   const T z = tdap_state<T, FAST>(th, g, st[0], st[1], st[2], st[3], LIN ? sp.alpha_w : sp.alpha_v, sp.egamma);
-  return tdap_refresh<T, FAST>(z, st[2], LIN ? sp.l1_w : sp.l1_v, LIN ? sp.l2_w : sp.l2_v);
+  return tdap_refresh<T, FAST, FAST>(z, st[2], LIN ? sp.l1_w : sp.l1_v, LIN ? sp.l2_w : sp.l2_v);
 }
 
 template <class T, int LPR, int CH, int SOLVER>
@@ -139,6 +139,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   __syncthreads();
   // sqrt of the w0 accumulator (FTRL n, TDAP u) is carried between samples by its owner
   double sq_acc = 0.0;
+  // fp32 models: the w0 state stays fp64 but its one constant divisor becomes a multiplication (a 1-ulp fp64 change,
+  // nine digits below the fp32 parameters); fp64 models keep the reference's division
+  const double inv_alpha_w = 1.0 / (double)sp.alpha_w;
   if (tid == W_PIPE * 32) sq_acc = sqrt(SOLVER == FMWR_FTRL ? sc[a.t_begin & 1][2] : sc[a.t_begin & 1][1]);
 
 #ifdef FMWR_EXACT_PROF
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           if (a.k0) {                                                            // FTRL_Learner.h:80-86
             s2 += g * g;
             const double sq = sqrt(s2);
-            const double delta = (sq - sq_acc) / (double)sp.alpha_w;
+            const double delta = sizeof(T) == 4 ? (sq - sq_acc) * inv_alpha_w : (sq - sq_acc) / (double)sp.alpha_w;
             sq_acc = sq;
             s1 += g - delta * s0;
           }
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
           if (a.k0) {                                                            // TDAP_Learner.h:96-105
             s1 += g * g; s2 += g;
             const double sq = sqrt(s1);
-            const double sigma = (sq - sq_acc) / (double)sp.alpha_w;
+            const double sigma = sizeof(T) == 4 ? (sq - sq_acc) * inv_alpha_w : (sq - sq_acc) / (double)sp.alpha_w;
             sq_acc = sq;
             s3 = (double)sp.egamma * (s3 + sigma);
             s4 = (double)sp.egamma * (s4 + sigma * s0);

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   constexpr int SPW = 32 / LPR;             // slots per factor warp
   constexpr int NS = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);   // state arrays (SGD: only with L1)
   constexpr bool KEEP = (CH == 1);          // registers for theta + state only at one vector per lane
-  constexpr bool FAST = (sizeof(T) == 4) && (SOLVER != FMWR_SGD);
+  constexpr bool FAST = sizeof(T) == 4;     // fp32: MUFU exp / sqrt / rcp (SGD only has the multiplier's exp and rcp)
   constexpr int RING = 8, CRING = 4;
   constexpr int RN = SLOTS > 32 * EX_NL ? SLOTS : 32 * EX_NL;   // non-zeros of a row staged in the shared-memory ring
   constexpr int NC = (RN + 31) / 32;        // ring entries per pipeline lane

@@ -23,7 +23,7 @@
 // Rows that fit one round (nnz <= SLOTS) read theta and its state once, with the forward gather,
 // and keep them in registers for the update.  Three barriers per sample: partials ready, S_f and the
 // multiplier published (summed by the pipeline warp alone), updates done.
-// fp32 FTRL/TDAP use the branch-free MUFU sqrt/rcp forms (<= 2 ulp, the same order as fp32 rounding
+// fp32 models use the branch-free MUFU exp/sqrt/rcp forms (<= 2 ulp, the same order as fp32 rounding
 // itself; lets the four elements of a vector interleave); fp64 keeps IEEE operations throughout.
 #include "forward.cuh"
 #include "coord.cuh"

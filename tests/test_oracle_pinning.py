@@ -77,6 +77,24 @@ def test_row_solvers_pinned_bitwise(port, ref, solver, task):
             assert np.array_equal(a[3]["rec_index"], b[3]["rec_index"]) and relerr(a[3]["eval_train"], b[3]["eval_train"]) < tol
 
 
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL, O.TDAP])
+@pytest.mark.parametrize("k,max_nnz", [(4, 70), (128, 45), (32, 100)])
+def test_row_solvers_pinned_on_ragged_empty_and_wide_rows(port, ref, solver, k, max_nnz):
+    # the shapes tests/test_gpu_exact.py::test_exact_row_shapes_and_layouts holds the CUDA kernel to: rows from empty to
+    # 100 non-zeros (the reference's TDAP position refresh, F6, reads z_w[0 .. nnz) there), k up to 128
+    rng = np.random.default_rng(11)
+    n, p = 90, 300
+    rowptr, col, val = synth.random_csr(n, p, max_nnz, seed=21, empty_rows=True)
+    assert (np.diff(rowptr.astype(np.int64)) == 0).any()
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.05, p); v = rng.normal(0, 0.05, (p, k))
+    c = O.make_cfg(solver=solver, k=k, max_iter=2 * (n - 1) + 7, l1_w=0.001, l2_w=0.001, l2_v=0.002)
+    a = port.train(c, n, p, rowptr, col, val, y, 0.1, w, v)
+    b = ref.train(c, n, p, rowptr, col, val, y, 0.1, w, v)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.isfinite(a[2]).all()
+
+
 def test_random_step_stream_pinned(port, ref):
     rng = np.random.default_rng(8)
     n, p, k = 200, 30, 2

@@ -156,6 +156,15 @@ class Context:
         buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
         check(lib().fmwr_comm_peer_open(self.h, buf))
 
+    def sort_pairs(self, keys, bits):
+        """the engine's stable radix sort on a host array of uint32 / uint64 keys -> (sorted keys, permutation)"""
+        keys = np.ascontiguousarray(keys)
+        assert keys.dtype in (np.uint32, np.uint64)
+        out = np.zeros_like(keys)
+        perm = np.zeros(keys.size, np.uint32)
+        check(lib().fmwr_sort_pairs(self.h, C.c_int32(keys.itemsize), C.c_int64(keys.size), C.c_int32(bits), ptr(keys), ptr(out), ptr(perm)))
+        return out, perm
+
     def link_table(self, which, x):
         x = np.ascontiguousarray(x, np.float64)
         out = np.zeros_like(x)
@@ -240,6 +249,11 @@ class Data:
         y = np.zeros(n, np.float32) if labels else None
         check(lib().fmwr_data_get_csr(self.h, ptr(rowptr), ptr(col), ptr(val), ptr(y)))
         return rowptr, col, val, y
+
+    def minibatch_info(self, batch_size, compat=COMPAT_REFERENCE):
+        nb, ns, ne = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().fmwr_data_minibatch_info(self.h, C.c_int32(batch_size), C.c_int32(compat), C.byref(nb), C.byref(ns), C.byref(ne)))
+        return dict(n_batches=nb.value, n_segments=ns.value, n_entries=ne.value)
 
     def transpose(self):
         check(lib().fmwr_data_transpose(self.h))

@@ -858,4 +858,37 @@ int fmwr_link_table_eval(fmwr_ctx* ctx, int32_t which, int64_t n, const double* 
   });
 }
 
+int fmwr_sort_pairs(fmwr_ctx* ctx, int32_t key_bytes, int64_t n, int32_t bits, const void* keys_in, void* keys_out, uint32_t* perm_out)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx && (n == 0 || (keys_in && keys_out && perm_out)), FMWR_ERR_ARG, "null argument");
+    FMWR_REQUIRE(key_bytes == 4 || key_bytes == 8, FMWR_ERR_ARG, "key_bytes must be 4 or 8");
+    FMWR_REQUIRE(n >= 0 && bits >= 1 && bits <= 8 * key_bytes, FMWR_ERR_ARG, "bad size / bit count");
+    FMWR_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return;
+    DBuf<char> kin, kout;
+    DBuf<uint32_t> perm;
+    kin.alloc((size_t)n * key_bytes); kout.alloc((size_t)n * key_bytes); perm.alloc(n);
+    FMWR_CUDA(cudaMemcpyAsync(kin.p, keys_in, (size_t)n * key_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (key_bytes == 4) sort_pairs_u32(ctx, (const uint32_t*)kin.p, (uint32_t*)kout.p, nullptr, perm.p, n, bits);
+    else sort_pairs_u64(ctx, (const uint64_t*)kin.p, (uint64_t*)kout.p, nullptr, perm.p, n, bits);
+    FMWR_CUDA(cudaMemcpyAsync(keys_out, kout.p, (size_t)n * key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaMemcpyAsync(perm_out, perm.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int fmwr_data_minibatch_info(fmwr_data* d, int32_t batch_size, int32_t compat, int64_t* n_batches, int64_t* n_segments, int64_t* n_entries)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(d && batch_size > 0, FMWR_ERR_ARG, "bad argument");
+    FMWR_CUDA(cudaSetDevice(d->ctx->device));
+    minibatch_build(d, (compat & FMWR_COMPAT_SKIP_ROW0) ? 1 : 0, batch_size);
+    const int64_t nb = (int64_t)d->mb_batch_seg.size() - 1;
+    if (n_batches) *n_batches = nb;
+    if (n_segments) *n_segments = nb >= 0 ? d->mb_batch_seg[nb] : 0;
+    if (n_entries) *n_entries = d->mb_batch_ent.empty() ? 0 : d->mb_batch_ent.back();
+  });
+}
+
 }  // extern "C"

@@ -71,6 +71,21 @@ void comm_allreduce_max_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count)
 
 using namespace fmwr;
 
+// A peer that never reached an in-kernel barrier leaves PEER_ERR set in our window (common.cuh: peer_wait).  Read it after the
+// final stream sync of a trainer, clear it (one timeout must not poison later calls) and report FMWR_ERR_COMM.
+namespace fmwr {
+void peer_check_error(fmwr_ctx* ctx)
+{
+  if (!ctx->peer.ready || !ctx->peer.base[ctx->rank]) return;
+  uint32_t* word = reinterpret_cast<uint32_t*>(ctx->peer.base[ctx->rank]) + PEER_ERR;
+  uint32_t err = 0;
+  FMWR_CUDA(cudaMemcpy(&err, word, 4, cudaMemcpyDeviceToHost));
+  if (!err) return;
+  FMWR_CUDA(cudaMemset(word, 0, 4));
+  throw Error(FMWR_ERR_COMM, "a peer rank did not reach the in-kernel barrier (timeout); the model is invalid");
+}
+}  // namespace fmwr
+
 extern "C" {
 
 int fmwr_comm_unique_id(uint8_t* id128)

@@ -218,6 +218,7 @@ namespace fmwr {
 // NCCL all-reduces on the context's stream (comm.cu)
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 void comm_allreduce_max_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count);
+void peer_check_error(fmwr_ctx* ctx);   // throws FMWR_ERR_COMM (and clears the flag) when an in-kernel peer barrier timed out
 
 // ---- device helpers ----------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -335,7 +336,9 @@ void build_link_tables(fmwr_ctx* ctx);
 void forward_launch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, int link, double lo, double hi);
 void transpose_build(fmwr_data* d);
 void launch_iota(fmwr_ctx* ctx, uint32_t* a, int64_t n);
+// stable LSD radix sort of (key, value) pairs on the low `bits` key bits (sort.cu); val_in == nullptr: values are 0, 1, 2, ...
 void sort_pairs_u32(fmwr_ctx* ctx, const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in, uint32_t* val_out, int64_t n, int bits);
+void sort_pairs_u64(fmwr_ctx* ctx, const uint64_t* key_in, uint64_t* key_out, const uint32_t* val_in, uint32_t* val_out, int64_t n, int bits);
 void phases_build(fmwr_data* d);
 void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch);
 void train_exact(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr);

@@ -5,7 +5,6 @@
 // src/util/Smatrix.h:44-61, :155-185, :98-153) and Data::add_data/add_target (src/core/Data.h:48-86).
 #include "common.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
 
@@ -354,19 +353,11 @@ void transpose_build(fmwr_data* d)
     d->has_csc = true;
     return;
   }
-  DBuf<uint32_t> erow, keys_out, idx_in, idx_out;
-  erow.alloc(nnz); keys_out.alloc(nnz); idx_in.alloc(nnz); idx_out.alloc(nnz);
+  DBuf<uint32_t> erow, keys_out, idx_out;
+  erow.alloc(nnz); keys_out.alloc(nnz); idx_out.alloc(nnz);
   FMWR_LAUNCH(ctx, expand_rows, ceil_div(n * 32, 256), 256, 0, d->rowptr.p, n, erow.p);
-  FMWR_LAUNCH(ctx, iota_u32, ceil_div(nnz, 256), 256, 0, idx_in.p, nnz);
-  size_t tmp_bytes = 0;
   const int end_bit = bits_for((uint64_t)(p > 0 ? p - 1 : 0));
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d->col.p, keys_out.p, idx_in.p, idx_out.p, (int)nnz, 0,
-                                            end_bit, ctx->stream));
-  DBuf<char> tmp;
-  tmp.alloc(tmp_bytes);
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d->col.p, keys_out.p, idx_in.p, idx_out.p, (int)nnz, 0,
-                                            end_bit, ctx->stream));
-  ctx->launches += 1;
+  sort_pairs_u32(ctx, d->col.p, keys_out.p, nullptr, idx_out.p, nnz, end_bit);      // values = entry ids 0 .. nnz-1 (sort.cu)
   FMWR_LAUNCH(ctx, gather_csc, ceil_div(nnz, 256), 256, 0, idx_out.p, erow.p, d->val.p, nnz, d->crow.p, d->cval.p);
   FMWR_LAUNCH(ctx, segment_ptr_from_sorted, ceil_div(nnz + 1, 256), 256, 0, keys_out.p, nnz, p, d->colptr.p);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -376,19 +367,6 @@ void transpose_build(fmwr_data* d)
 void launch_iota(fmwr_ctx* ctx, uint32_t* a, int64_t n)
 {
   if (n > 0) FMWR_LAUNCH(ctx, iota_u32, ceil_div(n, 256), 256, 0, a, n);
-}
-
-// stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key
-void sort_pairs_u32(fmwr_ctx* ctx, const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in, uint32_t* val_out, int64_t n, int bits)
-{
-  if (n <= 0) return;
-  size_t tmp_bytes = 0;
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, val_in, val_out, (int)n, 0, bits, ctx->stream));
-  DBuf<char> tmp;
-  tmp.alloc(tmp_bytes);
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in, key_out, val_in, val_out, (int)n, 0, bits, ctx->stream));
-  ctx->launches += 1;
-  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // ------------------------------------------------------------------------------------------ phases
@@ -593,23 +571,16 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
     return;
   }
   DBuf<K> keys_in, keys_out;
-  DBuf<uint32_t> erow, idx_in, idx_out, head, segid;
+  DBuf<uint32_t> erow, idx_out, head, segid;
   // values still uploading (one-shot training path): build the structure from rowptr / col alone and keep the permutation
   const bool deferred = d->val_ready != nullptr && !d->val_ev.empty() && cudaEventQuery(d->val_ready) != cudaSuccess;
-  keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); idx_in.alloc(m); head.alloc(m); segid.alloc(m);
+  keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); head.alloc(m); segid.alloc(m);
   if (deferred) d->mb_perm.alloc(m); else idx_out.alloc(m);
   uint32_t* perm_p = deferred ? d->mb_perm.p : idx_out.p;
   FMWR_LAUNCH(ctx, mb_keys<K>, ceil_div(rows * 32, 256), 256, 0, d->rowptr.p, d->col.p, row0, d->n, (uint32_t)batch, colbits,
               keys_in.p, erow.p);
-  FMWR_LAUNCH(ctx, iota_u32, ceil_div(m, 256), 256, 0, idx_in.p, m);
-  size_t tmp_bytes = 0;
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, perm_p, (int)m, 0,
-                                            colbits + batchbits, ctx->stream));
-  DBuf<char> tmp;
-  tmp.alloc(tmp_bytes);
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, idx_in.p, perm_p, (int)m, 0,
-                                            colbits + batchbits, ctx->stream));
-  ctx->launches += 1;
+  if (sizeof(K) == 4) sort_pairs_u32(ctx, (const uint32_t*)keys_in.p, (uint32_t*)keys_out.p, nullptr, perm_p, m, colbits + batchbits);
+  else sort_pairs_u64(ctx, (const uint64_t*)keys_in.p, (uint64_t*)keys_out.p, nullptr, perm_p, m, colbits + batchbits);
   FMWR_LAUNCH(ctx, mb_heads<K>, ceil_div(m, 256), 256, 0, keys_out.p, m, head.p);
   exclusive_scan_u32(ctx, head.p, segid.p, m);
   FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, segid.p + (m - 1), head.p + (m - 1), hp);

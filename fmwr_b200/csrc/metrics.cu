@@ -2,7 +2,6 @@
 // (reference src/core/Evaluation.h:20-115, used by Tracker::evaluate / report).
 #include "common.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 
 namespace fmwr {
 
@@ -115,12 +114,7 @@ static double evaluate_t(fmwr_ctx* ctx, fmwr_data* d, const T* yh, int task, int
   DBuf<uint32_t> pos_in, pos_out, cum, tot;
   key_in.alloc(n); key_out.alloc(n); pos_in.alloc(n); pos_out.alloc(n); cum.alloc(n);
   FMWR_LAUNCH(ctx, auc_keys<T>, ceil_div(n, 256), 256, 0, yh, d->y.p, n, key_in.p, pos_in.p);
-  size_t tmp_bytes = 0;
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in.p, key_out.p, pos_in.p, pos_out.p, (int)n, 0, 64, ctx->stream));
-  DBuf<char> tmp;
-  tmp.alloc(tmp_bytes);
-  FMWR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_in.p, key_out.p, pos_in.p, pos_out.p, (int)n, 0, 64, ctx->stream));
-  ctx->launches += 1;
+  sort_pairs_u64(ctx, key_in.p, key_out.p, pos_in.p, pos_out.p, n, 64);
   // two-level scan of the positive flags
   const int64_t per = 1024;
   const int64_t nthreads = ceil_div64(n, per);

@@ -1520,7 +1520,8 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
     }
   }
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (tr) { tr->n_rec = n_rec; tr->convergent = 0; tr->iters_done = sweep; }
+  if (ctx->world > 1) peer_check_error(ctx);      // a timed-out exchange means partial (A,B) sums: the replicas have diverged
+  if (tr) { tr->n_rec = std::min(n_rec, (int)tr->max_rec); tr->convergent = 0; tr->iters_done = sweep; }
 }
 
 void train_als_mcmc(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)

@@ -651,7 +651,7 @@ static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr
     }
   }
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (tr) { tr->n_rec = n_rec; tr->convergent = convergent; tr->iters_done = (int)iter; }
+  if (tr) { tr->n_rec = std::min(n_rec, (int)tr->max_rec); tr->convergent = convergent; tr->iters_done = (int)iter; }   // records WRITTEN (tracker_snapshot drops what does not fit)
 }
 
 void train_exact(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)

@@ -25,6 +25,7 @@ namespace fmwr {
 int solver_state_count(const SolverParams<double>& sp);
 double tracker_score(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s);
 void tracker_snapshot(fmwr_model* m, fmwr_trace* tr, int idx, int iter, double score);
+int tracker_step_size(int step_size, int max_iter);
 void minibatch_fill_values(fmwr_data* d, uint32_t seg_lo, uint32_t seg_hi);
 void data_wait_values(fmwr_data* d);
 void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi);
@@ -594,7 +595,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   ua.sp = params_from<T>(spd);
 
   const int64_t max_iter = s->max_iter;
-  const int step = s->step_size;
+  const int step = tracker_step_size(s->step_size, s->max_iter);   // Tracker::init's MAX_REC rule (src/core/Tracker.h:41-52)
   int64_t iter = 0, next_track = 0;
   int n_rec = 0, conv_times = 0, convergent = 0;
   double old_score = 0.0, u_w = 0.0, u_v = 0.0;
@@ -612,22 +613,35 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   const bool pending0 = d->mb_vals_pending;
   const bool use_graph = !ctx->profile && step <= 0 && (!multi || peer) && !pending0 && getenv("FMWR_NO_GRAPH") == nullptr;
   constexpr int GRAPH_CHUNK = 2048;
-  std::vector<cudaGraphExec_t> execs;
-  std::vector<cudaGraph_t> graphs;
+  // owns the graphs; if anything throws while the stream is capturing, the destructor ends and abandons the capture so the
+  // context's stream stays usable for the next call
+  struct GraphBag {
+    cudaStream_t stream; bool capturing = false;
+    std::vector<cudaGraphExec_t> execs; std::vector<cudaGraph_t> graphs;
+    ~GraphBag()
+    {
+      if (capturing) { cudaGraph_t g = nullptr; cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); }
+      for (auto ge : execs) cudaGraphExecDestroy(ge);
+      for (auto g : graphs) cudaGraphDestroy(g);
+    }
+  } bag;
+  bag.stream = ctx->stream;
   int captured = 0;
   auto flush_graph = [&]() {
     if (!use_graph || captured == 0) return;
     cudaGraph_t g = nullptr;
+    bag.capturing = false;
     FMWR_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+    bag.graphs.push_back(g);
     cudaGraphExec_t ge = nullptr;
     FMWR_CUDA(cudaGraphInstantiate(&ge, g, 0));
-    graphs.push_back(g); execs.push_back(ge);
+    bag.execs.push_back(ge);
     FMWR_CUDA(cudaGraphLaunch(ge, ctx->stream));
     captured = 0;
   };
   while (iter < max_iter && !convergent) {
     for (int64_t b = 0; b < n_batches && iter < max_iter; ++b) {
-      if (use_graph && captured == 0) FMWR_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      if (use_graph && captured == 0) { FMWR_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal)); bag.capturing = true; }
       const int64_t rb = row0 + b * B;
       if (d->mb_vals_pending) {
         const int64_t last_entry = (int64_t)d->mb_e0 + d->mb_batch_ent[b + 1] - 1;
@@ -681,14 +695,8 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   flush_graph();
   if (sgd_l1) { const double h[2] = {u_w, u_v}; FMWR_CUDA(cudaMemcpyAsync((double*)m->scal.p + 1, h, 16, cudaMemcpyHostToDevice, ctx->stream)); }
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (peer) {
-    uint32_t err = 0;
-    FMWR_CUDA(cudaMemcpy(&err, reinterpret_cast<uint32_t*>(pa.base[pa.rank]) + PEER_ERR, 4, cudaMemcpyDeviceToHost));
-    FMWR_REQUIRE(err == 0, FMWR_ERR_COMM, "a peer rank did not reach the in-kernel barrier (timeout); the model is invalid");
-  }
-  for (auto ge : execs) cudaGraphExecDestroy(ge);
-  for (auto g : graphs) cudaGraphDestroy(g);
-  if (tr) { tr->n_rec = n_rec; tr->convergent = convergent; tr->iters_done = (int)iter; }
+  if (peer) peer_check_error(ctx);
+  if (tr) { tr->n_rec = std::min(n_rec, (int)tr->max_rec); tr->convergent = convergent; tr->iters_done = (int)iter; }
 }
 
 void train_minibatch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)

@@ -227,8 +227,16 @@ int fmwr_track(const fmwr_model_cfg* cfg, int32_t solver, int32_t precision, int
                int32_t n_snap, const double* snap_w0, const double* snap_w, const double* snap_v,
                int32_t metric, double lo, double hi, double* out /*[n_snap]*/);
 
-/* ---- scalar helpers exposed for parity tests ---- */
+/* ---- helpers exposed for parity tests and for the roofline model ---- */
 int fmwr_link_table_eval(fmwr_ctx* ctx, int32_t which /*0 fast_pnorm, 1 fast_dpnorm*/, int64_t n, const double* x, double* out);
+/* The engine's stable radix sort (csrc/sort.cu) on host arrays: keys of key_bytes (4 or 8) each are sorted on their low `bits`
+ * bits; perm_out[i] = original position of the i-th smallest key, equal keys in input order (the property that makes the
+ * CSR -> CSC twin equal SMatrix::transpose, src/util/Smatrix.h:155-185). */
+int fmwr_sort_pairs(fmwr_ctx* ctx, int32_t key_bytes, int64_t n, int32_t bits, const void* keys_in, void* keys_out, uint32_t* perm_out);
+/* Shape of the per-batch CSC the minibatch trainers work on (built on first use for this batch size; compat as in fmwr_solver_cfg):
+ * number of batches, (batch, feature) segments = coordinates that get an optimizer step per epoch, and entries.  bench.py
+ * derives the compulsory bytes of the update kernel from these instead of a per-sample model. */
+int fmwr_data_minibatch_info(fmwr_data* d, int32_t batch_size, int32_t compat, int64_t* n_batches, int64_t* n_segments, int64_t* n_entries);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,13 @@ the data resident in HBM.  The same run also times predict.FM over the same rows
 end-to-end call through the C ABI with HOST buffers (`e2e`), the reference's CPU path on a bounded sample
 (`cpu_baseline`) and reports the dominant kernel's achieved HBM bandwidth (`roofline`).
 
+Roofline accounting: `roofline.frac` of the update kernel is COMPULSORY bytes per launch -- counted from
+the real per-batch structure (segments x (record + offset + theta/state rows and w scalars, read and write) + entries x 8 B)
+-- over the CUDA-event launch time over the measured HBM peak.  SURVEY 8(d)'s per-sample model (every gather at full width,
+no cache credit) is kept as a labelled second figure without a fraction: a 65 536-row batch touches a coordinate ~2.6 times
+and updates it once, so that model overstates the bytes this kernel has to move.  Kernels whose committed ncu DRAM traffic is
+below half the per-sample model (predict, K1: V is half L2-resident) report their fraction against the MEASURED traffic.
+
     python bench.py --gpus N --steps K --warmup W            # engine arm
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU implementation
 
@@ -36,6 +43,23 @@ ALG_BYTES = {
     "ftrl": lambda m, k: 8 + m * (8 + 6 * (4 + 4 * k)),
     "tdap": lambda m, k: 8 + m * (8 + 10 * (4 + 4 * k)),
 }
+
+
+N_ARRAYS = {"sgd": 1, "sgd_l1": 2, "ftrl": 3, "tdap": 5}      # theta + optimizer-state arrays a coordinate step reads and writes
+
+
+def k2_compulsory_bytes(solver, info, kp):
+    """bytes the coordinate-update kernel MUST move per epoch, from the real per-batch CSC: per (batch, feature) segment the
+    16-byte record, the 4-byte entry offset, the theta/state rows (kp x 4 B each) and the w scalars, read and written once;
+    per entry 8 bytes (row id + value).  The S-cache / multiplier gathers stay in L2 (8 MB per batch) and are not counted."""
+    na = N_ARRAYS[solver]
+    return info["n_segments"] * (20 + 2 * na * 4 * kp + 2 * na * 4) + info["n_entries"] * 8
+
+
+def k1_compulsory_bytes(info, n, m, kp):
+    """forward of the batches: the CSR rows once (8 B per entry + 4 B row offset + 4 B label) and, per batch, each touched
+    feature's factor row and weight once (a perfect cache inside a batch); the S-cache writes stay in L2"""
+    return n * (8 * m + 8) + info["n_segments"] * (4 * kp + 4)
 
 
 def measured_peak():
@@ -98,13 +122,14 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel, units_per_launch):
-    """DRAM bytes per launch from the committed ncu capture (profiles/traffic_r01.json), scaled to this run's launch size"""
-    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    try:
-        t = json.load(open(path))[kernel]
-        return int(t["dram_bytes"] * units_per_launch / t["rows_per_launch"])
-    except Exception:
-        return None
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic_r02.json), scaled to this run's launch size"""
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+            return int(t["dram_bytes"] * units_per_launch / t["rows_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def parse_profile(txt):
@@ -127,6 +152,39 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ engine arm
+def update_kernel_of(prof):
+    """the coordinate-update kernel that ran (dense TMA variant or the gather kernel): the one with the larger total"""
+    cands = [(v[1], name) for name, v in prof.items() if name.startswith("mb_update")]
+    return max(cands)[1] if cands else None
+
+
+def forward_kernel_of(prof):
+    cands = [(v[1], name) for name, v in prof.items() if "forward" in name]
+    return max(cands)[1] if cands else None
+
+
+def profiled(L, lib, ctx, fn, steps):
+    """run fn() `steps` times with a CUDA-event pair around every kernel launch (events pre-created by one untimed pass)"""
+    buf = C.create_string_buffer(1 << 16)
+    L.check(lib.fmwr_profile_enable(ctx.h, 1))
+    fn()
+    L.check(lib.fmwr_profile_enable(ctx.h, 1))          # returns the events to the pool, clears the records
+    ctx.timer_start()
+    for _ in range(steps):
+        fn()
+    ms = ctx.timer_stop_ms()
+    L.check(lib.fmwr_profile_read(ctx.h, buf, C.c_int64(len(buf))))
+    prof = parse_profile(buf.value.decode())
+    L.check(lib.fmwr_profile_enable(ctx.h, 0))
+    return prof, ms
+
+
+def mb_solver_cfg(L, solver, max_iter, B, mode=None, precision=None):
+    return L.SolverCfg(solver=solver, max_iter=max_iter, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                       gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH if mode is None else mode, batch_size=B,
+                       precision=L.F32 if precision is None else precision, compat=L.COMPAT_REFERENCE, step_size=-1)
+
+
 def run_engine(args):
     from fmwr_b200 import _lib as L
     rank, world, local = dist_env()
@@ -136,6 +194,7 @@ def run_engine(args):
     ctx = L.Context(local)
     peak, peak_src = measured_peak()
     n, F, k, B = args.rows, 39, args.k, args.batch
+    kp = (k + 3) // 4 * 4
     field = args.features // F
     p = field * F
     m_nnz = F
@@ -148,13 +207,12 @@ def run_engine(args):
     ctx.sync()
     t_gen = time.time() - t0
 
-    def scfg(max_iter):
-        return L.SolverCfg(solver=L.FTRL, max_iter=max_iter, random_step=1, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
-                           min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F32,
-                           compat=L.COMPAT_REFERENCE, step_size=-1)
-
     epoch = n - 1                       # one reference epoch == n-1 sample updates
-    sc = scfg(epoch)
+    sc = mb_solver_cfg(L, L.FTRL, epoch, B)
+    # ---- the per-batch CSC the update kernel works on: built once per (data, batch size), timed on its own ----------
+    ctx.sync(); ctx.timer_start()
+    info = data.minibatch_info(B)
+    prep_ms = ctx.timer_stop_ms()
     # ---- FTRL epoch, data resident ------------------------------------------------------------------
     for _ in range(args.warmup):
         L.train_dev(ctx, model, data, sc)
@@ -169,19 +227,8 @@ def run_engine(args):
     ms_train = ctx.timer_stop_ms()
     l1 = ctx.launches()
     train_sps = epoch * args.steps / (ms_train * 1e-3)
-    # timed region B: the same K steps with a CUDA-event pair around every kernel launch (events pre-created by one
-    # untimed profiled step) -> per-kernel durations for the roofline
-    buf = C.create_string_buffer(1 << 16)
-    L.check(lib.fmwr_profile_enable(ctx.h, 1))
-    L.train_dev(ctx, model, data, sc)
-    L.check(lib.fmwr_profile_enable(ctx.h, 1))          # returns the events to the pool, clears the records
-    ctx.timer_start()
-    for _ in range(args.steps):
-        L.train_dev(ctx, model, data, sc)
-    ms_train_prof = ctx.timer_stop_ms()
-    L.check(lib.fmwr_profile_read(ctx.h, buf, C.c_int64(len(buf))))
-    prof_train = parse_profile(buf.value.decode())
-    L.check(lib.fmwr_profile_enable(ctx.h, 0))
+    # timed region B: the same K steps with a CUDA-event pair around every kernel launch -> per-kernel durations for the roofline
+    prof_train, ms_train_prof = profiled(L, lib, ctx, lambda: L.train_dev(ctx, model, data, sc), args.steps)
 
     # ---- predict.FM, data resident -------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -190,51 +237,68 @@ def run_engine(args):
     for _ in range(args.steps):
         L.predict_dev(ctx, model, data, L.LINK_LOGISTIC)
     ms_pred = ctx.timer_stop_ms()
-    L.check(lib.fmwr_profile_enable(ctx.h, 1))
-    for _ in range(args.steps):
-        L.predict_dev(ctx, model, data, L.LINK_LOGISTIC)
-    L.check(lib.fmwr_profile_read(ctx.h, buf, C.c_int64(len(buf))))
-    prof_pred = parse_profile(buf.value.decode())
-    L.check(lib.fmwr_profile_enable(ctx.h, 0))
+    prof_pred, _ = profiled(L, lib, ctx, lambda: L.predict_dev(ctx, model, data, L.LINK_LOGISTIC), args.steps)
     clk = clocks.stop()
     pred_rps = n * args.steps / (ms_pred * 1e-3)
 
     # ---- roofline of the dominant kernel (the coordinate-update kernel K2) ---------------------------------
     b_fwd = ALG_BYTES["predict"](m_nnz, k)
     b_ftrl = ALG_BYTES["ftrl"](m_nnz, k)
+    nb = max(1, info["n_batches"])
+    k2_bytes = k2_compulsory_bytes("ftrl", info, kp)           # per epoch
+    k1_bytes = k1_compulsory_bytes(info, n, m_nnz, kp)
     roof = None
-    kn = "mb_update_kernel"
-    if kn in prof_train and prof_train[kn][1] > 0:
+    kn = update_kernel_of(prof_train)
+    if kn and prof_train[kn][1] > 0:
         launches, ms = prof_train[kn]
-        units = epoch * args.steps                      # samples whose coordinates the launches updated
-        ach = units * (b_ftrl - b_fwd) / (ms * 1e-3) / 1e9
+        per_launch = k2_bytes * args.steps / launches
+        ach = per_launch / (ms / launches * 1e-3) / 1e9
+        traffic = ncu_traffic(kn, min(B, n)) if (p, k) == (999999, 32) else None
         roof = {"kernel": kn, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": ncu_traffic(kn, min(B, n)) if (p, k) == (999999, 32) else None,
-                "alg_bytes_per_launch": int((b_ftrl - b_fwd) * units / launches),
-                "traffic_note": "ncu dram bytes per launch (profiles/r01_ncu_full.csv); below the algorithmic bytes because a batch "
-                                "touches each coordinate ~2.6x and updates it once, and V re-reads hit L2",
+                "traffic": traffic,
+                "alg_bytes_per_launch": int(per_launch),
+                "model": "compulsory bytes of one batch from its real structure: %d segments x (16 B record + 4 B offset + theta/z/n rows and w scalars read+written) "
+                         "+ %d entries x 8 B, per epoch / %d batches; S-cache gathers are L2-resident and not counted" % (info["n_segments"], info["n_entries"], nb),
+                "frac_of_traffic": round(traffic / (ms / launches * 1e-3) / 1e9 / peak, 4) if traffic else None,
+                "survey_model_bytes_per_launch": int((b_ftrl - b_fwd) * epoch * args.steps / launches),
+                "survey_model_note": "SURVEY 8(d) per-sample model (every gather at full width, no cache credit): more than this kernel has to move, "
+                                     "because a batch touches a coordinate %.2f times and updates it once -- reported without a fraction" % (info["n_entries"] / max(1, info["n_segments"])),
                 "peak_source": peak_src, "launches": launches, "avg_launch_ms": round(ms / launches, 5),
-                "alg_bytes_per_sample": b_ftrl - b_fwd,
                 "share_of_step": round(ms / ms_train_prof, 4), "ms_per_step_with_events": round(ms_train_prof / args.steps, 3)}
     fwd_roof = None
-    if "forward_kernel" in prof_pred and prof_pred["forward_kernel"][1] > 0:
-        launches, ms = prof_pred["forward_kernel"]
-        ach = n * args.steps * b_fwd / (ms * 1e-3) / 1e9
-        fwd_roof = {"kernel": "forward_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": ncu_traffic("forward_kernel", n) if (p, k) == (999999, 32) else None,
-                    "alg_bytes_per_row": b_fwd, "avg_launch_ms": round(ms / launches, 4)}
-    k1 = prof_train.get("mb_forward_kernel")
+    fk = forward_kernel_of(prof_pred)
+    if fk and prof_pred[fk][1] > 0:
+        launches, ms = prof_pred[fk]
+        traffic = ncu_traffic(fk, n) if (p, k) == (999999, 32) else None
+        t_s = ms / launches * 1e-3
+        # guard of SURVEY 8(d): measured DRAM bytes below half the per-row model (V is half L2-resident) -> fraction against the measured bytes
+        # the per-row model counts every factor-row gather as DRAM traffic; with V (128 MB) about half L2-resident the kernel moves
+        # less than half of it, so the fraction is taken against the MEASURED bytes (null until a capture of this kernel is committed)
+        use_traffic = traffic is not None and traffic < 0.5 * n * b_fwd
+        basis = traffic if use_traffic else (n * b_fwd if traffic is not None else None)
+        fwd_roof = {"kernel": fk, "bound": "hbm", "achieved": round(basis / t_s / 1e9, 1) if basis else None, "peak": peak, "unit": "GB/s",
+                    "frac": round(basis / t_s / 1e9 / peak, 4) if basis else None, "traffic": traffic,
+                    "basis": "measured DRAM bytes (ncu): below half the per-row model because V is half L2-resident" if use_traffic else "SURVEY 8(d) per-row model",
+                    "survey_model_gbs": round(n * b_fwd / t_s / 1e9, 1), "alg_bytes_per_row": b_fwd, "avg_launch_ms": round(ms / launches, 4),
+                    "gather_ceiling_ms": GATHER_CEILING_MS.get((p, k)),
+                    "gather_ceiling_note": "profiles/r02_gather_bench.md: a kernel that does nothing but this launch's 390M random 128-byte row gathers from a 128 MB table "
+                                           "(8 loads in flight per lane, 32 warps/SM) takes this long on the same B200"}
     kernels = {name: {"launches": v[0], "ms": round(v[1], 3)} for name, v in prof_train.items()}
+    step_bytes = k1_bytes + k2_bytes
+    step_gbs = step_bytes / (ms_train / args.steps * 1e-3) / 1e9
 
     # ---- the other solvers of the north_star (secondary lines) ------------------------------------------------------
     solvers = None
     if not args.no_solvers:
-        solvers = run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B)
+        solvers = run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B, info, kp)
+        if not args.no_sweep:
+            solvers["batch_sweep"] = run_batch_sweep(L, ctx, data, args, n, F, field, p, k)
+        solvers["c1"] = run_c1(L, ctx, args)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(L, lib, ctx, data, mcfg, scfg(epoch), n, p, k, args)
+        e2e = run_e2e(L, lib, ctx, data, mcfg, mb_solver_cfg(L, L.FTRL, epoch, B), n, p, k, args)
 
     # ---- CPU baseline (the reference's own C++ where available, else the C port) on a bounded sample ----------------
     cpu = None
@@ -249,10 +313,16 @@ def run_engine(args):
         "config": {"workload": "configs[1]: Criteo-shaped %d rows x %d nnz, %d features, k=%d, FTRL L1+L2 binary logloss" % (n, F, p, k),
                    "rows": n, "nnz_per_row": F, "features": p, "k": k, "batch_size": B, "mode": "minibatch",
                    "l2_flush": "inputs (%.1f GB CSR + %.1f GB params/state) larger than L2" % (n * F * 8 / 1e9, p * (k + 1) * 12 / 1e9),
-                   "epoch": "n-1 sample updates (reference scan skips row 0)"},
+                   "epoch": "n-1 sample updates (reference scan skips row 0)",
+                   "optimizer_steps_per_epoch": info["n_batches"],
+                   "quality": "train LL / AUC after one epoch for this and other batch sizes, next to the batch = 1 run: solvers.batch_sweep"},
         "roofline": roof,
-        "step_roofline": {"alg_bytes_per_sample": b_ftrl, "achieved": round(train_sps * b_ftrl / 1e9, 1), "unit": "GB/s",
-                          "frac": round(train_sps * b_ftrl / 1e9 / peak, 4)},
+        "step_roofline": {"compulsory_bytes_per_step": int(step_bytes), "achieved": round(step_gbs, 1), "unit": "GB/s", "frac": round(step_gbs / peak, 4),
+                          "model": "forward (CSR once + each touched factor row once per batch) + update (roofline.model)",
+                          "survey_model_bytes_per_sample": b_ftrl},
+        "prep_ms": round(prep_ms, 2),
+        "prep_note": "per-batch CSC build (hand-written radix sort + segment emit), once per (data, batch size): not inside `value`, inside `e2e`; "
+                     "R's default run is 2 epochs (R/fm_train.R:92)",
         "kernels": kernels,
         "predict": {"value": round(pred_rps, 1), "unit": "rows/s", "ms_per_step": round(ms_pred / args.steps, 3),
                     "roofline": fwd_roof},
@@ -265,10 +335,15 @@ def run_engine(args):
     data.close(); model.close(); ctx.close()
 
 
-def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B):
+# measured by profiles/tools/gather_bench.cu on this pool's B200 (profiles/r02_gather_bench.md), keyed by (features, k)
+GATHER_CEILING_MS = {(999999, 32): 3.85}
+
+
+def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B, info, kp):
     """the north_star's other training paths, same timing rules (3 warm-ups, CUDA events, data resident): SGD and TDAP
     minibatch epochs on the configs[1] matrix already on the device; one ALS sweep on configs[2] and one MCMC sweep on
-    configs[3] (MovieLens-shaped 20M ratings, 3 one-hot fields).  Fractions are against SURVEY 8(d)'s algorithmic bytes."""
+    configs[3] (MovieLens-shaped 20M ratings, 3 one-hot fields).  Minibatch fractions are against the compulsory bytes of the
+    epoch (forward + update, see k1_/k2_compulsory_bytes); SURVEY 8(d)'s per-sample model is given without a fraction."""
     out = {}
     steps = max(1, min(args.steps, 3))
 
@@ -285,14 +360,23 @@ def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B):
                         l1_v=0.0, l2_v=1e-3)
         m = L.Model(ctx, mc, p, L.F32)
         m.init_random(0.0, 0.01, 20240603)
-        sc = L.SolverCfg(solver=solver, max_iter=n - 1, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
-                         gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F32,
-                         compat=L.COMPAT_REFERENCE, step_size=-1)
+        sc = mb_solver_cfg(L, solver, n - 1, B)
         ms = timed(lambda: L.train_dev(ctx, m, data, sc))
+        prof, ms_prof = profiled(L, lib, ctx, lambda: L.train_dev(ctx, m, data, sc), 1)
         b = ALG_BYTES[name](F, k)
         sps = (n - 1) / (ms * 1e-3)
+        comp = k1_compulsory_bytes(info, n, F, kp) + k2_compulsory_bytes(name, info, kp)
+        kn = update_kernel_of(prof)
+        k2 = None
+        if kn:
+            launches, kms = prof[kn]
+            per_launch = k2_compulsory_bytes(name, info, kp) / launches
+            k2 = {"kernel": kn, "avg_launch_ms": round(kms / launches, 5), "alg_bytes_per_launch": int(per_launch),
+                  "frac": round(per_launch / (kms / launches * 1e-3) / 1e9 / peak, 4), "traffic": ncu_traffic(kn + "_" + name, min(B, n)) if (p, k) == (999999, 32) else None}
         out[name] = {"workload": "configs[1] matrix, %s minibatch epoch (batch %d)" % (name.upper(), B), "value": round(sps, 1), "unit": "samples/s",
-                     "ms_per_step": round(ms, 3), "alg_bytes_per_sample": b, "achieved_gbs": round(sps * b / 1e9, 1), "frac": round(sps * b / 1e9 / peak, 4)}
+                     "ms_per_step": round(ms, 3), "compulsory_bytes_per_step": int(comp), "achieved_gbs": round(comp / (ms * 1e-3) / 1e9, 1),
+                     "frac": round(comp / (ms * 1e-3) / 1e9 / peak, 4), "update_kernel": k2, "survey_model_bytes_per_sample": b,
+                     "kernels": {kk: {"launches": v[0], "ms": round(v[1], 3)} for kk, v in prof.items()}}
         m.close()
     # exact mode (batch = 1, the reference's own sample order and arithmetic): one persistent CTA, latency-bound by
     # construction (every sample reads w0 written by the previous one), so it is reported in samples/s on a bounded
@@ -303,9 +387,7 @@ def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B):
         mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
         m = L.Model(ctx, mc, p, L.F32)
         m.init_random(0.0, 0.01, 20240603)
-        sc = L.SolverCfg(solver=solver, max_iter=it, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
-                         gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_EXACT, batch_size=1, precision=L.F32,
-                         compat=L.COMPAT_REFERENCE, step_size=-1)
+        sc = mb_solver_cfg(L, solver, it, 1, mode=L.MODE_EXACT)
         L.train_dev(ctx, m, data, sc)
         ctx.sync(); ctx.timer_start()
         L.train_dev(ctx, m, data, sc)
@@ -334,6 +416,108 @@ def run_other_solvers(L, lib, ctx, data, args, peak, n, F, p, k, B):
                      "achieved_gbs": round(sweep_bytes / (ms * 1e-3) / 1e9, 1), "frac": round(sweep_bytes / (ms * 1e-3) / 1e9 / peak, 4)}
         m.close()
     da.close()
+    return out
+
+
+def quality(L, ctx, model, data):
+    """train-set LL (the reference's sum form, src/core/Evaluation.h:80-89, divided by n here) and AUC of the model"""
+    L.predict_dev(ctx, model, data, L.LINK_LOGISTIC)
+    nrow = data.shape()[0]
+    ll = L.evaluate_dev(ctx, data, L.CLASSIFICATION, L.LL)
+    auc = L.evaluate_dev(ctx, data, L.CLASSIFICATION, L.AUC)
+    return round(ll / nrow, 6), round(auc, 5)
+
+
+def run_batch_sweep(L, ctx, data, args, n, F, field, p, k):
+    """ties the throughput numbers to model quality: for batch sizes 4096 / 16384 / 65536 the epoch rate on the full matrix
+    and the train LL / AUC after ONE epoch over a 10^6-row prefix (same ids per field, so the same touches per coordinate
+    per batch as the full matrix), next to the batch = 1 (reference order and arithmetic) epoch over the same prefix"""
+    n_pre = int(min(n, args.sweep_rows))
+    pre = L.Data.synth(ctx, n_pre, [field] * F, None, 0, 1, 0.1, 20240601)      # rows 0 .. n_pre-1 of the same matrix (hash keyed by row)
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+    out = {"workload": "FTRL L1+L2, one epoch; quality on the first %d rows of the configs[1] matrix (p=%d, k=%d), rate on all %d rows" % (n_pre, p, k, n),
+           "ll": "mean train log-loss as the reference sums it (Evaluation.h:80-89) / rows"}
+    m = L.Model(ctx, mc, p, L.F32)
+    m.init_random(0.0, 0.01, 20240603)
+    out["init"] = dict(zip(("ll", "auc"), quality(L, ctx, m, pre)))
+    sc = mb_solver_cfg(L, L.FTRL, n_pre - 1, 1, mode=L.MODE_EXACT)
+    ctx.sync(); ctx.timer_start()
+    L.train_dev(ctx, m, pre, sc)
+    ms = ctx.timer_stop_ms()
+    ll, auc = quality(L, ctx, m, pre)
+    out["exact_batch1"] = {"ll": ll, "auc": auc, "samples_per_s": round((n_pre - 1) / (ms * 1e-3), 1), "optimizer_steps": n_pre - 1}
+    m.close()
+    for B in (4096, 16384, 65536):
+        m = L.Model(ctx, mc, p, L.F32)
+        m.init_random(0.0, 0.01, 20240603)
+        L.train_dev(ctx, m, pre, mb_solver_cfg(L, L.FTRL, n_pre - 1, B))
+        ll, auc = quality(L, ctx, m, pre)
+        m.close()
+        # rate on the full matrix (its per-batch CSC is rebuilt for this batch size: prep_ms)
+        ctx.sync(); ctx.timer_start()
+        data.minibatch_info(B)
+        prep = ctx.timer_stop_ms()
+        mf = L.Model(ctx, mc, p, L.F32)
+        mf.init_random(0.0, 0.01, 20240603)
+        scf = mb_solver_cfg(L, L.FTRL, n - 1, B)
+        L.train_dev(ctx, mf, data, scf)
+        ctx.sync(); ctx.timer_start()
+        for _ in range(2):
+            L.train_dev(ctx, mf, data, scf)
+        msf = ctx.timer_stop_ms() / 2
+        mf.close()
+        out["batch_%d" % B] = {"ll": ll, "auc": auc, "optimizer_steps": -(-(n_pre - 1) // B), "samples_per_s": round((n - 1) / (msf * 1e-3), 1),
+                               "ms_per_epoch": round(msf, 3), "prep_ms": round(prep, 2)}
+    pre.close()
+    data.minibatch_info(args.batch)             # leave the headline batch size cached for the callers that follow
+    return out
+
+
+def run_c1(L, ctx, args):
+    """BASELINE configs[0]: fm.train SGD.solver, k=8, L2, 100k x 10k regression, 10 nnz/row -- the case the reference runs on a CPU.
+    Exact mode (the reference's order and arithmetic, one persistent CTA), the throughput mode, and the reference's own C++ on
+    this box's host, one epoch each.  Says plainly which side wins in exact mode."""
+    n, fields, k = 100_000, [1000] * 10, 8
+    p = sum(fields)
+    d = L.Data.synth(ctx, n, fields, None, 1, 2, 0.1, 20240601)
+    mc = L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=0.0, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+    rowptr, col, val, y = d.get_csr()
+    lo, hi = float(y.min()), float(y.max())
+    out = {"workload": "configs[0]: SGD L2, k=8, %d x %d regression, 10 nnz/row, one epoch (n-1 updates)" % (n, p)}
+
+    def run(mode, prec, B, reps):
+        m = L.Model(ctx, mc, p, prec)
+        m.init_random(0.0, 0.01, 20240603)
+        sc = L.SolverCfg(solver=L.SGD, max_iter=n - 1, random_step=1, learn_rate=0.01, min_target=lo, max_target=hi, mode=mode, batch_size=B,
+                         precision=prec, compat=L.COMPAT_REFERENCE, step_size=-1)
+        L.train_dev(ctx, m, d, sc)
+        ctx.sync(); ctx.timer_start()
+        for _ in range(reps):
+            L.train_dev(ctx, m, d, sc)
+        ms = ctx.timer_stop_ms() / reps
+        m.close()
+        return {"value": round((n - 1) / (ms * 1e-3), 1), "unit": "samples/s", "ms_per_epoch": round(ms, 3)}
+
+    out["exact_f32"] = run(L.MODE_EXACT, L.F32, 1, 2)
+    out["exact_f64"] = run(L.MODE_EXACT, L.F64, 1, 2)
+    out["minibatch_f32_b4096"] = run(L.MODE_MINIBATCH, L.F32, 4096, 5)
+    if not args.no_cpu:
+        O, orc, kind = oracle_for_baseline()
+        rng = np.random.default_rng(20240603)
+        w = np.zeros(p); v = rng.normal(0, 0.01, (p, k))
+        cfg = O.make_cfg(solver=O.SGD, task=O.REGRESSION, k=k, max_iter=n - 1, l2_w=1e-3, l2_v=1e-3, learn_rate=0.01, nthreads=1,
+                         min_target=lo, max_target=hi)
+        orc.train(cfg, n, p, rowptr, col, val, y, 0.0, w.copy(), v.copy())
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            orc.train(cfg, n, p, rowptr, col, val, y, 0.0, w.copy(), v.copy())
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_reference"] = {"value": round((n - 1) / dt, 1), "unit": "samples/s", "cores": 1, "kind": kind, "ms_per_epoch": round(dt * 1e3, 3)}
+        g, c = out["exact_f32"]["value"], out["cpu_reference"]["value"]
+        out["exact_mode_verdict"] = ("the reference's single-thread CPU loop is %.1fx FASTER than the GPU exact mode on this 4 MB problem (it fits the CPU's cache; "
+                                     "the GPU path is one latency-bound CTA)" % (c / g)) if c > g else "GPU exact mode is %.1fx the reference CPU" % (g / c)
+    d.close()
     return out
 
 
@@ -471,9 +655,122 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, prec, solver, n_rows, B):
+    """driver-side correctness of the feature-parallel path: train an n_rows prefix of the configs[1] matrix on `world` GPUs
+    (column slices, in-kernel peer exchange) and on ONE GPU (rank 0, a context without communicator), same initial model and
+    batches; returns max |a-b| / max(1,|b|) over (w0, w, V) on rank 0"""
+    F = len(fields)
+    p = int(sum(fields))
+    f0, f1, c0, c1 = multi.field_partition(fields, world)[rank]
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+    sc = mb_solver_cfg(L, solver, 2 * (n_rows - 1), B, precision=prec)
+    full = L.Data.synth(ctx, n_rows, fields, None, 0, 1, 0.1, 20240601)
+    part = full.slice_columns(c0, c1)
+    # identical initial parameters on both sides: the full model's device init, sliced
+    m0 = L.Model(ctx, mc, p, prec)
+    m0.init_random(0.0, 0.01, 20240603)
+    w0_, w_, v_ = m0.get()
+    m0.close()
+    m = L.Model(ctx, mc, c1 - c0, prec)
+    m.set(w0_, w_[c0:c1], v_[c0:c1])
+    L.train_dev(ctx, m, part, sc)
+    mine = m.get()
+    m.close(); part.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    err = None
+    if rank == 0:
+        gw0, gw, gv = multi.gather_model(parts)
+        solo = L.Context(local)                           # no communicator: the single-GPU path
+        rowptr, col, val, y = full.get_csr()
+        d1 = L.Data.from_csr32(solo, n_rows, p, rowptr, col, val, y)
+        m1 = L.Model(solo, mc, p, prec)
+        m1.set(w0_, w_, v_)
+        L.train_dev(solo, m1, d1, sc)
+        sw0, sw, sv = m1.get()
+        m1.close(); d1.close(); solo.close()
+        err = max(abs(gw0 - sw0) / max(1.0, abs(sw0)), float(np.max(np.abs(gw - sw) / np.maximum(1, np.abs(sw)))),
+                  float(np.max(np.abs(gv - sv) / np.maximum(1, np.abs(sv)))))
+        moved = float(np.max(np.abs(sv - v_)))
+        if not moved > 1e-4:
+            err = float("inf")                            # a run that did not train proves nothing
+    full.close()
+    return err
+
+
+def run_c5(L, multi, dist, ctx, args, rank, world, timed, peak):
+    """BASELINE configs[4]: SGD / TDAP minibatch epochs + predict on 100M rows x 39 nnz, 50M features, k=32, sharded over the box.
+    Training is feature-parallel (every rank: all rows, its fields' columns, generated in row chunks on the device);
+    predict is row-sharded with the 6.4 GB model replicated.  In this regime a batch touches a feature about once
+    (1.28M ids per field against 65 536 rows), so nothing is L2-resident and the compulsory bytes are close to SURVEY 8(d)'s model."""
+    n, F, k, B = args.c5_rows, 39, 32, args.batch
+    field = args.c5_features // F
+    fields = [field] * F
+    p = field * F
+    f0, f1, c0, c1 = multi.field_partition(fields, world)[rank]
+    t0 = time.time()
+    parts = []
+    chunk = 10_000_000
+    for r0 in range(0, n, chunk):
+        full = L.Data.synth_rows(ctx, r0, min(chunk, n - r0), fields, None, 0, 1, 0.1, 20240601)
+        parts.append(full.slice_columns(c0, c1))
+        full.close()
+    shard = L.Data.concat_rows(parts) if len(parts) > 1 else parts[0]
+    if len(parts) > 1:
+        for q in parts:
+            q.close()
+    ctx.sync()
+    t_gen = time.time() - t0
+    out = {"workload": "configs[4]: %d rows x 39 nnz, %d features, k=32; training feature-parallel x%d (fields %s), batch %d; predict row-sharded" % (
+               n, p, world, [b - a for a, b, _, _ in multi.field_partition(fields, world)], B),
+           "setup_s": round(t_gen, 1)}
+    ctx.sync(); ctx.timer_start()
+    info = shard.minibatch_info(B)
+    out["prep_ms"] = round(ctx.timer_stop_ms(), 1)
+    for name, solver in (("sgd", L.SGD), ("tdap", L.TDAP)):
+        mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=0.0 if name == "sgd" else 1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+        m = L.Model(ctx, mc, c1 - c0, L.F32)
+        m.init_random(0.0, 0.01, 20240603 + c0)
+        sc = mb_solver_cfg(L, solver, n - 1, B)
+        L.train_dev(ctx, m, shard, sc)
+        steps = 2
+        ms = timed(lambda: L.train_dev(ctx, m, shard, sc), steps) / steps
+        m.close()
+        sps = (n - 1) / (ms * 1e-3)
+        # compulsory bytes of the whole job: every rank's update bytes from ITS segment counts (all-reduced) + the forward's
+        segs = [None] * world
+        dist.all_gather_object(segs, info)
+        tot = {"n_segments": sum(q["n_segments"] for q in segs), "n_entries": sum(q["n_entries"] for q in segs)}
+        comp = k1_compulsory_bytes(tot, n, F, 32) + k2_compulsory_bytes(name, tot, 32)
+        out[name] = {"value": round(sps, 1), "unit": "samples/s", "ms_per_step": round(ms, 2), "optimizer_steps_per_epoch": info["n_batches"],
+                     "compulsory_bytes_per_step": int(comp), "achieved_gbs": round(comp / (ms * 1e-3) / 1e9, 1),
+                     "frac_of_n_gpus_peak": round(comp / (ms * 1e-3) / 1e9 / (peak * world), 4),
+                     "survey_model_bytes_per_sample": ALG_BYTES[name](F, k)}
+    shard.close()
+    # predict: rows sharded, model replicated
+    r0, r1 = multi.row_partition(n, world)[rank]
+    pd = L.Data.synth_rows(ctx, r0, r1 - r0, fields, None, 0, 0, 0.1, 20240601)
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k)
+    pm = L.Model(ctx, mc, p, L.F32)
+    pm.init_random(0.0, 0.01, 20240603)
+    for _ in range(2):
+        L.predict_dev(ctx, pm, pd, L.LINK_LOGISTIC)
+    steps = 3
+    ms = timed(lambda: L.predict_dev(ctx, pm, pd, L.LINK_LOGISTIC), steps) / steps
+    pd.close(); pm.close()
+    b_fwd = ALG_BYTES["predict"](F, k)
+    rps = n / (ms * 1e-3)
+    out["predict"] = {"value": round(rps, 1), "unit": "rows/s", "ms_per_step": round(ms, 3), "alg_bytes_per_row": b_fwd,
+                      "achieved_gbs": round(rps * b_fwd / 1e9, 1), "frac_of_n_gpus_peak": round(rps * b_fwd / 1e9 / (peak * world), 4),
+                      "note": "6.4 GB of factor rows per GPU: every gather is a DRAM access, so SURVEY 8(d)'s per-row model is the compulsory traffic here"}
+    return out
+
+
 def run_engine_multi(args, rank, world, local):
-    """N > 1 (torchrun, one rank per GPU): FTRL minibatch epoch FEATURE-parallel with one NCCL all-reduce per batch;
-    predict.FM row-sharded with no collective.  Strong scaling: the configs[1] problem is fixed, N grows."""
+    """N > 1 (torchrun, one rank per GPU): minibatch epochs FEATURE-parallel, the per-batch exchange of the rows' partials inside
+    our own kernels over CUDA-IPC peer windows (NVLink stores + in-kernel flags; FMWR_BENCH_NCCL=1: one NCCL all-reduce per batch
+    instead); predict.FM row-sharded with no collective; ALS / MCMC row-sharded with one statistics exchange per coordinate step.
+    Strong scaling: the configs[1] problem is fixed, N grows."""
     import torch
     import torch.distributed as dist
     from fmwr_b200 import _lib as L
@@ -485,22 +782,23 @@ def run_engine_multi(args, rank, world, local):
     ctx.comm_init(multi.exchange_unique_id(dist, L.Context, rank), rank, world)
     peak, peak_src = measured_peak()
     n, F, k, B = args.rows, 39, args.k, args.batch
+    kp = (k + 3) // 4 * 4
     use_peer = os.environ.get("FMWR_BENCH_NCCL", "0") != "1"
     if use_peer:
         multi.open_peer_windows(dist, ctx, rank, world, B, k)      # per-batch exchange inside our kernels (NVLink), no NCCL call
     field = args.features // F
     p = field * F
-    f0, f1, c0, c1 = multi.field_partition([field] * F, world)[rank]
+    fields = [field] * F
+    f0, f1, c0, c1 = multi.field_partition(fields, world)[rank]
 
-    full = L.Data.synth(ctx, n, [field] * F, None, 0, 1, 0.1, 20240601)
+    full = L.Data.synth(ctx, n, fields, None, 0, 1, 0.1, 20240601)
     data = full.slice_columns(c0, c1)
     full.close()
     mcfg = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=1e-3, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
     model = L.Model(ctx, mcfg, c1 - c0, L.F32)
     model.init_random(0.0, 0.01, 20240603 + c0)
     epoch = n - 1
-    sc = L.SolverCfg(solver=L.FTRL, max_iter=epoch, random_step=1, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0, min_target=-1.0,
-                     max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F32, compat=L.COMPAT_REFERENCE, step_size=-1)
+    sc = mb_solver_cfg(L, L.FTRL, epoch, B)
 
     def timed(fn, steps):
         ctx.sync(); dist.barrier()
@@ -513,6 +811,7 @@ def run_engine_multi(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # device time, max over ranks
         return float(t[0])
 
+    info = data.minibatch_info(B)
     for _ in range(args.warmup):
         L.train_dev(ctx, model, data, sc)
     clocks = ClockSampler(local)
@@ -531,11 +830,52 @@ def run_engine_multi(args, rank, world, local):
     L.check(lib.fmwr_profile_read(ctx.h, buf, C.c_int64(len(buf))))
     prof = parse_profile(buf.value.decode())
     L.check(lib.fmwr_profile_enable(ctx.h, 0))
-    data.close(); model.close()
+    model.close()
+    infos = [None] * world
+    dist.all_gather_object(infos, info)
+    tot = {"n_segments": sum(q["n_segments"] for q in infos), "n_entries": sum(q["n_entries"] for q in infos)}
+
+    # SGD epoch on the same column slices (the solver the north_star's scaling target names)
+    sgd = None
+    if not args.no_solvers:
+        mc_s = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w0=0.0, l1_w1=0.0, l2_w1=1e-3, l1_v=0.0, l2_v=1e-3)
+        ms_ = L.Model(ctx, mc_s, c1 - c0, L.F32)
+        ms_.init_random(0.0, 0.01, 20240603 + c0)
+        sc_s = mb_solver_cfg(L, L.SGD, epoch, B)
+        for _ in range(args.warmup):
+            L.train_dev(ctx, ms_, data, sc_s)
+        steps_s = max(1, min(args.steps, 5))
+        ms_sgd = timed(lambda: L.train_dev(ctx, ms_, data, sc_s), steps_s) / steps_s
+        ms_.close()
+        comp = k1_compulsory_bytes(tot, n, F, kp) + k2_compulsory_bytes("sgd", tot, kp)
+        sgd = {"workload": "configs[1] matrix, SGD minibatch epoch (batch %d), feature-parallel x%d" % (B, world),
+               "value": round(epoch / (ms_sgd * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_sgd, 3),
+               "compulsory_bytes_per_step": int(comp), "frac_of_n_gpus_peak": round(comp / (ms_sgd * 1e-3) / 1e9 / (peak * world), 4)}
+    data.close()
+
+    # correctness carried in the line: N GPUs against one GPU on a prefix, same batches
+    parity = None
+    if not args.no_parity:
+        e64 = multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, L.F64, L.FTRL, args.parity_rows, 8192)
+        e32 = multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, L.F32, L.FTRL, args.parity_rows, 8192)
+        es = multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, L.F64, L.SGD, args.parity_rows, 8192)
+        if rank == 0:
+            parity = {"multi_vs_single_max_rel_err": e64, "ftrl_f32": e32, "sgd_f64": es, "rows": args.parity_rows, "batch": 8192, "epochs": 2,
+                      "what": "max |a-b|/max(1,|b|) over (w0, w, V): FTRL fp64 (headline key), FTRL fp32 (the benchmarked precision; the S_f sums are "
+                              "split by shard, so fp32 differs by rounding), SGD fp64 -- %d GPUs (in-kernel peer exchange) against one GPU" % world,
+                      "asserted": "fp64 < 1e-8, fp32 < 5e-3"}
+        ok = [parity is None or (parity["multi_vs_single_max_rel_err"] < 1e-8 and parity["sgd_f64"] < 1e-8 and parity["ftrl_f32"] < 5e-3)]
+        dist.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed", "parity": parity}), flush=True)
+            ctx.comm_destroy(); ctx.close()
+            dist.barrier(); dist.destroy_process_group()
+            sys.exit(3)
 
     # predict.FM: rows sharded, full model replicated
     r0, r1 = multi.row_partition(n, world)[rank]
-    pdata = L.Data.synth_rows(ctx, r0, r1 - r0, [field] * F, None, 0, 0, 0.1, 20240601)
+    pdata = L.Data.synth_rows(ctx, r0, r1 - r0, fields, None, 0, 0, 0.1, 20240601)
     pmodel = L.Model(ctx, mcfg, p, L.F32)
     pmodel.init_random(0.0, 0.01, 20240603)
     for _ in range(args.warmup):
@@ -544,39 +884,53 @@ def run_engine_multi(args, rank, world, local):
     pred_rps = n * args.steps / (ms_pred * 1e-3)
     pdata.close(); pmodel.close()
 
-    # ALS sweep, rows sharded: configs[2] split into `world` row ranges, one NCCL all-reduce of the field's
-    # statistics per coordinate step; every rank ends the sweep with the same model
-    als = None
+    # ALS / MCMC sweeps, rows sharded: configs[2] / configs[3] split into `world` row ranges, one exchange of the
+    # field's statistics per coordinate step (peer windows, else one NCCL all-reduce); every rank ends the sweep with the same model
+    als = {}
     if not args.no_solvers and args.rows >= 1_000_000:
-        na, fields, ka = 20_000_000, [138493, 26744, 2048], 32
+        na, afields = 20_000_000, [138493, 26744, 2048]
         a0, a1 = multi.row_partition(na, world)[rank]
-        ad = L.Data.synth_rows(ctx, a0, a1 - a0, fields, [0, 1, 0], 0, 3, 0.3, 20240601)
-        am = L.Model(ctx, L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=ka), sum(fields), L.F32)
-        am.init_random(0.0, 0.01, 20240603)
-        asc = L.SolverCfg(solver=L.ALS, max_iter=1, random_step=1, min_target=0.5, max_target=5.0, mode=L.MODE_EXACT, precision=L.F32,
-                          compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=5)
-        for _ in range(args.warmup):
-            L.train_dev(ctx, am, ad, asc)
-        ms_als = timed(lambda: L.train_dev(ctx, am, ad, asc), args.steps) / args.steps
-        pa_, Na_ = sum(fields), 3 * na
-        sweep_bytes = na * (8 + 3 * (12 + 4 * ka)) + 16 * na + 16 * Na_ + ka * (32 * Na_ + 4 * na + 8 * pa_)
-        als = {"workload": "configs[2]: 20000000 ratings x 3 one-hot fields, k=32, one ALS sweep, rows sharded over %d GPUs "
-                           "(one NCCL all-reduce of 2 x |field| f32 per coordinate step, 99 per sweep)" % world,
-               "value": round(na / (ms_als * 1e-3), 1), "unit": "ratings/s", "ms_per_step": round(ms_als, 3),
-               "frac_of_n_gpus_peak": round(sweep_bytes / (ms_als * 1e-3) / 1e9 / (peak * world), 4)}
-        ad.close(); am.close()
+        ad = L.Data.synth_rows(ctx, a0, a1 - a0, afields, [0, 1, 0], 0, 3, 0.3, 20240601)
+        pa_, Na_ = sum(afields), 3 * na
+        for name, solver, ka in (("als", L.ALS, 32), ("mcmc", L.MCMC, 64)):
+            am = L.Model(ctx, L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=ka), pa_, L.F32)
+            am.init_random(0.0, 0.01, 20240603)
+            asc = L.SolverCfg(solver=solver, max_iter=1, random_step=1, min_target=0.5, max_target=5.0, mode=L.MODE_EXACT, precision=L.F32,
+                              compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=5)
+            for _ in range(args.warmup):
+                L.train_dev(ctx, am, ad, asc)
+            steps_a = max(1, min(args.steps, 5))
+            ms_a = timed(lambda: L.train_dev(ctx, am, ad, asc), steps_a) / steps_a
+            sweep_bytes = na * (8 + 3 * (12 + 4 * ka)) + 16 * na + 16 * Na_ + ka * (32 * Na_ + 4 * na + 8 * pa_) + (8 * na if name == "mcmc" else 0)
+            als[name] = {"workload": "configs[%d]: 20000000 ratings x 3 one-hot fields, k=%d, one %s sweep, rows sharded over %d GPUs "
+                                     "(statistics of 2 x |field| f32 exchanged per coordinate step through the peer windows)" % (2 if name == "als" else 3, ka, name.upper(), world),
+                         "value": round(na / (ms_a * 1e-3), 1), "unit": "ratings/s", "ms_per_step": round(ms_a, 3),
+                         "frac_of_n_gpus_peak": round(sweep_bytes / (ms_a * 1e-3) / 1e9 / (peak * world), 4)}
+            am.close()
+        ad.close()
+
+    c5 = None
+    if (world == 8 and not args.no_c5) or os.environ.get("FMWR_BENCH_C5") == "1":
+        c5 = run_c5(L, multi, dist, ctx, args, rank, world, timed, peak)
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
         b_fwd, b_ftrl = ALG_BYTES["predict"](F, k), ALG_BYTES["ftrl"](F, k)
         roof = None
-        if "mb_update_kernel" in prof and prof["mb_update_kernel"][1] > 0:
-            launches, ms = prof["mb_update_kernel"]
-            share = (f1 - f0) / F                                      # rank 0's share of every sample's coordinates
-            ach = epoch * args.steps * (b_ftrl - b_fwd) * share / (ms * 1e-3) / 1e9
-            roof = {"kernel": "mb_update_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                    "traffic": None, "peak_source": peak_src, "launches": launches, "avg_launch_ms": round(ms / launches, 5),
-                    "note": "rank 0 only: %d of %d fields" % (f1 - f0, F), "share_of_step": round(ms / ms_prof, 4)}
+        kn = update_kernel_of(prof)
+        if kn and prof[kn][1] > 0:
+            launches, ms = prof[kn]
+            per_launch = k2_compulsory_bytes("ftrl", info, kp) * (args.steps) / launches     # rank 0's own segments
+            ach = per_launch / (ms / launches * 1e-3) / 1e9
+            roof = {"kernel": kn, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "traffic": None, "alg_bytes_per_launch": int(per_launch), "peak_source": peak_src, "launches": launches, "avg_launch_ms": round(ms / launches, 5),
+                    "note": "rank 0 only: %d of %d fields; compulsory bytes from its real segment counts" % (f1 - f0, F), "share_of_step": round(ms / ms_prof, 4)}
+        step_bytes = k1_compulsory_bytes(tot, n, F, kp) + k2_compulsory_bytes("ftrl", tot, kp)
+        solvers = dict(als)
+        if sgd:
+            solvers["sgd"] = sgd
+        if c5:
+            solvers["c5"] = c5
         out = {
             "metric": METRIC,
             "value": round(train_sps, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -585,17 +939,20 @@ def run_engine_multi(args, rank, world, local):
             "config": {"workload": "configs[1]: Criteo-shaped %d rows x %d nnz, %d features, k=%d, FTRL L1+L2 binary logloss" % (n, F, p, k),
                        "rows": n, "nnz_per_row": F, "features": p, "k": k, "batch_size": B, "mode": "minibatch",
                        "parallelism": "feature-parallel x%d (fields split %s), per minibatch one exchange of rows x (k+4) f32 partials %s; predict row-sharded" % (
-                           world, [b - a for a, b, _, _ in multi.field_partition([field] * F, world)],
+                           world, [b - a for a, b, _, _ in multi.field_partition(fields, world)],
                            "inside the forward/exchange/update kernels (peer-memory stores over NVLink + in-kernel flags)" if use_peer else "by NCCL all-reduce"),
                        "l2_flush": "inputs larger than L2"},
             "roofline": roof,
-            "step_roofline": {"alg_bytes_per_sample": b_ftrl, "achieved": round(train_sps * b_ftrl / 1e9, 1), "unit": "GB/s",
-                              "frac_of_n_gpus_peak": round(train_sps * b_ftrl / 1e9 / (peak * world), 4)},
+            "step_roofline": {"compulsory_bytes_per_step": int(step_bytes), "achieved": round(step_bytes / (ms_train / args.steps * 1e-3) / 1e9, 1), "unit": "GB/s",
+                              "frac_of_n_gpus_peak": round(step_bytes / (ms_train / args.steps * 1e-3) / 1e9 / (peak * world), 4),
+                              "survey_model_bytes_per_sample": b_ftrl},
+            "parity": parity,
+            "multi_vs_single_max_rel_err": parity["multi_vs_single_max_rel_err"] if parity else None,
             "kernels": {name: {"launches": v[0], "ms": round(v[1], 3)} for name, v in prof.items()},
             "predict": {"value": round(pred_rps, 1), "unit": "rows/s", "ms_per_step": round(ms_pred / args.steps, 3),
-                        "roofline": {"bound": "hbm", "achieved": round(pred_rps * b_fwd / 1e9, 1), "unit": "GB/s",
-                                     "frac_of_n_gpus_peak": round(pred_rps * b_fwd / 1e9 / (peak * world), 4)}},
-            "solvers": {"als": als} if als else None,
+                        "roofline": {"bound": "hbm", "survey_model_gbs": round(pred_rps * b_fwd / 1e9, 1), "unit": "GB/s",
+                                     "note": "per-row model, no cache credit (V is L2-resident per GPU at this size): see the N=1 line for the fraction by measured DRAM bytes"}},
+            "solvers": solvers or None,
             "cpu_baseline": None,
             "e2e": None,
             "gpu_launches": int(l1 - l0),
@@ -621,6 +978,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solvers", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--sweep-rows", type=int, default=1_000_000)
+    ap.add_argument("--parity-rows", type=int, default=200_000)
+    ap.add_argument("--c5-rows", type=int, default=100_000_000)
+    ap.add_argument("--c5-features", type=int, default=50_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)

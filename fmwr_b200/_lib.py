@@ -225,6 +225,13 @@ class Data:
         check(lib().fmwr_data_slice_columns(self.h, C.c_int64(c0), C.c_int64(c1), C.byref(h)))
         return Data(self.ctx, h)
 
+    @classmethod
+    def concat_rows(cls, parts):
+        arr = (C.c_void_p * len(parts))(*[q.h for q in parts])
+        h = C.c_void_p()
+        check(lib().fmwr_data_concat_rows(arr, C.c_int32(len(parts)), C.byref(h)))
+        return cls(parts[0].ctx, h)
+
     def close(self):
         if self.h:
             lib().fmwr_data_destroy(self.h)

@@ -241,10 +241,10 @@ bool model_alloc_state(fmwr_model* m, int n_state, int solver, bool warm)
   FMWR_REQUIRE(n_state <= 5, FMWR_ERR_ARG, "too many optimizer state arrays");
   bool have = m->n_state == n_state && m->state_solver == solver;
   for (int i = 0; i < n_state && have; ++i)
-    have = m->sw[i].p && m->sv[i].p && m->sw[i].bytes() == (size_t)m->p * m->esz() && m->sv[i].bytes() == (size_t)m->p * m->kp * m->esz();
+    have = m->sw[i].p && m->sv[i].p && m->sw[i].bytes() == (size_t)(m->p + 4) * m->esz() && m->sv[i].bytes() == (size_t)m->p * m->kp * m->esz();
   if (warm && have) return true;
   for (int i = 0; i < n_state; ++i) {
-    m->sw[i].alloc((size_t)m->p * m->esz());
+    m->sw[i].alloc((size_t)(m->p + 4) * m->esz());      // +4 elements: 16-byte-rounded staging reads (update_tma.cuh)
     m->sv[i].alloc((size_t)m->p * m->kp * m->esz());
     FMWR_CUDA(cudaMemsetAsync(m->sw[i].p, 0, m->sw[i].bytes(), m->ctx->stream));
     FMWR_CUDA(cudaMemsetAsync(m->sv[i].p, 0, m->sv[i].bytes(), m->ctx->stream));
@@ -566,6 +566,15 @@ int fmwr_data_slice_columns(fmwr_data* d, int64_t col_begin, int64_t col_end, fm
   });
 }
 
+int fmwr_data_concat_rows(fmwr_data* const* parts, int32_t n_parts, fmwr_data** out)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(parts && out && n_parts > 0 && parts[0], FMWR_ERR_ARG, "null argument");
+    FMWR_CUDA(cudaSetDevice(parts[0]->ctx->device));
+    *out = data_concat_rows(parts, n_parts);
+  });
+}
+
 // ---- model ---------------------------------------------------------------------------------------
 int fmwr_model_create(fmwr_ctx* ctx, const fmwr_model_cfg* cfg, int64_t p, int32_t precision, fmwr_model** out)
 {
@@ -580,7 +589,7 @@ int fmwr_model_create(fmwr_ctx* ctx, const fmwr_model_cfg* cfg, int64_t p, int32
       m->ctx = ctx; m->cfg = *cfg; m->p = p; m->prec = precision; m->k = cfg->k;
       m->kp = padded_k(cfg->k, precision);
       m->scal.alloc(64 * sizeof(double));
-      m->w.alloc((size_t)p * m->esz());
+      m->w.alloc((size_t)(p + 4) * m->esz());            // +4 elements: 16-byte-rounded staging reads (update_tma.cuh)
       m->v.alloc((size_t)p * m->kp * m->esz());
       FMWR_CUDA(cudaMemsetAsync(m->scal.p, 0, m->scal.bytes(), ctx->stream));
       FMWR_CUDA(cudaMemsetAsync(m->w.p, 0, m->w.bytes(), ctx->stream));

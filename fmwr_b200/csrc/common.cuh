@@ -192,6 +192,7 @@ struct fmwr_data {
   fmwr::DBuf<float> pred32;      // [n]
   fmwr::DBuf<double> pred64;     // [n]
   double min_y = 0, max_y = 0;
+  int64_t min_col_nnz = -1;      // smallest non-zero column count (-1: not computed yet); train_als.cu precision policy
 };
 
 struct fmwr_model {
@@ -355,6 +356,7 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int64_t row_begin, int32_t n_fields, c
                 int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
 void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);
 fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1);
+fmwr_data* data_concat_rows(fmwr_data* const* parts, int n_parts);
 void link_table_eval(fmwr_ctx* ctx, int which, int64_t n, const double* x, double* out);
 
 }  // namespace fmwr

@@ -563,7 +563,7 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   const int64_t m = (int64_t)e1 - e0;
   const int colbits = bits_for((uint64_t)(d->p > 0 ? d->p - 1 : 0));
   const int batchbits = bits_for((uint64_t)(n_batches > 0 ? n_batches - 1 : 0));
-  d->mb_ent_row.alloc(m); d->mb_ent_val.alloc(m);
+  d->mb_ent_row.alloc(m + 8); d->mb_ent_val.alloc(m + 8);      // +8: the dense update kernel stages 16-byte-rounded ranges (update_tma.cuh)
   if (m == 0) {
     d->mb_seg_ptr.alloc(1); d->mb_seg_rec.alloc(1);
     FMWR_CUDA(cudaMemsetAsync(d->mb_seg_ptr.p, 0, 4, ctx->stream));
@@ -586,7 +586,7 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, segid.p + (m - 1), head.p + (m - 1), hp);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   const uint32_t n_seg = hp[0] + hp[1];
-  d->mb_seg_ptr.alloc((size_t)n_seg + 1); d->mb_seg_rec.alloc(n_seg);
+  d->mb_seg_ptr.alloc((size_t)n_seg + 1 + 8); d->mb_seg_rec.alloc(n_seg);
   if (!deferred) data_wait_values(d);
   FMWR_LAUNCH(ctx, mb_emit<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, perm_p, erow.p, deferred ? (const float*)nullptr : d->val.p, e0, m,
               colbits, d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_ent_row.p, d->mb_ent_val.p, n_seg);
@@ -897,6 +897,53 @@ fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1)
       d->y.alloc(n); d->has_labels = true; d->min_y = src->min_y; d->max_y = src->max_y;
       FMWR_CUDA(cudaMemcpyAsync(d->y.p, src->y.p, 4 * n, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) { delete d; throw; }
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ row concatenation
+__global__ void add_offset_u32(const uint32_t* __restrict__ in, int64_t n, uint32_t off, uint32_t* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] + off;
+}
+
+// rows of parts[0], then parts[1], ...: how a shard too large to generate in one piece is assembled (bench.py builds the
+// 100M-row column slices of BASELINE configs[4] from 10M-row chunks)
+fmwr_data* data_concat_rows(fmwr_data* const* parts, int n_parts)
+{
+  FMWR_REQUIRE(n_parts > 0 && parts && parts[0], FMWR_ERR_ARG, "nothing to concatenate");
+  fmwr_ctx* ctx = parts[0]->ctx;
+  int64_t n = 0, nnz = 0;
+  for (int i = 0; i < n_parts; ++i) {
+    FMWR_REQUIRE(parts[i] && parts[i]->ctx == ctx && parts[i]->p == parts[0]->p && parts[i]->has_labels == parts[0]->has_labels, FMWR_ERR_SHAPE,
+                 "parts must share context, feature count and label presence");
+    n += parts[i]->n; nnz += parts[i]->nnz;
+  }
+  FMWR_REQUIRE(nnz < (int64_t)0xffffffffll && n < (int64_t)0xffffffffll, FMWR_ERR_UNSUPPORTED, "dimensions must fit 32-bit indices per device shard");
+  fmwr_data* d = new fmwr_data();
+  try {
+    d->ctx = ctx; d->n = n; d->p = parts[0]->p; d->nnz = nnz; d->has_labels = parts[0]->has_labels;
+    d->rowptr.alloc(n + 1); d->col.alloc(nnz); d->val.alloc(nnz);
+    if (d->has_labels) d->y.alloc(n);
+    d->min_y = INFINITY; d->max_y = -INFINITY;
+    int64_t r0 = 0, e0 = 0;
+    for (int i = 0; i < n_parts; ++i) {
+      fmwr_data* q = parts[i];
+      if (q->n > 0) FMWR_LAUNCH(ctx, add_offset_u32, ceil_div(q->n, 256), 256, 0, q->rowptr.p, q->n, (uint32_t)e0, d->rowptr.p + r0);
+      if (q->nnz > 0) {
+        FMWR_CUDA(cudaMemcpyAsync(d->col.p + e0, q->col.p, 4 * q->nnz, cudaMemcpyDeviceToDevice, ctx->stream));
+        FMWR_CUDA(cudaMemcpyAsync(d->val.p + e0, q->val.p, 4 * q->nnz, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      if (d->has_labels && q->n > 0) {
+        FMWR_CUDA(cudaMemcpyAsync(d->y.p + r0, q->y.p, 4 * q->n, cudaMemcpyDeviceToDevice, ctx->stream));
+        d->min_y = std::min(d->min_y, q->min_y); d->max_y = std::max(d->max_y, q->max_y);
+      }
+      r0 += q->n; e0 += q->nnz;
+    }
+    const uint32_t last = (uint32_t)nnz;
+    FMWR_CUDA(cudaMemcpyAsync(d->rowptr.p + n, &last, 4, cudaMemcpyHostToDevice, ctx->stream));
     FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   } catch (...) { delete d; throw; }
   return d;

@@ -1,7 +1,8 @@
 // predict.FM / error-cache forward pass: replaces Model::predict_batch + predict_prob + the
 // regression clamp (reference src/core/Model.h:106-180, src/FM.cpp:197-211).
-#include "forward.cuh"
+#include "forward_stream.cuh"
 
+#include <algorithm>
 namespace fmwr {
 
 template <class T, int LPR, int CH, int TEAM>
@@ -74,6 +75,19 @@ void forward_launch(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, int link, double
   // shape checks of Model::predict_batch (reference src/core/Model.h:112-113)
   FMWR_REQUIRE(d->p == m->p, FMWR_ERR_SHAPE, "number of input's features is not correct...");
   if (d->n == 0) return;
+  if (stream_forward_ok(m, d->nnz, d->n)) {
+    // fp32, 32-float factor rows, long rows: the software-pipelined stream kernel (forward_stream.cuh) + elementwise link
+    d->pred64.ensure(d->n);
+    d->pred_prec = FMWR_F64;
+    SfArgs a;
+    memset(&a, 0, sizeof a);
+    a.rowptr = d->rowptr.p; a.col = d->col.p; a.val = d->val.p; a.w = (const float*)m->w.p; a.v = (const float*)m->v.p;
+    a.scal = (const double*)m->scal.p; a.k0 = m->cfg.keep_w0; a.k1 = m->cfg.keep_w1; a.row_begin = 0; a.rows = d->n; a.out = d->pred64.p;
+    const int grid = stream_grid(ctx, d->n, &a.rpg);
+    FMWR_LAUNCH(ctx, forward_stream_kernel<SF_PREDICT>, grid, 256, 0, a);
+    if (link != FMWR_LINK_NONE) FMWR_LAUNCH(ctx, link_inplace_kernel, ceil_div(d->n, 256), 256, 0, d->pred64.p, d->n, link, lo, hi, ctx->pn_table.p);
+    return;
+  }
   FwdLaunch f{ctx, m, d, link, lo, hi};
   if (m->prec == FMWR_F64) dispatch_layout<double>(m->kp, f);
   else dispatch_layout<float>(m->kp, f);

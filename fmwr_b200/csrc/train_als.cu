@@ -1524,10 +1524,96 @@ static void train_als_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_s
   if (tr) { tr->n_rec = std::min(n_rec, (int)tr->max_rec); tr->convergent = 0; tr->iters_done = sweep; }
 }
 
+// ---- precision policy ------------------------------------------------------------------------------------------------------
+// fp32 ALS / MCMC is a throughput mode; two situations make it miss the reference's fp64 results by more than rounding, and in
+// both the sweep runs in fp64 on a shadow model instead (the fp32 handle gets the result back):
+//   * MCMC classification: the truncated-normal augmentation (reference MCMC_ALS_Learner.h:531-541) takes a data-dependent
+//     number of rejection steps -- fp32 noise in e changes which draws are consumed;
+//   * a feature with one or two non-zeros: h = x q - x^2 v cancels to rounding noise there and var = 1/(lambda + alpha sum h^2)
+//     amplifies it (long-tail one-hot data).
+__global__ void col_count_kernel(const uint32_t* __restrict__ col, int64_t nnz, uint32_t* __restrict__ cnt)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) atomicAdd(cnt + col[i], 1u);
+}
+__global__ void col_count_min_kernel(const uint32_t* __restrict__ cnt, int64_t p, uint32_t* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t c = 0xffffffffu;
+  if (i < p && cnt[i] > 0u) c = cnt[i];
+  for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
+  if ((threadIdx.x & 31) == 0 && c != 0xffffffffu) atomicMin(out, c);
+}
+
+static bool has_thin_columns(fmwr_ctx* ctx, fmwr_data* d)
+{
+  if (d->min_col_nnz < 0) {
+    DBuf<uint32_t> cnt, mn;
+    cnt.alloc(std::max<int64_t>(d->p, 1)); mn.alloc(1);
+    cnt.zero(ctx->stream);
+    FMWR_CUDA(cudaMemsetAsync(mn.p, 0xff, 4, ctx->stream));
+    if (d->nnz > 0) FMWR_LAUNCH(ctx, col_count_kernel, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->nnz, cnt.p);
+    if (d->p > 0) FMWR_LAUNCH(ctx, col_count_min_kernel, ceil_div(d->p, 256), 256, 0, cnt.p, d->p, mn.p);
+    uint32_t h = 0;
+    FMWR_CUDA(cudaMemcpyAsync(&h, mn.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    d->min_col_nnz = h == 0xffffffffu ? (1ll << 40) : (int64_t)h;
+  }
+  uint32_t flag = d->min_col_nnz <= 2 ? 1u : 0u;
+  if (ctx->nccl_comm && ctx->world > 1) {
+    // row shards: a shard sees only its part of a column, so "thin here" over-approximates "thin overall"; what matters is
+    // that every rank takes the same branch
+    DBuf<uint32_t> f;
+    f.alloc(1);
+    FMWR_CUDA(cudaMemcpyAsync(f.p, &flag, 4, cudaMemcpyHostToDevice, ctx->stream));
+    comm_allreduce_max_u32(ctx, f.p, 1);
+    FMWR_CUDA(cudaMemcpyAsync(&flag, f.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return flag != 0u;
+}
+
+template <class A, class B>
+__global__ void repack_rows_kernel(const A* __restrict__ src, int kp_src, B* __restrict__ dst, int kp_dst, int64_t p, int k)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p * kp_dst) return;
+  const int f = (int)(i % kp_dst);
+  const int64_t j = i / kp_dst;
+  dst[i] = f < k ? (B)src[j * kp_src + f] : B(0);
+}
+
+int als_effective_precision(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s)
+{
+  if (m->prec == FMWR_F64) return FMWR_F64;
+  if (getenv("FMWR_ALS_F32_STRICT")) return FMWR_F32;       // diagnostics: measure what fp32 does on such data
+  if (s->solver == FMWR_MCMC && m->cfg.task == FMWR_CLASSIFICATION) return FMWR_F64;
+  return has_thin_columns(ctx, d) ? FMWR_F64 : FMWR_F32;
+}
+
 void train_als_mcmc(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
 {
-  if (m->prec == FMWR_F64) train_als_t<double>(ctx, m, d, s, tr);
-  else train_als_t<float>(ctx, m, d, s, tr);
+  if (m->prec == FMWR_F64) { train_als_t<double>(ctx, m, d, s, tr); return; }
+  if (als_effective_precision(ctx, m, d, s) == FMWR_F32) { train_als_t<float>(ctx, m, d, s, tr); return; }
+  // fp64 shadow of the fp32 handle
+  fmwr_model* sh = nullptr;
+  FMWR_REQUIRE(fmwr_model_create(ctx, &m->cfg, m->p, FMWR_F64, &sh) == 0, FMWR_ERR_CUDA, fmwr_last_error());
+  try {
+    const int64_t p = m->p;
+    FMWR_CUDA(cudaMemcpyAsync(sh->scal.p, m->scal.p, 8 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (p > 0) {
+      FMWR_LAUNCH(ctx, (repack_rows_kernel<float, double>), ceil_div(p, 256), 256, 0, (const float*)m->w.p, 1, (double*)sh->w.p, 1, p, 1);
+      FMWR_LAUNCH(ctx, (repack_rows_kernel<float, double>), ceil_div(p * sh->kp, 256), 256, 0, (const float*)m->v.p, m->kp, (double*)sh->v.p, sh->kp, p, m->k);
+    }
+    train_als_t<double>(ctx, sh, d, s, tr);
+    FMWR_CUDA(cudaMemcpyAsync(m->scal.p, sh->scal.p, 8 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (p > 0) {
+      FMWR_LAUNCH(ctx, (repack_rows_kernel<double, float>), ceil_div(p, 256), 256, 0, (const double*)sh->w.p, 1, (float*)m->w.p, 1, p, 1);
+      FMWR_LAUNCH(ctx, (repack_rows_kernel<double, float>), ceil_div(p * m->kp, 256), 256, 0, (const double*)sh->v.p, sh->kp, (float*)m->v.p, m->kp, p, m->k);
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) { fmwr_model_destroy(sh); throw; }
+  fmwr_model_destroy(sh);
 }
 
 }  // namespace fmwr

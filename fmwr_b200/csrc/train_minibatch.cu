@@ -14,7 +14,7 @@
 // K2 does not use atomics: the batch's non-zeros are pre-sorted by (batch, feature, row)
 // (data.cu: minibatch_build), so one lane group owns one (batch, feature) segment, reduces its rows'
 // gradients in registers and writes the coordinate once -- deterministic and contention-free.
-#include "forward.cuh"
+#include "forward_stream.cuh"
 #include "coord.cuh"
 
 #include <cmath>
@@ -208,26 +208,27 @@ template <class T, int SOLVER>
 __device__ __forceinline__ void mb_intercept(const MbUpdArgs<T>& a)
 {
   const SolverParams<T>& sp = a.sp;
-  __shared__ double red[8];
+  __shared__ double red[32];
   double acc = 0.0;
+  const int nt = (int)blockDim.x;
   {
     constexpr int UN = 16;
     int r = threadIdx.x;
-    for (; r + (UN - 1) * 256 < a.rows; r += UN * 256) {
+    for (; r + (UN - 1) * nt < a.rows; r += UN * nt) {
       T t[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) t[u] = a.mult[(size_t)(r + u * 256) * a.mult_stride];
+      for (int u = 0; u < UN; ++u) t[u] = a.mult[(size_t)(r + u * nt) * a.mult_stride];
 #pragma unroll
       for (int u = 0; u < UN; ++u) acc += (double)t[u];
     }
-    for (; r < a.rows; r += 256) acc += (double)a.mult[(size_t)r * a.mult_stride];
+    for (; r < a.rows; r += nt) acc += (double)a.mult[(size_t)r * a.mult_stride];
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double gsum = 0;
-    for (int i = 0; i < 8; ++i) gsum += red[i];
+    for (int i = 0; i < (nt >> 5); ++i) gsum += red[i];
     double* sc = a.scal;
     if (SOLVER == FMWR_SGD) {
       if (a.k0) sc[0] -= (double)sp.lr * (gsum / (double)a.rows + (double)sp.reg_w0 * sc[0]);
@@ -465,12 +466,219 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 && CH == 1) ? K2Tune<SOLV
   }
 }
 
+}  // namespace fmwr
+#include "update_tma.cuh"
+namespace fmwr {
+
+// ---- K2, dense variant (update_tma.cuh): producer warp + 8 consumer warps over a ring of TMA-filled stages ----------------
+template <class T, int LPR, int CH, int SOLVER, bool L1, int TS, int NS, int MINB>
+__global__ void __launch_bounds__(TM_THREADS, MINB) mb_update_tma_kernel(MbUpdArgs<T> a, int hint)
+{
+  typedef TmGeom<T, LPR, CH, SOLVER, L1, TS, NS> G;
+  constexpr int GRP = 32 / LPR;                         // lane groups (segments) per warp
+  constexpr int NSTW = G::NST;
+  extern __shared__ __align__(128) unsigned char tm_smem[];
+  unsigned char* stages = tm_smem;
+  uint32_t* hdr_all = reinterpret_cast<uint32_t*>(tm_smem + NS * G::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tm_smem + NS * G::STAGE_BYTES + NS * G::HDR_WORDS * 4);   // full[NS], done[NS]
+  if (a.peer) peer_wait(a.pa, PEER_FLAG2, PEER_EPOCH2);
+  if (blockIdx.x == 0) { mb_intercept<T, SOLVER>(a); return; }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(bars + s), 1u); mbar_init(smem_u32(bars + NS + s), TM_CONS_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t n_seg = a.seg_end - a.seg_begin;
+  const uint32_t n_tiles = (n_seg + TS - 1) / TS;
+  const uint32_t first = blockIdx.x - 1, stride = gridDim.x - 1;
+  const uint32_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0u;
+
+  if (warp == TM_CONS_WARPS) {
+    // ================================ producer: loads and write-backs, lane 0 only =================================
+    if (lane != 0) return;
+    const uint64_t pol_th = l2_policy(hint ? 2 : 0);     // theta rows are re-read by the next batch's forward: keep
+    const uint64_t pol_st = l2_policy(hint ? 1 : 0);     // optimizer state and the batch's lists are touched once per batch: stream
+    uint32_t wb_c0[NS], wb_rows[NS];                      // pending write-back of each stage (rows == 0: none)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { wb_c0[s] = 0u; wb_rows[s] = 0u; }
+    auto write_back = [&](int s) {
+      unsigned char* st = stages + (size_t)s * G::STAGE_BYTES;
+      const uint32_t c0 = wb_c0[s], nr = wb_rows[s];
+      if (nr) {
+        const uint32_t bytes = nr * G::ROWB;
+        bulk_s2g(reinterpret_cast<unsigned char*>(a.v) + (size_t)c0 * G::ROWB, smem_u32(st + G::OFF_PAR), bytes, pol_th);
+        if (G::USE_STATE) {
+#pragma unroll
+          for (int i = 0; i < NSTW; ++i)
+            bulk_s2g(reinterpret_cast<unsigned char*>(a.sv[i]) + (size_t)c0 * G::ROWB, smem_u32(st + G::OFF_PAR + (i + 1) * G::RMAX * G::ROWB), bytes, pol_st);
+        }
+        bulk_commit();
+        bulk_wait_read0();                                 // the stage may be refilled once the stores have READ it
+      }
+    };
+    // the tile's extent (first / last feature, first / one-past-last entry) comes from four scattered words: fetched one
+    // tile ahead so their latency never sits between a freed stage and its refill
+    uint32_t d_c0 = 0u, d_c1 = 0u, d_e0 = 0u, d_e1 = 0u;
+    auto fetch_desc = [&](uint32_t i) {
+      if (i >= my_tiles) return;
+      const uint32_t s0 = a.seg_begin + (first + i * stride) * TS;
+      const uint32_t ns = min((uint32_t)TS, a.seg_end - s0);
+      d_c0 = __ldg(&a.seg_rec[s0].x); d_c1 = __ldg(&a.seg_rec[s0 + ns - 1].x);
+      d_e0 = __ldg(a.seg_ptr + s0); d_e1 = __ldg(a.seg_ptr + s0 + ns);
+    };
+    fetch_desc(0);
+    for (uint32_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i % NS);
+      unsigned char* st = stages + (size_t)s * G::STAGE_BYTES;
+      uint32_t* hdr = hdr_all + s * G::HDR_WORDS;
+      const uint32_t c0 = d_c0, c1 = d_c1, e0 = d_e0, e1 = d_e1;
+      fetch_desc(i + 1);
+      if (i >= NS) {
+        mbar_wait(smem_u32(bars + NS + s), ((i / NS) - 1) & 1u);     // consumers are done with the tile that lived here
+        write_back(s);
+      }
+      const uint32_t t = first + i * stride;
+      const uint32_t s0 = a.seg_begin + t * TS;
+      const uint32_t ns = min((uint32_t)TS, a.seg_end - s0);
+      const uint32_t nrows = c1 - c0 + 1u;
+      const uint32_t s0a = s0 & ~3u, e0a = e0 & ~3u, c0a = c0 & ~3u;
+      const uint32_t nsp = ((s0 + ns + 1u) - s0a + 3u) & ~3u;          // seg_ptr words [s0a, s0 + ns], rounded to 16 bytes
+      const uint32_t nen = (e1 - e0a + 3u) & ~3u;
+      const uint32_t nw = ((c1 + 1u) - c0a + 3u) & ~3u;
+      const bool dense = nrows <= (uint32_t)G::RMAX && nen <= (uint32_t)G::EMAX + 8u;
+      hdr[0] = dense ? 1u : 0u; hdr[1] = c0; hdr[2] = nrows; hdr[3] = s0 - s0a; hdr[4] = e0; hdr[5] = e0 - e0a; hdr[6] = c0 - c0a; hdr[7] = ns;
+      const uint32_t full = smem_u32(bars + s);
+      uint32_t tx = ns * 16u + nsp * 4u;
+      bulk_g2s(smem_u32(st + G::OFF_REC), a.seg_rec + s0, ns * 16u, full, pol_st);
+      bulk_g2s(smem_u32(st + G::OFF_SEGP), a.seg_ptr + s0a, nsp * 4u, full, pol_st);
+      wb_rows[s] = 0u;
+      if (dense) {
+        if (nen) {
+          bulk_g2s(smem_u32(st + G::OFF_EROW), a.ent_row + e0a, nen * 4u, full, pol_st);
+          bulk_g2s(smem_u32(st + G::OFF_EVAL), a.ent_val + e0a, nen * 4u, full, pol_st);
+          tx += 2u * nen * 4u;
+        }
+        const uint32_t pbytes = nrows * G::ROWB;
+        bulk_g2s(smem_u32(st + G::OFF_PAR), reinterpret_cast<const unsigned char*>(a.v) + (size_t)c0 * G::ROWB, pbytes, full, pol_th);
+        tx += pbytes;
+        if (G::USE_STATE) {
+#pragma unroll
+          for (int k = 0; k < NSTW; ++k) {
+            bulk_g2s(smem_u32(st + G::OFF_PAR + (k + 1) * G::RMAX * G::ROWB), reinterpret_cast<const unsigned char*>(a.sv[k]) + (size_t)c0 * G::ROWB, pbytes, full, pol_st);
+            tx += pbytes;
+          }
+        }
+        if (a.k1) {
+          const uint32_t wbytes = nw * (uint32_t)sizeof(T);
+          bulk_g2s(smem_u32(st + G::OFF_W), a.w + c0a, wbytes, full, pol_th);
+          tx += wbytes;
+          if (G::USE_STATE) {
+#pragma unroll
+            for (int k = 0; k < NSTW; ++k) {
+              bulk_g2s(smem_u32(st + G::OFF_W + (k + 1) * (G::RMAX + 8) * (int)sizeof(T)), a.sw[k] + c0a, wbytes, full, pol_st);
+              tx += wbytes;
+            }
+          }
+        }
+        wb_c0[s] = c0; wb_rows[s] = nrows;
+      }
+      mbar_arrive_expect_tx(full, tx);
+    }
+    // drain: write back what the consumers are still working on
+    for (uint32_t i = (my_tiles > (uint32_t)NS ? my_tiles - NS : 0u); i < my_tiles; ++i) {
+      const int s = (int)(i % NS);
+      mbar_wait(smem_u32(bars + NS + s), (i / NS) & 1u);
+      write_back(s);
+    }
+    bulk_wait0();
+    return;
+  }
+
+  // ==================================== consumers ====================================================================
+  const int g = lane / LPR, l = lane % LPR;
+  for (uint32_t i = 0; i < my_tiles; ++i) {
+    const int s = (int)(i % NS);
+    unsigned char* st = stages + (size_t)s * G::STAGE_BYTES;
+    const uint32_t* hdr = hdr_all + s * G::HDR_WORDS;
+    mbar_wait(smem_u32(bars + s), (i / NS) & 1u);
+    const int ns = (int)hdr[7];
+    if (hdr[0]) {
+      for (int j = warp * GRP + g; j < ns; j += TM_CONS_WARPS * GRP) seg_dense<T, LPR, CH, SOLVER, L1, G>(a, st, hdr, j, l);
+      fence_proxy_async();                               // this thread's shared-memory writes -> visible to the bulk stores
+    } else {
+      // sparse tile: the gather path of mb_update_kernel, records and offsets from the stage
+      for (int j0 = warp * GRP; j0 < ns; j0 += TM_CONS_WARPS * GRP) {      // warp-uniform trip count (seg_finish shuffles)
+        const int j = j0 + g;
+        const bool live = j < ns;
+        const uint4 rec = live ? reinterpret_cast<const uint4*>(st + G::OFF_REC)[j] : make_uint4(0u, 0u, 0xffffffffu, 0u);
+        const uint32_t eb = live ? reinterpret_cast<const uint32_t*>(st + G::OFF_SEGP)[hdr[3] + j] : 0u;
+        SegStage<T, CH, NSTW> sg;
+        seg_issue<T, LPR, CH, SOLVER, L1>(a, rec, eb, l, live, sg);
+        seg_finish<T, LPR, CH, SOLVER, L1>(a, g, l, sg);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(bars + NS + s));
+  }
+}
+
 template <class T>
 struct MbLaunch {
   fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; const fmwr_solver_cfg* s;
   int64_t row_begin; int rows; T* mult; T* Scache; MbUpdArgs<T> ua; int phase;   // phase 0: K1, 1: K2
   int s_stride; int partial; PeerArgs pa;
   template <class TT, int LPR, int CH, int TEAM> void k1();
+  void k1_stream()
+  {
+    SfArgs a;
+    memset(&a, 0, sizeof a);
+    a.rowptr = d->rowptr.p; a.col = d->col.p; a.val = d->val.p; a.y = d->y.p; a.w = (const float*)m->w.p; a.v = (const float*)m->v.p;
+    a.scal = (const double*)m->scal.p; a.k0 = m->cfg.keep_w0; a.k1 = m->cfg.keep_w1; a.task = m->cfg.task;
+    a.lo = (float)s->min_target; a.hi = (float)s->max_target; a.row_begin = row_begin; a.rows = rows;
+    a.mult = (float*)mult; a.Scache = (float*)Scache; a.s_stride = s_stride; a.pa = pa;
+    const int grid = stream_grid(ctx, rows, &a.rpg);
+    if (partial == 2) FMWR_LAUNCH(ctx, forward_stream_kernel<SF_PARTIAL_PEER>, grid, 256, 0, a);
+    else if (partial == 1) FMWR_LAUNCH(ctx, forward_stream_kernel<SF_PARTIAL>, grid, 256, 0, a);
+    else FMWR_LAUNCH(ctx, forward_stream_kernel<SF_TRAIN>, grid, 256, 0, a);
+  }
+  template <class TT, int LPR, int CH, int SOLVER, bool L1, int TS, int NS, int MINB>
+  void tma_launch(uint32_t nseg)
+  {
+    typedef TmGeom<TT, LPR, CH, SOLVER, L1, TS, NS> G;
+    static int occ = 0;                                   // resident CTAs per SM of this instantiation
+    if (!occ) {
+      FMWR_CUDA(cudaFuncSetAttribute(mb_update_tma_kernel<TT, LPR, CH, SOLVER, L1, TS, NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+      int o = 0;
+      FMWR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mb_update_tma_kernel<TT, LPR, CH, SOLVER, L1, TS, NS, MINB>, TM_THREADS, (size_t)G::SMEM_BYTES));
+      occ = o < 1 ? 1 : o;
+    }
+    const int hint = getenv("FMWR_K2_HINT") ? atoi(getenv("FMWR_K2_HINT")) : 0;
+    const int ctas = getenv("FMWR_K2_CTAS") ? atoi(getenv("FMWR_K2_CTAS")) : 0;
+    const int64_t n_tiles = ceil_div64((int64_t)nseg, TS);
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * (ctas > 0 ? std::min(ctas, occ) : occ)) + 1;     // +1: the intercept block
+    FMWR_LAUNCH(ctx, (mb_update_tma_kernel<TT, LPR, CH, SOLVER, L1, TS, NS, MINB>), grid, TM_THREADS, (size_t)G::SMEM_BYTES, ua, hint);
+  }
+  template <class TT, int LPR, int CH>
+  void tma(uint32_t nseg)
+  {
+    switch (s->solver) {
+      case FMWR_SGD:
+        if (ua.sp.l1) tma_launch<TT, LPR, CH, FMWR_SGD, true, 32, 3, 3>(nseg);
+        else tma_launch<TT, LPR, CH, FMWR_SGD, false, 32, 3, 3>(nseg);
+        break;
+      case FMWR_FTRL: {
+        const int var = getenv("FMWR_K2_VAR") ? atoi(getenv("FMWR_K2_VAR")) : 0;
+        // measured on configs[1] (profiles/r02_summary.md): 32-segment tiles, 3 stages, 3 CTAs/SM 168 us per batch; 2 stages 180;
+        // 4 CTAs/SM (56 registers, spills) 204; 64-segment tiles x 2 stages x 2 CTAs 184; the gather kernel 178
+        if (var == 1) tma_launch<TT, LPR, CH, FMWR_FTRL, false, 32, 4, 2>(nseg);
+        else if (var == 2) tma_launch<TT, LPR, CH, FMWR_FTRL, false, 16, 4, 3>(nseg);
+        else tma_launch<TT, LPR, CH, FMWR_FTRL, false, 32, 3, 3>(nseg);
+        break;
+      }
+      default: tma_launch<TT, LPR, CH, FMWR_TDAP, false, 32, 2, 2>(nseg); break;
+    }
+  }
   template <class TT, int LPR, int CH>
   void run()
   {
@@ -480,6 +688,7 @@ struct MbLaunch {
       FMWR_LAUNCH(ctx, (mb_exchange_kernel<TT, LPR, CH>), xgrid, 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
                   m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, s_stride, pa);
     } else if (phase == 0) {
+      if (sizeof(TT) == 4 && stream_forward_ok(m, d->nnz, d->n)) { k1_stream(); return; }
       const int tm = team_mode(d->nnz, d->n, LPR);
       if (tm == 1) k1<TT, LPR, CH, LPR>();
       else if (tm == 2) k1<TT, LPR, CH, (LPR <= 8 ? 16 : 32)>();
@@ -494,6 +703,10 @@ struct MbLaunch {
         // feature-parallel ranks hold a fraction of the segments: there the one-shot grid measured faster (N = 2/4/8)
         if (persist > 0 && !(ctx->nccl_comm && ctx->world > 1)) grid = std::min(grid, ctx->sm_count * resident * persist + 1);
       }
+      // dense variant (update_tma.cuh): fp32, one 16-byte vector per lane, rows of at most 128 bytes; FMWR_K2_GATHER=1 keeps the
+      // original gather kernel for every tile
+      const bool no_tma = getenv("FMWR_K2_GATHER") != nullptr;     // read per launch: tests flip it between calls
+      if (sizeof(TT) == 4 && CH == 1 && LPR <= 8 && !no_tma) { tma<TT, (LPR <= 8 ? LPR : 8), (CH == 1 ? CH : 1)>(nseg); return; }
       switch (s->solver) {
         case FMWR_SGD:
           if (ua.sp.l1) FMWR_LAUNCH(ctx, (mb_update_kernel<TT, LPR, CH, FMWR_SGD, true>), grid, 256, 0, ua);

@@ -163,6 +163,10 @@ int fmwr_data_synth_rows(fmwr_ctx* ctx, int64_t row_begin, int64_t n_rows, int32
 /* column slice [col_begin, col_end) of a dataset, ids rebased to 0 (feature-parallel sharding; labels are shared) */
 int fmwr_data_slice_columns(fmwr_data* d, int64_t col_begin, int64_t col_end, fmwr_data** out);
 
+/* rows of parts[0], parts[1], ... stacked into one dataset (same feature count; a shard too large to generate in one piece is
+ * assembled from row chunks this way) */
+int fmwr_data_concat_rows(fmwr_data* const* parts, int32_t n_parts, fmwr_data** out);
+
 /* ---- multi-GPU (one process per GPU): feature-parallel minibatch training, SURVEY section 8e ----
  * Rank 0 calls fmwr_comm_unique_id and ships the 128 bytes to the other ranks with whatever the host has
  * (bench.py: torch.distributed); every rank then calls fmwr_comm_init.  Afterwards fmwr_train_dev in

@@ -1,6 +1,6 @@
 """ALS / MCMC coordinate-pass parity against the oracle (reference src/solver/MCMC_ALS_Learner.h), exact
 Gauss-Seidel order (nthreads = 1).  Tolerances: 1e-4 relative (north star) for fp32, 1e-8 for fp64;
-MCMC with identical injected RNG streams 1e-4 / 1e-8; native RNG statistically (RMSE within 0.5 %... see below)."""
+MCMC with identical injected RNG streams 1e-4 / 1e-8; native RNG: posterior-mean RMSE within 0.5 %."""
 import numpy as np
 import pytest
 
@@ -71,9 +71,10 @@ def test_als_matches_oracle(gpu_ctx, port, task, enable_v, layout):
     rw0, rw, rv, rt = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v, max_rec=20)
     # fields_odd has ~1.2 non-zeros per feature in its wide field: 1/(alpha*A) amplifies the summation-order noise
     t64 = 1e-6 if layout == "fields_odd" else 1e-8
-    # (fp32 is not compared on fields_odd: with one non-zero per feature h = x q - x^2 v cancels to rounding noise and
-    # 1/(alpha * sum h^2) blows it up -- the fp64 instantiation is the parity instrument there)
-    for prec, tol in ((L.F64, t64),) + (((L.F32, 1e-4),) if layout != "fields_odd" else ()):
+    # fp32 handles: on fields_odd (features with one or two non-zeros: h = x q - x^2 v cancels to rounding noise and
+    # 1/(alpha * sum h^2) blows it up) the engine runs the sweep in fp64 on a shadow model and hands the result back
+    # (train_als.cu: precision policy), so the fp32 handle meets the north star's 1e-4 on every layout
+    for prec, tol in ((L.F64, t64), (L.F32, 1e-4)):
         (gw0, gw, gv), gt, _ = gpu_als(gpu_ctx, prec, ds, y, task, L.ALS, k, w0, w, v, sweeps, enable_v, l2_w0=0.1, step_size=1,
                                        metric=L.LL if task == O.CLASSIFICATION else L.RMSE)
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol, (prec, relerr(gw0, rw0), relerr(gw, rw), relerr(gv, rv))
@@ -110,41 +111,66 @@ def test_mcmc_injected_streams_match_oracle(gpu_ctx, port, task, enable_v):
     pos = port.stream_pos()
     port.set_streams(None, None, None)
     assert pos["overrun"] == 0
-    for prec, tol in ((L.F64, 1e-8), (L.F32, 1e-4 if task == O.REGRESSION else 5e-3)):
+    # fp32 + classification runs in fp64 internally (the truncated-normal rejection loops are data-dependent): 1e-4 either way
+    for prec, tol in ((L.F64, 1e-8), (L.F32, 1e-4)):
         (gw0, gw, gv), _, _ = gpu_als(gpu_ctx, prec, ds, y, task, L.MCMC, k, w0, w, v, sweeps, enable_v, l2_w0=0.1,
                                       streams=(normals, gammas, rands))
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol, (prec, relerr(gw0, rw0), relerr(gw, rw), relerr(gv, rv))
 
 
-def test_mcmc_native_rng_statistical(gpu_ctx, port):
-    # native counter-based RNG vs the oracle fed numpy streams: posterior-mean predictions (averaged over sweeps,
-    # outside both codes) must give RMSE within a few % of each other on a planted regression
+def test_mcmc_native_rng_posterior_mean(gpu_ctx, port):
+    """north star: under the native RNG the posterior-mean RMSE matches within 0.5 %.  The reference returns the LAST draw
+    (MCMC_ALS_Learner.h:98-127), so the posterior mean is formed outside both codes, identically: every sweep's model is
+    snapshotted by the tracker (step_size = 1), predictions of the post-burn-in snapshots are averaged, then scored.
+    Oracle: numpy streams through the injection hooks; engine: its own counter-based generator (seed only)."""
     rng = np.random.default_rng(4)
     ds = fields_ds(6000, [60, 40], 11, value_mode=0)
     n, p, k = ds["n"], ds["p"], 4
     score = synth.planted_scores_fast(ds["rowptr"], ds["col"], ds["val"], p, k=4, seed=12, scale=0.5)
     y = (score + 0.1 * rng.standard_normal(n)).astype(np.float32)
     w = np.zeros(p); v = rng.normal(0, 0.1, (p, k))
-    sweeps = 30
-    cfg = O.make_cfg(task=O.REGRESSION, solver=O.MCMC, k=k, max_iter=sweeps, enable_v=1, min_target=float(y.min()), max_target=float(y.max()))
-    port.set_streams(rng.standard_normal(2_000_000), rng.gamma(3000.0, 1.0, 10000) , None)
-    # gamma shapes differ per draw ((1+n)/2 vs (1+p+1)/2); the oracle takes unit-scale draws as given, so feed draws
-    # of the right order of magnitude per slot: alpha first, then lambda_w, then k lambda_v per sweep
+    sweeps, burn = 80, 30
+    cfgp = O.make_cfg(task=O.REGRESSION, k=k)
+
+    def posterior_mean_rmse(snaps):
+        acc = np.zeros(n)
+        for (sw0, sw, sv) in snaps:
+            acc += np.clip(port.predict(cfgp, n, p, ds["rowptr"], ds["col"], ds["val"], sw0, sw, sv, 0), float(y.min()), float(y.max()))
+        return float(np.sqrt(np.mean((acc / len(snaps) - y) ** 2)))
+
+    # oracle side: one sweep per call, warm-started from the previous draw, so every draw is visible (the hyper-parameters
+    # alpha / lambda / mu restart each call exactly as Learner::init does on fm.update; both sides are driven the same way)
     per = 2 + k
-    g = np.empty(sweeps * per)
+    ow0, ow, ov = 0.0, w.copy(), v.copy()
+    osn = []
     for sidx in range(sweeps):
-        g[sidx * per] = rng.gamma((1 + n) / 2.0)
-        g[sidx * per + 1: (sidx + 1) * per] = rng.gamma((1 + p + 1) / 2.0, size=per - 1)
-    port.set_streams(rng.standard_normal(2_000_000), g, None)
-    rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, 0.0, w, v)
+        g = np.empty(per)
+        g[0] = rng.gamma((1 + n) / 2.0)
+        g[1:] = rng.gamma((1 + p + 1) / 2.0, size=per - 1)
+        port.set_streams(rng.standard_normal(4 * (p * (k + 1) + 2 * k + 4)), g, None)
+        cfg = O.make_cfg(task=O.REGRESSION, solver=O.MCMC, k=k, max_iter=1, enable_v=1, min_target=float(y.min()), max_target=float(y.max()))
+        ow0, ow, ov, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, ow0, ow, ov)
+        assert port.stream_pos()["overrun"] == 0
+        if sidx >= burn:
+            osn.append((ow0, ow.copy(), ov.copy()))
     port.set_streams(None, None, None)
-    rp = port.predict(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], rw0, rw, rv, 0)
-    (_, _, _), _, gp = gpu_als(gpu_ctx, L.F32, ds, y, L.REGRESSION, L.MCMC, k, 0.0, w, v, sweeps, 1, seed=99)
-    rmse_r = float(np.sqrt(np.mean((rp - y) ** 2)))
-    rmse_g = float(np.sqrt(np.mean((gp - y) ** 2)))
+    # engine side: native generator, one sweep per call on a persistent fp32 handle, a different seed per sweep
+    d = L.Data.from_csr32(gpu_ctx, n, p, ds["rowptr"], ds["col"], ds["val"], y)
+    m = L.Model(gpu_ctx, L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=k), p, L.F32)
+    m.set(0.0, w, v)
+    gsn = []
+    for sidx in range(sweeps):
+        sc = L.SolverCfg(solver=L.MCMC, max_iter=1, random_step=1, min_target=float(y.min()), max_target=float(y.max()), mode=L.MODE_EXACT,
+                         precision=L.F32, compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=1000 + sidx)
+        L.train_dev(gpu_ctx, m, d, sc)
+        if sidx >= burn:
+            gsn.append(m.get())
+    m.close(); d.close()
+    rmse_r, rmse_g = posterior_mean_rmse(osn), posterior_mean_rmse(gsn)
     base = float(np.std(y))
-    assert rmse_g < 0.5 * base and rmse_r < 0.5 * base            # both learned the planted model
-    assert abs(rmse_g - rmse_r) / rmse_r < 0.25, (rmse_g, rmse_r)  # last-draw models: Monte-Carlo noise dominates
+    print("MCMC posterior-mean RMSE: oracle %.5f engine %.5f (%.3f %%), sd(y) %.3f" % (rmse_r, rmse_g, 100 * (rmse_g - rmse_r) / rmse_r, base))
+    assert rmse_g < 0.2 * base and rmse_r < 0.2 * base             # both chains found the planted model
+    assert abs(rmse_g - rmse_r) / rmse_r < 0.005, (rmse_g, rmse_r)
 
 
 def test_als_converges_on_planted_fm(gpu_ctx):

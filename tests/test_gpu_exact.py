@@ -204,3 +204,23 @@ def test_exact_tdap_single_nnz_rows_no_fma_residue(gpu_ctx, port):
         rw0, rw, rv, _ = port.train(cfg, n, p, rowptr, col, val, y, 0.3, w, v)
         (gw0, gw, gv), _ = gpu_train(gpu_ctx, prec, ds, y, L.CLASSIFICATION, L.TDAP, k, 0.3, w, v, 2 * (n - 1))
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol
+
+
+def test_configs0_in_full_against_the_reference(gpu_ctx, ref):
+    """BASELINE configs[0] at its full size: fm.train SGD.solver, k=8, L2, 100k x 10k regression (10 nnz/row, real-valued x).
+    Exact mode over all 99 999 updates of an epoch, two epochs, against the reference's own SGD_Learner (oracle/_ref;
+    reference src/solver/SGD_Learner.h:86-177): fp32 within the north star's 1e-4, fp64 within 1e-9."""
+    ds = synth.make_dataset("c1", 100_000)
+    n, p, k = ds["n"], ds["p"], 8
+    y = ds["y"]
+    rng = np.random.default_rng(20240603)
+    w = np.zeros(p); v = rng.normal(0, 0.01, (p, k)); w0 = 0.0
+    iters = 2 * (n - 1)
+    regs = dict(l2_w=0.001, l2_v=0.001)
+    cfg = O.make_cfg(task=O.REGRESSION, solver=O.SGD, k=k, max_iter=iters, min_target=float(y.min()), max_target=float(y.max()), **regs)
+    rw0, rw, rv, _ = ref.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v)
+    assert float(np.max(np.abs(rv - v))) > 1e-3              # the run trained
+    for prec, tol in ((L.F64, 1e-9), (L.F32, 1e-4)):
+        (gw0, gw, gv), tr = gpu_train(gpu_ctx, prec, ds, y, L.REGRESSION, L.SGD, k, w0, w, v, iters, regs)
+        assert tr["iters_done"] == iters
+        assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol

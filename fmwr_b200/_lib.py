@@ -124,6 +124,12 @@ class Context:
         check(lib().fmwr_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def transfer_bytes(self):
+        """(host -> device, device -> host) bytes the library has copied for the caller on this context"""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().fmwr_ctx_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def flush_l2(self):
         check(lib().fmwr_flush_l2(self.h))
 
@@ -280,6 +286,13 @@ class Data:
         sd = np.zeros(p)
         check(lib().fmwr_data_scales(self.h, ptr(nc), C.c_int64(nc.size), ptr(mean), ptr(sd)))
         return mean, sd
+
+    def set_labels(self, labels):
+        lab = np.ascontiguousarray(labels, np.float64)
+        check(lib().fmwr_data_set_labels(self.h, ptr(lab)))
+
+    def restore_values(self):
+        check(lib().fmwr_data_restore_values(self.h))
 
     def normalize(self, mean, sd):
         mean = np.ascontiguousarray(mean, np.float64)

@@ -10,7 +10,11 @@ Engine options ride on `options()` exactly as the survey proposes for R (`option
 function signatures stay drop-in:
     FM.mode      "exact" (batch = 1, reference order; default) | "minibatch"
     FM.batch     minibatch rows (default 65536)
-    FM.precision "f32" (default) | "f64"
+    FM.precision "auto" (default): f64 wherever the result is held to the reference's -- exact mode (batch = 1), ALS, MCMC -- and f32 in
+                 the throughput (minibatch) mode | "f32" | "f64".  The reference computes in fp64 throughout; f32 is an explicit
+                 throughput opt-in (parameters within 1e-4 for SGD / FTRL, looser for TDAP: tests/test_gpu_exact.py)
+    FM.cache     True (default): the device copy of an fm.matrix lives in a slot of that object, so fm.train -> predict -> fm.update ->
+                 fm.track upload X once; False: upload per call like the reference's deep copy (src/FM.cpp:31-34)
     FM.compat    "reference" (default; reproduces SURVEY F5/F6/F7) | "fixed"
     FM.enable_v  ALS/MCMC: run the V block the shipped update_all comments out (default False = as shipped)
     FM.device    CUDA ordinal (default 0)
@@ -22,7 +26,7 @@ import numpy as np
 
 from . import _lib as L
 
-_OPTIONS = {"FM.threads": 1, "FM.mode": "exact", "FM.batch": 65536, "FM.precision": "f32", "FM.compat": "reference",
+_OPTIONS = {"FM.threads": 1, "FM.mode": "exact", "FM.batch": 65536, "FM.precision": "auto", "FM.cache": True, "FM.compat": "reference",
             "FM.enable_v": False, "FM.device": 0, "FM.seed": 1,
             # engine extension: keep the optimizer state (FTRL z/n, TDAP u/nu/delta/h, SGD-L1 q) in the FM object
             # and continue from it in fm.update; False = the reference's behaviour (state dropped, FTRL_Learner.h:48-56)
@@ -217,8 +221,40 @@ class FM(dict):
     """class "FM": list(Model = list(w0, w, v) + attrs, Scales, Trace)"""
 
 
-def _precision():
-    return L.F64 if str(_OPTIONS["FM.precision"]).lower() in ("f64", "double", "fp64") else L.F32
+def _precision(solver_name=None):
+    """FM.precision; "auto" = fp64 where parity with the reference is the point (exact mode, ALS, MCMC, predict), fp32 in throughput mode"""
+    opt = str(_OPTIONS["FM.precision"]).lower()
+    if opt in ("f64", "double", "fp64"):
+        return L.F64
+    if opt in ("f32", "float", "fp32"):
+        return L.F32
+    if solver_name in ("SGD", "FTRL", "TDAP") and _OPTIONS["FM.mode"] == "minibatch":
+        return L.F32
+    return L.F64
+
+
+def _acquire(ctx, feats, labels, normalized):
+    """device handle of an fm.matrix: uploaded once and parked in a slot of the features list (the external-pointer slot of the R
+    glue); labels are replaced in place when they changed; the values go back to the uploaded ones unless this
+    call rescales them itself (fmwr_data_scales / normalize always start from the uploaded values)"""
+    n, p = feats["dim"]
+    key = (id(feats["value"]), id(feats["col_idx"]), id(feats["row_size"]), int(n), int(p), int(np.asarray(feats["value"]).size), id(ctx))
+    slot = feats.get("_handle") if _OPTIONS["FM.cache"] else None
+    if slot is not None and slot["key"] == key and slot["data"].h:
+        d = slot["data"]
+        if labels is not None and slot["labels_id"] != id(labels):
+            d.set_labels(labels)
+            slot["labels_id"] = id(labels)
+            slot["labels_ref"] = labels
+        if not normalized:
+            d.restore_values()
+        return d, True
+    d = L.Data.from_r_lists(ctx, n, p, feats["row_size"], feats["col_idx"], feats["value"], labels)
+    if _OPTIONS["FM.cache"]:
+        # labels_ref keeps the array alive so its id() cannot be recycled by another array
+        feats["_handle"] = dict(key=key, data=d, labels_id=id(labels) if labels is not None else None, labels_ref=labels)
+        return d, True
+    return d, False
 
 
 def _compat():
@@ -238,10 +274,10 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
     feats = data["features"]
     n, p = feats["dim"]
     labels = data["labels"]
-    d = L.Data.from_r_lists(ctx, n, p, feats["row_size"], feats["col_idx"], feats["value"], labels)
+    normalize0 = np.atleast_1d(np.asarray(normalize0, np.int64))
+    d, parked = _acquire(ctx, feats, labels, normalize0[0] > -1)
     try:
         scales = {}
-        normalize0 = np.atleast_1d(np.asarray(normalize0, np.int64))
         if normalize0[0] > -1:                                            # FM.cpp:36-38
             mean, sd = d.scales(normalize0.astype(np.int32))
             scales["mean"], scales["std"] = mean, sd
@@ -249,7 +285,7 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
         mc = _model_cfg(fm_controls)
         hp = fm_controls["hyper.params"]
         k = mc.k
-        prec = _precision()
+        prec = _precision(solver_controls["solver"].solver)
         m = L.Model(ctx, mc, p, prec)
         try:
             # Model::init (src/core/Model.h:63-72): w = 0, V ~ rnorm(mean, sd) filled factor-major (f outer, feature inner)
@@ -298,7 +334,8 @@ def _FM(data, normalize0, fm_controls, solver_controls, track_controls, model_li
         finally:
             m.close()
     finally:
-        d.close()
+        if not parked:
+            d.close()
     model = dict(w0=gw0, w=gw, v=gv.T.copy())                              # v returned k x p like Model::save_model
     model["model.control"] = fm_controls
     model["solver.control"] = solver_controls
@@ -378,7 +415,7 @@ def predict(obj, newdata=None, normalize=True):
     feats = newdata["features"]
     n, p = feats["dim"]
     model = obj["Model"]
-    d = L.Data.from_r_lists(ctx, n, p, feats["row_size"], feats["col_idx"], feats["value"], None)
+    d, parked = _acquire(ctx, feats, None, bool(normalize))
     try:
         if normalize:
             d.normalize(obj["Scales"]["mean"], obj["Scales"]["std"])
@@ -391,7 +428,8 @@ def predict(obj, newdata=None, normalize=True):
         finally:
             m.close()
     finally:
-        d.close()
+        if not parked:
+            d.close()
 
 
 def fm_update(obj, data, normalize=None, control=None):
@@ -433,7 +471,6 @@ def fm_update(obj, data, normalize=None, control=None):
 def fm_track(obj, newdata, normalize=True, evaluate_metric=None):
     """R/fm_track.R:27 + FMTrack / Tracker::report (src/FM.cpp:218-258, src/core/Tracker.h:70-94):
     score every recorded snapshot on new data"""
-    import ctypes as C
     if "Trace" not in obj:
         raise ValueError("there is no trace in FM model, please set step_size > 0 in track.control")
     if newdata.get("labels") is None:
@@ -442,30 +479,31 @@ def fm_track(obj, newdata, normalize=True, evaluate_metric=None):
     metric = evaluate_metric or model["track.control"]["evaluate.metric"]
     feats = newdata["features"]
     n, p = feats["dim"]
-    value = np.asarray(feats["value"], np.float64)
-    if normalize and obj["Scales"].get("mean") is not None:
-        # SMatrix::normalize (src/util/Smatrix.h:144-150) through the engine, then read the values back
-        ctx = _ctx()
-        d = L.Data.from_r_lists(ctx, n, p, feats["row_size"], feats["col_idx"], value, None)
-        d.normalize(obj["Scales"]["mean"], obj["Scales"]["std"])
-        value = d.get_csr(labels=False)[2].astype(np.float64)
-        d.close()
-    snaps = obj["Trace"]["trace"][1:]
-    k = int(model["model.control"]["hyper.params"]["factor.number"])
-    sw0 = np.array([s["w0"] for s in snaps], np.float64)
-    sw = np.ascontiguousarray([np.asarray(s["w"], np.float64) for s in snaps])
-    sv = np.ascontiguousarray([np.asarray(s["v"], np.float64).T for s in snaps]) if k > 0 else np.zeros((len(snaps), p, 0))
     labels = np.asarray(newdata["labels"], np.float64)
     if model["model.control"]["task"] == "CLASSIFICATION" and np.array_equal(np.unique(labels), [0, 1]):
         labels = np.where(labels < 1, -1.0, 1.0)
+    do_norm = bool(normalize and obj["Scales"].get("mean") is not None)
+    ctx = _ctx()
+    # Tracker::report (src/core/Tracker.h:70-94) on the parked device copy of newdata: per snapshot a forward + the metric
+    d, parked = _acquire(ctx, feats, labels, do_norm)
+    snaps = obj["Trace"]["trace"][1:]
     out = np.zeros(len(snaps))
-    mc = _model_cfg(model["model.control"])
-    lo, hi = obj["Scales"]["target.range"]
-    rs = np.ascontiguousarray(feats["row_size"], np.int32)
-    ci = np.ascontiguousarray(feats["col_idx"], np.int32)
-    L.check(L.lib().fmwr_track(C.byref(mc), L.SOLVERS[model["solver.control"]["solver"].solver], _precision(), C.c_int64(n), C.c_int64(p),
-                               C.c_int64(ci.size), L.ptr(rs), L.ptr(ci), L.ptr(value), L.ptr(labels), len(snaps), L.ptr(sw0), L.ptr(sw),
-                               L.ptr(sv), L.METRICS[metric], C.c_double(lo), C.c_double(hi), L.ptr(out)))
+    try:
+        if do_norm:
+            d.normalize(obj["Scales"]["mean"], obj["Scales"]["std"])        # SMatrix::normalize, src/util/Smatrix.h:144-150
+        mc = _model_cfg(model["model.control"])
+        lo, hi = obj["Scales"]["target.range"]
+        m = L.Model(ctx, mc, p, _precision())
+        try:
+            for i, sn in enumerate(snaps):
+                m.set(float(sn["w0"]), np.asarray(sn["w"], np.float64), np.asarray(sn["v"], np.float64).T.copy())
+                L.predict_dev(ctx, m, d, _link_for(model), lo, hi)
+                out[i] = L.evaluate_dev(ctx, d, mc.task, L.METRICS[metric])
+        finally:
+            m.close()
+    finally:
+        if not parked:
+            d.close()
     return dict(index=obj["Trace"]["trace"][0], train=obj["Trace"]["evaluation.train"], test=out, metric=metric)
 
 

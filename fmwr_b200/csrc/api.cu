@@ -186,6 +186,7 @@ void model_set_host(fmwr_model* m, double w0, const double* w, const double* v)
 {
   fmwr_ctx* ctx = m->ctx;
   const int64_t p = m->p;
+  ctx->h2d_bytes += 8 + 8 * p + 8 * p * (int64_t)m->k;
   FMWR_CUDA(cudaMemsetAsync(m->scal.p, 0, m->scal.bytes(), ctx->stream));
   FMWR_CUDA(cudaMemcpyAsync(m->scal.p, &w0, 8, cudaMemcpyHostToDevice, ctx->stream));
   DBuf<double> stage;
@@ -222,6 +223,7 @@ void model_get_host(fmwr_model* m, double* w0, double* w, double* v)
   DBuf<double> stage;
   const int64_t vk = p * (int64_t)(m->k > 0 ? m->k : 1);
   stage.alloc(std::max<int64_t>(p, vk));
+  ctx->d2h_bytes += (w0 ? 8 : 0) + (w ? 8 * p : 0) + (v ? 8 * p * (int64_t)m->k : 0);
   if (p > 0 && w) {
     if (m->prec == FMWR_F64) FMWR_LAUNCH(ctx, cast_to_f64<double>, ceil_div(p, 256), 256, 0, (const double*)m->w.p, stage.p, p);
     else FMWR_LAUNCH(ctx, cast_to_f64<float>, ceil_div(p, 256), 256, 0, (const float*)m->w.p, stage.p, p);
@@ -263,6 +265,7 @@ fmwr_data* data_create_csr32(fmwr_ctx*, int64_t, int64_t, int64_t, const uint32_
 static void fetch_pred(fmwr_ctx* ctx, fmwr_data* d, double* out)
 {
   if (d->n == 0) return;
+  ctx->d2h_bytes += 8 * d->n;
   if (d->pred_prec == FMWR_F64) {
     FMWR_REQUIRE(d->pred64.p, FMWR_ERR_ARG, "no forward result on the device");
     FMWR_CUDA(cudaMemcpyAsync(out, d->pred64.p, 8 * d->n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -381,6 +384,15 @@ int fmwr_timer_stop_ms(fmwr_ctx* ctx, double* ms)
     float f = 0;
     FMWR_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
     *ms = f;
+  });
+}
+
+int fmwr_ctx_transfer_bytes(fmwr_ctx* ctx, int64_t* h2d, int64_t* d2h)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(ctx, FMWR_ERR_ARG, "null ctx");
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
   });
 }
 
@@ -563,6 +575,24 @@ int fmwr_data_slice_columns(fmwr_data* d, int64_t col_begin, int64_t col_end, fm
     FMWR_REQUIRE(d && out, FMWR_ERR_ARG, "null argument");
     FMWR_CUDA(cudaSetDevice(d->ctx->device));
     *out = data_slice_columns(d, col_begin, col_end);
+  });
+}
+
+int fmwr_data_set_labels(fmwr_data* d, const double* labels)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(d && (labels || d->n == 0), FMWR_ERR_ARG, "null argument");
+    FMWR_CUDA(cudaSetDevice(d->ctx->device));
+    data_set_labels(d, labels);
+  });
+}
+
+int fmwr_data_restore_values(fmwr_data* d)
+{
+  return guarded([&] {
+    FMWR_REQUIRE(d, FMWR_ERR_ARG, "null data");
+    FMWR_CUDA(cudaSetDevice(d->ctx->device));
+    data_restore_values(d);
   });
 }
 

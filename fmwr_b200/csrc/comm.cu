@@ -120,7 +120,7 @@ int64_t fmwr_comm_peer_bytes(int64_t batch_size, int32_t k, int32_t world)
   // stride <= 2k + 8 covers the padding of either precision; slabs: world x ceil(B / world) rows, S cache: B rows, mult: B
   const int64_t stride = 2 * (int64_t)k + 8;
   const int64_t rpo = (batch_size + world - 1) / world;
-  return PEER_CTL_BYTES + 8 * (world * rpo * stride + batch_size * stride + batch_size) + 3 * 256;
+  return PEER_CTL_BYTES + 8 * (world * rpo * stride + batch_size * stride + batch_size) + 4 * 256 + 8192;   // + the multiplier-sum slots
 }
 
 int fmwr_comm_peer_alloc(fmwr_ctx* ctx, int64_t bytes, uint8_t* handle64)

@@ -123,6 +123,7 @@ struct fmwr_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
   int64_t launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes the library copied between host and device on behalf of the caller (fmwr_ctx_transfer_bytes)
   // per-kernel CUDA-event profile (bench.py: roofline.achieved is measured live, on this stream)
   bool profile = false;
   struct ProfRec { const char* tag; cudaEvent_t e0, e1; };
@@ -149,6 +150,7 @@ struct fmwr_data {
   fmwr::DBuf<uint32_t> rowptr;   // [n+1]
   fmwr::DBuf<uint32_t> col;      // [nnz]
   fmwr::DBuf<float> val;         // [nnz]
+  fmwr::DBuf<float> val_raw;     // [nnz] pristine values, kept once a z-score pass rewrote `val` (persistent handles: scales / normalize always start from these)
   fmwr::DBuf<float> y;           // [n]
   // CSC twin (rows ascending inside each column)
   bool has_csc = false;
@@ -243,6 +245,7 @@ struct PeerArgs {
   int rank, world;
   int rows_per_owner;  // rows of a batch a rank finalises: owner(r) = r / rows_per_owner
   size_t off_P, off_S, off_mult;   // byte offsets of the partial slabs [world][rows_per_owner][stride], S cache [B][stride], mult [B]
+  size_t off_msum;                 // fused exchange: [0..8) each rank's sum of multipliers (doubles), [8..) this rank's per-CTA partial sums
 };
 
 // pa.base[i] with a run-time i, as a chain of selects: indexing a kernel parameter array dynamically makes the compiler copy
@@ -290,6 +293,44 @@ __device__ __forceinline__ void peer_wait(const PeerArgs& pa, int flag_base, int
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(f) - ep) < 0) {
       if (clock64() - t0 > 40000000000ll) { ctl[PEER_ERR] = 1u; break; }   // ~20 s: a peer died; the host reports it
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
+// Variants for a kernel that runs BOTH sides of a barrier itself (forward_stream.cuh fuses the partial pass and the owner's
+// reduction): the epoch to publish / wait for is passed in, because the local epoch word is bumped by this very kernel's last
+// CTA and a CTA that reads it "before or after?" would race.  `extra` runs once, in the last CTA, before the flags go out.
+template <class F>
+__device__ __forceinline__ void peer_signal_ep(const PeerArgs& pa, int flag_base, int epoch_word, int count_word, uint32_t ep, F&& extra)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
+    __threadfence_system();
+    const unsigned done = atomicAdd(ctl + count_word, 1u);
+    if (done == gridDim.x - 1) {
+      ctl[count_word] = 0u;
+      ctl[epoch_word] = ep;
+      __threadfence();                                        // the other CTAs' (local) stores before `extra` reads them
+      extra();
+      __threadfence_system();
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < pa.world) st_release_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
+    }
+  }
+}
+
+__device__ __forceinline__ void peer_wait_ep(const PeerArgs& pa, int flag_base, uint32_t ep)
+{
+  if ((int)threadIdx.x < pa.world) {
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
+    const uint32_t* f = ctl + flag_base + 32 * threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - ep) < 0) {
+      if (clock64() - t0 > 40000000000ll) { ctl[PEER_ERR] = 1u; break; }
       __nanosleep(64);
     }
   }
@@ -352,6 +393,9 @@ void model_set_host(fmwr_model* m, double w0, const double* w, const double* v);
 double model_get_w0(fmwr_model* m);
 void data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double* mean, double* sd);
 void data_normalize(fmwr_data* d, const double* mean, const double* sd);
+void data_values_from_raw(fmwr_data* d);
+void data_restore_values(fmwr_data* d);
+void data_set_labels(fmwr_data* d, const double* labels);
 void data_synth(fmwr_ctx* ctx, int64_t n, int64_t row_begin, int32_t n_fields, const int64_t* field_size, const int32_t* skew,
                 int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
 void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);

@@ -10,6 +10,8 @@
 
 namespace fmwr {
 
+void data_wait_values(fmwr_data* d);
+
 // ------------------------------------------------------------------------------------------ scan
 // exclusive prefix sum of u32 (reduce-then-scan, 3 phases, recursive on the block sums)
 constexpr int SCAN_THREADS = 256;
@@ -268,6 +270,7 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
       }
     }
     if (labels) set_labels_f64(d, labels);
+    ctx->h2d_bytes += 4 * n + 12 * nnz + (labels ? 8 * n : 0);
     finish_create(d);
   } catch (...) { delete d; throw; }
   return d;
@@ -291,6 +294,7 @@ fmwr_data* data_create_csr32(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, c
     FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
     FMWR_REQUIRE(rowptr[n] == (uint32_t)nnz && rowptr[0] == 0, FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
     if (labels) set_labels(d, labels);
+    ctx->h2d_bytes += 4 * (n + 1) + 8 * nnz + (labels ? 4 * n : 0);
     finish_create(d);
   } catch (...) { delete d; throw; }
   return d;
@@ -650,10 +654,38 @@ __global__ void col_rescale(const uint32_t* __restrict__ col, float* __restrict_
   }
 }
 
+// A handle may outlive one call (the glue parks it inside the fm.matrix object) and every fm.train / predict on it
+// z-scores "the input": the passes below therefore always start from the values as uploaded.  The first pass keeps a
+// pristine copy; later ones (and data_restore_values) copy it back first.
+void data_values_from_raw(fmwr_data* d)
+{
+  data_wait_values(d);
+  if (d->nnz == 0) return;
+  if (!d->val_raw.p) {
+    d->val_raw.alloc(d->nnz);
+    FMWR_CUDA(cudaMemcpyAsync(d->val_raw.p, d->val.p, 4 * d->nnz, cudaMemcpyDeviceToDevice, d->ctx->stream));
+  } else {
+    FMWR_CUDA(cudaMemcpyAsync(d->val.p, d->val_raw.p, 4 * d->nnz, cudaMemcpyDeviceToDevice, d->ctx->stream));
+  }
+}
+
+// undo a z-score pass (no-op on a handle that was never rescaled)
+void data_restore_values(fmwr_data* d)
+{
+  if (!d->val_raw.p || d->nnz == 0) return;
+  FMWR_CUDA(cudaMemcpyAsync(d->val.p, d->val_raw.p, 4 * d->nnz, cudaMemcpyDeviceToDevice, d->ctx->stream));
+  d->val_raw.release();
+  FMWR_CUDA(cudaStreamSynchronize(d->ctx->stream));
+  d->has_csc = false; d->mb_batch = 0; d->als_cache.reset();   // derived layouts hold the rescaled values
+}
+
+void data_set_labels(fmwr_data* d, const double* labels) { set_labels_f64(d, labels); d->ctx->h2d_bytes += 8 * d->n; }
+
 void data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double* mean, double* sd)
 {
   fmwr_ctx* ctx = d->ctx;
   const int64_t p = d->p, n = d->n;
+  data_values_from_raw(d);
   DBuf<double> s, q;
   s.alloc(p); q.alloc(p);
   s.zero(ctx->stream); q.zero(ctx->stream);
@@ -683,6 +715,7 @@ void data_normalize(fmwr_data* d, const double* mean, const double* sd)
 {
   fmwr_ctx* ctx = d->ctx;
   const int64_t p = d->p;
+  data_values_from_raw(d);
   DBuf<double> s, q;
   s.alloc(p); q.alloc(p);
   FMWR_CUDA(cudaMemcpyAsync(s.p, mean, 8 * p, cudaMemcpyHostToDevice, ctx->stream));

@@ -47,6 +47,9 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
   // rows are counted in 32 bits (a launch covers < 2^31 rows: callers split larger ranges)
   const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + g;
   const int rpg = a.rpg;
+  uint32_t ep_base = 0u;
+  if (MODE == SF_PARTIAL_PEER)       // EPOCH2 is only bumped after every CTA of the previous launch passed its last barrier: stable here
+    ep_base = *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(peer_base(a.pa, a.pa.rank)) + PEER_EPOCH2);
   int r = (int)min((int64_t)group * rpg, a.rows);         // current row (relative to row_begin)
   const int r1 = (int)min((int64_t)r + rpg, a.rows);
   if (r < r1) {
@@ -147,7 +150,66 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
     }
     while (r < r1) finalize();                             // the last row and trailing empty rows
   }
-  if (MODE == SF_PARTIAL_PEER) peer_signal(a.pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1);
+  if (MODE == SF_PARTIAL_PEER) {
+    // ---- the exchange, fused: this rank's partials are on their way to the rows' owners; now, as the owner of rows
+    // [rank * rpo, ...), wait for everybody's partials, sum them IN RANK ORDER (deterministic), form score and multiplier and
+    // store the row [S_f totals, multiplier] into every rank's S cache.  The batch's sum of multipliers (the intercept's
+    // gradient) is reduced on the way: per group -> per CTA -> the last CTA -> one double per rank in every window, so the
+    // update kernel adds `world` numbers instead of walking 65 536 strided multipliers in one CTA.
+    const PeerArgs& pa = a.pa;
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
+    const uint32_t ep = ep_base + 1u;
+    peer_signal_ep(pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1, ep, [] {});
+    peer_wait_ep(pa, PEER_FLAG1, ep);
+    const int rpo = pa.rows_per_owner;
+    const int r_lo = pa.rank * rpo;
+    const int n_local = max(0, (int)min((int64_t)(r_lo + rpo), a.rows) - r_lo);
+    const float* P = reinterpret_cast<const float*>(peer_base(pa, pa.rank) + pa.off_P);
+    const float w0 = a.k0 ? (float)a.scal[0] : 0.f;
+    const int ngroups = gridDim.x * (blockDim.x >> 5) * 4;
+    double msum = 0.0;
+    for (int rl = group; rl < n_local; rl += ngroups) {
+      float S[4] = {0.f, 0.f, 0.f, 0.f};
+      float add = 0.f;
+      for (int h = 0; h < pa.world; ++h) {
+        const float* row = P + ((size_t)h * rpo + rl) * a.s_stride;
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(row) + l);
+        S[0] += t.x; S[1] += t.y; S[2] += t.z; S[3] += t.w;
+        if (l == 0) add += __ldcg(row + 32);
+      }
+      float acc = add + 0.5f * ((S[0] * S[0] + S[1] * S[1]) + (S[2] * S[2] + S[3] * S[3]));
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+      const int r = r_lo + rl;
+      const float m = grad_mult_fast(a.task, w0 + acc, __ldg(a.y + a.row_begin + r), a.lo, a.hi);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h >= pa.world) break;
+        float* dst = reinterpret_cast<float*>(pa.base[h] + pa.off_S) + (size_t)r * a.s_stride;
+        reinterpret_cast<float4*>(dst)[l] = make_float4(S[0], S[1], S[2], S[3]);
+        if (l == 0) *reinterpret_cast<float4*>(dst + 32) = make_float4(m, 0.f, 0.f, 0.f);
+      }
+      msum += (double)m;
+    }
+    __shared__ double s_msum[32];
+    if (l == 0) s_msum[(threadIdx.x >> 5) * 4 + g] = msum;
+    __syncthreads();
+    double* part = reinterpret_cast<double*>(peer_base(pa, pa.rank) + pa.off_msum) + 8;
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5) * 4; ++i) t += s_msum[i];
+      part[blockIdx.x] = t;
+    }
+    const int nblk = gridDim.x;
+    peer_signal_ep(pa, PEER_FLAG2, PEER_EPOCH2, PEER_COUNT2, ep, [&] {
+      double t = 0.0;
+      for (int i = 0; i < nblk; ++i) t += *reinterpret_cast<volatile double*>(part + i);
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < pa.world) reinterpret_cast<double*>(pa.base[h] + pa.off_msum)[pa.rank] = t;
+    });
+    (void)ctl;
+  }
 }
 
 // raw score -> link, in place (SF_PREDICT's second pass; fp64 like the reference's predict_prob, src/core/Model.h:163-180)

@@ -191,6 +191,7 @@ struct MbUpdArgs {
   T u_w, u_v;                           // SGD cumulative-L1 totals after this batch
   int mult_stride;                      // 1, or the S-cache row stride when the multiplier lives in the row's padding (peer mode)
   int peer;                             // peer-window exchange: wait for every rank's row totals first
+  const double* msum; int msum_n;       // fused exchange: the ranks' sums of multipliers (else the intercept block sums a.mult itself)
   PeerArgs pa;
 };
 
@@ -211,7 +212,9 @@ __device__ __forceinline__ void mb_intercept(const MbUpdArgs<T>& a)
   __shared__ double red[32];
   double acc = 0.0;
   const int nt = (int)blockDim.x;
-  {
+  if (a.msum) {
+    if (threadIdx.x == 0) for (int i = 0; i < a.msum_n; ++i) acc += a.msum[i];      // rank order: every rank forms the same sum
+  } else {
     constexpr int UN = 16;
     int r = threadIdx.x;
     for (; r + (UN - 1) * nt < a.rows; r += UN * nt) {
@@ -627,7 +630,7 @@ template <class T>
 struct MbLaunch {
   fmwr_ctx* ctx; fmwr_model* m; fmwr_data* d; const fmwr_solver_cfg* s;
   int64_t row_begin; int rows; T* mult; T* Scache; MbUpdArgs<T> ua; int phase;   // phase 0: K1, 1: K2
-  int s_stride; int partial; PeerArgs pa;
+  int s_stride; int partial; PeerArgs pa; bool fused_exchange = false;
   template <class TT, int LPR, int CH, int TEAM> void k1();
   void k1_stream()
   {
@@ -688,7 +691,7 @@ struct MbLaunch {
       FMWR_LAUNCH(ctx, (mb_exchange_kernel<TT, LPR, CH>), xgrid, 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
                   m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, s_stride, pa);
     } else if (phase == 0) {
-      if (sizeof(TT) == 4 && stream_forward_ok(m, d->nnz, d->n)) { k1_stream(); return; }
+      if (sizeof(TT) == 4 && stream_forward_ok(m, d->nnz, d->n) && (partial != 2 || fused_exchange)) { k1_stream(); return; }
       const int tm = team_mode(d->nnz, d->n, LPR);
       if (tm == 1) k1<TT, LPR, CH, LPR>();
       else if (tm == 2) k1<TT, LPR, CH, (LPR <= 8 ? 16 : 32)>();
@@ -783,7 +786,8 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
     pa.off_P = PEER_CTL_BYTES;
     pa.off_S = up(pa.off_P + (size_t)ctx->world * pa.rows_per_owner * s_stride * sizeof(T));
     pa.off_mult = up(pa.off_S + (size_t)B * s_stride * sizeof(T));
-    FMWR_REQUIRE(up(pa.off_mult + (size_t)B * sizeof(T)) <= ctx->peer.bytes, FMWR_ERR_COMM,
+    pa.off_msum = up(pa.off_mult + (size_t)B * sizeof(T));
+    FMWR_REQUIRE(pa.off_msum + 8192 <= ctx->peer.bytes, FMWR_ERR_COMM,
                  "peer window too small for this batch size / factor count (see fmwr_comm_peer_bytes)");
     for (int r = 0; r < ctx->world; ++r) pa.base[r] = (char*)ctx->peer.base[r];
   }
@@ -802,6 +806,10 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   ua.seg_ptr = d->mb_seg_ptr.p; ua.seg_rec = d->mb_seg_rec.p; ua.ent_row = d->mb_ent_row.p; ua.ent_val = d->mb_ent_val.p;
   ua.mult = mult_p; ua.Scache = sc_p;
   ua.peer = peer ? 1 : 0; ua.pa = pa; ua.mult_stride = peer ? s_stride : 1;
+  // fp32 models with 32-float rows on long rows: the stream forward kernel runs the exchange itself
+  const bool fused_exchange = peer && sizeof(T) == 4 && stream_forward_ok(m, d->nnz, d->n) && getenv("FMWR_NO_FUSED_EXCHANGE") == nullptr;
+  if (fused_exchange) { ua.msum = reinterpret_cast<const double*>(pa.base[pa.rank] + pa.off_msum); ua.msum_n = ctx->world; }
+  L.fused_exchange = fused_exchange;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
   ua.kp = m->kp; ua.k0 = m->cfg.keep_w0; ua.k1 = m->cfg.keep_w1; ua.s_stride = s_stride;
@@ -871,9 +879,11 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
       L.row_begin = rb; L.rows = (int)rows;
       L.phase = 0;
       dispatch_layout<T>(m->kp, L);
-      if (peer) {
+      if (peer && !fused_exchange) {
         L.phase = 2;
         dispatch_layout<T>(m->kp, L);
+      } else if (peer) {
+        // the stream forward kernel did the owner's reduction itself (forward_stream.cuh)
       } else if (multi) {
         // one exchange per minibatch: sum the per-row partials over the feature shards (NCCL over NVLink / NVSwitch)
         comm_allreduce_sum(ctx, Scache.p, (size_t)rows * s_stride, sizeof(T) == 8);

@@ -147,9 +147,19 @@ int fmwr_data_get_csr(fmwr_data* d, uint32_t* rowptr, uint32_t* col_idx, float* 
  * Output ordering: rows ascending inside each column (bit-exact with the reference on data without empty rows). */
 int fmwr_data_transpose(fmwr_data* d);
 int fmwr_data_get_csc(fmwr_data* d, uint32_t* colptr /*[p+1]*/, uint32_t* row_idx /*[nnz]*/, float* value /*[nnz]*/);
-/* z-score of the non-zeros: replaces SMatrix::scales / normalize (src/util/Smatrix.h:98-153) */
+/* z-score of the non-zeros: replaces SMatrix::scales / normalize (src/util/Smatrix.h:98-153).  Both always start from the values
+ * as uploaded (a pristine copy is kept from the first pass on), so a handle that outlives one call -- the glue parks it inside the
+ * fm.matrix object, see below -- is never rescaled twice; fmwr_data_restore_values puts the uploaded values back. */
 int fmwr_data_scales(fmwr_data* d, const int32_t* norm_cols, int64_t n_norm, double* mean /*[p]*/, double* sd /*[p]*/);
 int fmwr_data_normalize(fmwr_data* d, const double* mean /*[p]*/, const double* sd /*[p]*/);
+int fmwr_data_restore_values(fmwr_data* d);
+/* Persistent handles: the reference deep-copies the fm.matrix lists on every .Call (src/FM.cpp:31-34); the drop-in
+ * glue instead keeps the fmwr_data of an fm.matrix in an external-pointer slot of that R object, so
+ * fm.train -> predict -> fm.update -> fm.track upload X once.  What changes between such calls is replaced in place: */
+int fmwr_data_set_labels(fmwr_data* d, const double* labels /*[n]*/);
+/* bytes this library has copied host -> device / device -> host for the caller on this context (data ingest, labels, model set /
+ * get, prediction fetch): lets a test state "the second call uploaded no X" */
+int fmwr_ctx_transfer_bytes(fmwr_ctx* ctx, int64_t* h2d, int64_t* d2h);
 /* synthetic field-structured data generated on the device.  field_size[f] ids per field,
  * skew[f]: 0 uniform, 1 power-law ids; value_mode: 0 -> x = 1, 1 -> x ~ U(0.5,1.5) from the hash.
  * label_mode: 0 none, 1 +-1 ~ Bernoulli(sigmoid(planted score)), 2 planted score + N(0, noise^2),

@@ -2,6 +2,9 @@
 // (reference src/FM.cpp:7, :177, :218; src/RcppExports.cpp is unchanged) and become thin glue that
 // unpacks the R lists into raw pointers and calls libfmwr_b200.so (include/fmwr_b200.h).
 //
+// Device copies of fm.matrix objects persist across calls (see "persistent handles" below); the default precision is the
+// reference's fp64 except in the throughput mode.
+//
 // UNVERIFIED IN THIS REPOSITORY: the build image has no R / Rcpp, so this file has never been compiled.
 // It is the binding a maintainer adds; the same call sequence is exercised by fmwr_b200/api.py.
 //
@@ -16,6 +19,72 @@
 using namespace Rcpp;
 
 static void check(int rc) { if (rc != 0) stop(fmwr_last_error()); }   // Rcpp::stop -> R error, as before
+
+// ---- persistent handles -------------------------------------------------------------------------------------
+// The reference deep-copies the fm.matrix lists on every .Call (src/FM.cpp:31-34).  Here the device copy of an fm.matrix is
+// created once and parked in an external pointer stored as attribute "fmwr.handle" of its `features` list; R's copy-on-modify
+// gives a modified matrix new vectors, so the key (addresses + sizes of value / col_idx / row_size) goes stale exactly when the
+// contents can have changed.  The finalizer frees the device memory when R collects the object.  options(FM.cache = FALSE)
+// restores upload-per-call.  One context per device lives for the session.
+struct Parked {
+  fmwr_data* d; const void* kv; const void* kc; const void* kr; R_xlen_t nnz; int n, p; const void* klab;
+};
+static void parked_finalizer(SEXP xp)
+{
+  Parked* h = static_cast<Parked*>(R_ExternalPtrAddr(xp));
+  if (h) { fmwr_data_destroy(h->d); delete h; R_ClearExternalPtr(xp); }
+}
+static fmwr_ctx* session_ctx(int device)
+{
+  static std::map<int, fmwr_ctx*> ctxs;
+  if (!ctxs.count(device)) { fmwr_ctx* c = NULL; check(fmwr_ctx_create(device, &c)); ctxs[device] = c; }
+  return ctxs[device];
+}
+static bool opt_flag(const char* name, bool dflt)
+{
+  Function getOption("getOption");
+  return as<bool>(getOption(name, dflt));
+}
+// device handle of an fm.matrix; `owned` tells the caller to destroy it (caching off).  labels may be R_NilValue (predict).
+static fmwr_data* acquire(fmwr_ctx* ctx, List X, SEXP labels, bool will_rescale, bool* owned)
+{
+  NumericVector value = X["value"]; IntegerVector col_idx = X["col_idx"]; IntegerVector row_size = X["row_size"]; IntegerVector dim = X["dim"];
+  const int64_t n = dim[0], p = dim[1], nnz = value.size();
+  const double* lab = Rf_isNull(labels) ? NULL : REAL(labels);
+  *owned = !opt_flag("FM.cache", true);
+  if (!*owned) {
+    SEXP slot = X.attr("fmwr.handle");
+    if (!Rf_isNull(slot) && TYPEOF(slot) == EXTPTRSXP && R_ExternalPtrAddr(slot)) {
+      Parked* h = static_cast<Parked*>(R_ExternalPtrAddr(slot));
+      if (h->kv == (const void*)value.begin() && h->kc == (const void*)col_idx.begin() && h->kr == (const void*)row_size.begin() &&
+          h->nnz == value.size() && h->n == dim[0] && h->p == dim[1]) {
+        if (lab && h->klab != (const void*)lab) { check(fmwr_data_set_labels(h->d, lab)); h->klab = lab; }
+        if (!will_rescale) check(fmwr_data_restore_values(h->d));      // fmwr_data_scales / normalize start from the uploaded values themselves
+        return h->d;
+      }
+    }
+  }
+  fmwr_data* d = NULL;
+  check(fmwr_data_create(ctx, n, p, nnz, row_size.begin(), col_idx.begin(), value.begin(), lab, &d));
+  if (!*owned) {
+    Parked* h = new Parked{d, value.begin(), col_idx.begin(), row_size.begin(), value.size(), dim[0], dim[1], lab};
+    SEXP xp = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(xp, parked_finalizer, TRUE);
+    Rf_setAttrib(X, Rf_install("fmwr.handle"), xp);                    // in place: the slot belongs to the caller's object
+    UNPROTECT(1);
+  }
+  return d;
+}
+
+// FM.precision: "auto" (default) = fp64 wherever the result is held to the reference's (exact mode, ALS, MCMC, predict),
+// fp32 in the throughput (minibatch) mode; "f32" / "f64" force it
+static int precision_for(int solver, bool minibatch)
+{
+  const std::string o = opt_str("FM.precision", "auto");
+  if (o == "f64") return FMWR_F64;
+  if (o == "f32") return FMWR_F32;
+  return (minibatch && (solver == FMWR_SGD || solver == FMWR_FTRL || solver == FMWR_TDAP)) ? FMWR_F32 : FMWR_F64;
+}
 
 static int opt_int(const char* name, int dflt)
 {
@@ -68,9 +137,10 @@ List FM(List data_, IntegerVector normalize, List fm_controls, List solver_contr
   NumericVector target = as<NumericVector>(data_["labels"]);
   const int64_t n = dim[0], p = dim[1], nnz = value.size();
 
-  fmwr_ctx* ctx = NULL; fmwr_data* d = NULL; fmwr_model* m = NULL;
-  check(fmwr_ctx_create(opt_int("FM.device", 0), &ctx));
-  check(fmwr_data_create(ctx, n, p, nnz, row_size.begin(), col_idx.begin(), value.begin(), target.begin(), &d));
+  fmwr_ctx* ctx = session_ctx(opt_int("FM.device", 0));
+  fmwr_model* m = NULL;
+  bool owned = false;
+  fmwr_data* d = acquire(ctx, X, target, normalize[0] > -1, &owned);
 
   List scales;
   if (normalize[0] > -1) {                                            // reference FM.cpp:36-38
@@ -83,7 +153,8 @@ List FM(List data_, IntegerVector normalize, List fm_controls, List solver_contr
   fmwr_model_cfg mc = model_cfg(fm_controls);
   List hp = fm_controls["hyper.params"];
   const int k = mc.k;
-  const int prec = opt_str("FM.precision", "f32") == "f64" ? FMWR_F64 : FMWR_F32;
+  const bool minibatch = opt_str("FM.mode", "exact") == "minibatch";
+  const int prec = precision_for(solver_id(solver_controls), minibatch);
   check(fmwr_model_create(ctx, &mc, p, prec, &m));
 
   // Model::init (reference src/core/Model.h:63-72): w = 0, V ~ rnorm drawn HERE, factor-major, so set.seed() holds
@@ -118,7 +189,7 @@ List FM(List data_, IntegerVector normalize, List fm_controls, List solver_contr
   sc.beta_v = solver.containsElementNamed("beta_v") ? (double)solver["beta_v"] : 1.0;
   sc.gamma = solver.containsElementNamed("gamma") ? (double)solver["gamma"] : 1e-4;
   sc.min_target = lo; sc.max_target = hi;
-  sc.mode = opt_str("FM.mode", "exact") == "minibatch" ? FMWR_MODE_MINIBATCH : FMWR_MODE_EXACT;
+  sc.mode = minibatch ? FMWR_MODE_MINIBATCH : FMWR_MODE_EXACT;
   sc.batch_size = opt_int("FM.batch", 65536);
   sc.precision = prec;
   sc.compat = opt_str("FM.compat", "reference") == "reference" ? FMWR_COMPAT_REFERENCE : 0;
@@ -138,8 +209,10 @@ List FM(List data_, IntegerVector normalize, List fm_controls, List solver_contr
   }
   int rc = fmwr_train_dev(ctx, m, d, &sc, sc.step_size > 0 ? &tr : NULL);
   if (rc == 0) rc = fmwr_model_get(m, &w0, w.begin(), v.begin());
-  fmwr_model_destroy(m); fmwr_data_destroy(d); fmwr_ctx_destroy(ctx);
+  fmwr_model_destroy(m);
+  if (owned) fmwr_data_destroy(d);
   check(rc);
+  const int n_rec = std::min(tr.n_rec, tr.max_rec);                   // records actually written (never read past the buffers)
 
   List md = List::create(_["w0"] = w0, _["w"] = w, _["v"] = v);      // Model::save_model
   md.attr("model.control") = fm_controls;
@@ -151,17 +224,17 @@ List FM(List data_, IntegerVector normalize, List fm_controls, List solver_contr
   scales.attr("target.range") = NumericVector::create(lo, hi);
   res["Scales"] = scales;
   if (sc.step_size > 0) {                                             // Tracker::save, src/core/Tracker.h:96-119
-    List valid(tr.n_rec + 1);
-    NumericVector idx(tr.n_rec);
-    for (int i = 0; i < tr.n_rec; ++i) idx[i] = ri[i];
+    List valid(n_rec + 1);
+    NumericVector idx(n_rec);
+    for (int i = 0; i < n_rec; ++i) idx[i] = ri[i];
     valid[0] = idx;
-    for (int i = 0; i < tr.n_rec; ++i) {
+    for (int i = 0; i < n_rec; ++i) {
       NumericVector wi(sw.begin() + (size_t)i * p, sw.begin() + (size_t)(i + 1) * p);
       NumericMatrix vi(k, p);
       std::copy(sv.begin() + (size_t)i * p * k, sv.begin() + (size_t)(i + 1) * p * k, vi.begin());
       valid[i + 1] = List::create(_["w0"] = sw0[i], _["w"] = wi, _["v"] = vi);
     }
-    res["Trace"] = List::create(_["trace"] = valid, _["evaluation.train"] = NumericVector(ev.begin(), ev.begin() + tr.n_rec));
+    res["Trace"] = List::create(_["trace"] = valid, _["evaluation.train"] = NumericVector(ev.begin(), ev.begin() + n_rec));
   }
   res.attr("class") = "FM";
   return res;
@@ -171,20 +244,20 @@ List FM(List data_, IntegerVector normalize, List fm_controls, List solver_contr
 NumericVector FMPredict(List newdata, bool normalize, List model_list, int max_threads)
 {
   List X = newdata["features"];
-  NumericVector value = clone(as<NumericVector>(X["value"]));
-  IntegerVector col_idx = X["col_idx"]; IntegerVector row_size = X["row_size"]; IntegerVector dim = X["dim"];
-  const int64_t n = dim[0], p = dim[1], nnz = value.size();
+  IntegerVector dim = X["dim"];
+  const int64_t n = dim[0], p = dim[1];
   List model = model_list["Model"];
   List scales = model_list["Scales"];                                 // read unconditionally (latent crash in the reference)
   fmwr_model_cfg mc = model_cfg(as<List>(model.attr("model.control")));
   const int solver = solver_id(as<List>(model.attr("solver.control")));
-  const int prec = opt_str("FM.precision", "f32") == "f64" ? FMWR_F64 : FMWR_F32;
+  const int prec = precision_for(0, false);
   NumericVector w = model["w"]; NumericMatrix v = model["v"];
   NumericVector tr = as<NumericVector>(scales.attr("target.range"));
 
-  fmwr_ctx* ctx = NULL; fmwr_data* d = NULL; fmwr_model* m = NULL;
-  check(fmwr_ctx_create(opt_int("FM.device", 0), &ctx));
-  check(fmwr_data_create(ctx, n, p, nnz, row_size.begin(), col_idx.begin(), value.begin(), NULL, &d));
+  fmwr_ctx* ctx = session_ctx(opt_int("FM.device", 0));
+  fmwr_model* m = NULL;
+  bool owned = false;
+  fmwr_data* d = acquire(ctx, X, R_NilValue, normalize, &owned);
   if (normalize) {
     NumericVector mean = scales["mean"], sd = scales["std"];
     check(fmwr_data_normalize(d, mean.begin(), sd.begin()));
@@ -197,7 +270,8 @@ NumericVector FMPredict(List newdata, bool normalize, List model_list, int max_t
   NumericVector pred(n);
   int rc = fmwr_predict_dev(ctx, m, d, link, tr[0], tr[1]);
   if (rc == 0) rc = fmwr_predict_fetch(ctx, d, pred.begin());
-  fmwr_model_destroy(m); fmwr_data_destroy(d); fmwr_ctx_destroy(ctx);
+  fmwr_model_destroy(m);
+  if (owned) fmwr_data_destroy(d);
   check(rc);
   return pred;
 }
@@ -205,31 +279,39 @@ NumericVector FMPredict(List newdata, bool normalize, List model_list, int max_t
 // [[Rcpp::export]]
 NumericVector FMTrack(List newdata, List model_list, bool normalize, String type, int max_threads)
 {
+  // Tracker::report (src/core/Tracker.h:70-94): per recorded snapshot a forward over newdata + the metric, on the parked handle
   List X = newdata["features"];
-  NumericVector value = clone(as<NumericVector>(X["value"]));
-  IntegerVector col_idx = X["col_idx"]; IntegerVector row_size = X["row_size"]; IntegerVector dim = X["dim"];
-  NumericVector labels = as<NumericVector>(newdata["labels"]);
-  const int64_t n = dim[0], p = dim[1], nnz = value.size();
+  IntegerVector dim = X["dim"];
+  const int64_t p = dim[1];
   List model = model_list["Model"]; List scales = model_list["Scales"];
   fmwr_model_cfg mc = model_cfg(as<List>(model.attr("model.control")));
   const int solver = solver_id(as<List>(model.attr("solver.control")));
-  const int prec = opt_str("FM.precision", "f32") == "f64" ? FMWR_F64 : FMWR_F32;
-  if (normalize) {                                                    // SMatrix::normalize on the host copy, Smatrix.h:144-150
-    NumericVector mean = scales["mean"], sd = scales["std"];
-    for (int64_t e = 0; e < nnz; ++e) { int c = col_idx[e]; if (sd[c] != 0) value[e] = (float)(((float)value[e] - mean[c]) / sd[c]); }
-  }
-  List trace = model_list["Trace"]; List snaps = trace["trace"];
-  const int ns = snaps.size() - 1, k = mc.k;
-  std::vector<double> sw0(ns), sw((size_t)ns * p), sv((size_t)ns * p * std::max(k, 1));
-  for (int i = 0; i < ns; ++i) {
-    List s = snaps[i + 1];
-    sw0[i] = (double)s["w0"];
-    NumericVector wi = s["w"]; std::copy(wi.begin(), wi.end(), sw.begin() + (size_t)i * p);
-    NumericMatrix vi = s["v"]; std::copy(vi.begin(), vi.end(), sv.begin() + (size_t)i * p * k);
-  }
   NumericVector tr = as<NumericVector>(scales.attr("target.range"));
+  fmwr_ctx* ctx = session_ctx(opt_int("FM.device", 0));
+  bool owned = false;
+  fmwr_data* d = acquire(ctx, X, newdata["labels"], normalize, &owned);
+  if (normalize) {                                                    // SMatrix::normalize, Smatrix.h:144-150
+    NumericVector mean = scales["mean"], sd = scales["std"];
+    check(fmwr_data_normalize(d, mean.begin(), sd.begin()));
+  }
+  fmwr_model* m = NULL;
+  check(fmwr_model_create(ctx, &mc, p, precision_for(0, false), &m));
+  const int link = mc.task == FMWR_CLASSIFICATION
+                       ? ((solver == FMWR_MCMC || solver == FMWR_ALS) ? FMWR_LINK_PROBIT_TABLE : FMWR_LINK_LOGISTIC)
+                       : FMWR_LINK_CLAMP;
+  List trace = model_list["Trace"]; List snaps = trace["trace"];
+  const int ns = snaps.size() - 1;
   NumericVector out(ns);
-  check(fmwr_track(&mc, solver, prec, n, p, nnz, row_size.begin(), col_idx.begin(), value.begin(), labels.begin(), ns,
-                   sw0.data(), sw.data(), sv.data(), metric_id(type), tr[0], tr[1], out.begin()));
+  int rc = 0;
+  for (int i = 0; i < ns && rc == 0; ++i) {
+    List s = snaps[i + 1];
+    NumericVector wi = s["w"]; NumericMatrix vi = s["v"];
+    rc = fmwr_model_set(m, (double)s["w0"], wi.begin(), vi.begin());
+    if (rc == 0) rc = fmwr_predict_dev(ctx, m, d, link, tr[0], tr[1]);
+    if (rc == 0) rc = fmwr_evaluate_dev(ctx, d, mc.task, metric_id(type), &out[i]);
+  }
+  fmwr_model_destroy(m);
+  if (owned) fmwr_data_destroy(d);
+  check(rc);
   return out;
 }

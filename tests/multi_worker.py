@@ -62,6 +62,40 @@ def main():
               ok = ok and err < tol and moved > 1e-3
               for q in parts[1:]:
                   ok = ok and q[0] == parts[0][0]          # w0 is replicated bit for bit
+    # k = 32 in fp32 takes the stream forward kernel, which runs the owner's reduction itself (forward_stream.cuh: partials ->
+    # owners -> totals -> every rank, all in one kernel, plus the intercept's multiplier sum); same comparison, fp32 tolerance
+    k2 = 32
+    v2 = rng.normal(0, 0.05, (p, k2))
+    for solver in (L.FTRL, L.SGD):
+        iters = 2 * (n - 1) + 77
+        mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k2, l1_w1=1e-3, l2_w1=1e-3, l2_v=1e-3)
+        sc = L.SolverCfg(solver=solver, max_iter=iters, random_step=1, learn_rate=0.01, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0,
+                         gamma=1e-4, min_target=-1.0, max_target=1.0, mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F32,
+                         compat=L.COMPAT_SKIP_ROW0, step_size=-1)
+        full = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)
+        part = full.slice_columns(c0, c1)
+        full.close()
+        m = L.Model(ctx, mc, c1 - c0, L.F32)
+        m.set(w0, w[c0:c1], v2[c0:c1])
+        L.train_dev(ctx, m, part, sc)
+        mine = m.get()
+        m.close(); part.close()
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank == 0:
+            gw0, gw, gv = multi.gather_model(parts)
+            solo = L.Context(local)
+            d1 = L.Data.from_csr32(solo, n, p, rowptr, col, val, y)
+            m1 = L.Model(solo, mc, p, L.F32)
+            m1.set(w0, w, v2)
+            L.train_dev(solo, m1, d1, sc)
+            sw0, sw, sv = m1.get()
+            m1.close(); d1.close(); solo.close()
+            err = max(abs(gw0 - sw0), float(np.max(np.abs(gw - sw) / np.maximum(1, np.abs(sw)))),
+                      float(np.max(np.abs(gv - sv) / np.maximum(1, np.abs(sv)))))
+            moved = float(np.max(np.abs(sv - v2)))
+            print("fused exchange (k=32, fp32) solver=%d world=%d max rel err vs single GPU = %.3e (params moved by %.3e)" % (solver, world, err, moved), flush=True)
+            ok = ok and err < 2e-4 and moved > 1e-3
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     ctx.comm_destroy(); ctx.close()

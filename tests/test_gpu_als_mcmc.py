@@ -68,13 +68,17 @@ def test_als_matches_oracle(gpu_ctx, port, task, enable_v, layout):
     sweeps = 6
     cfg = O.make_cfg(task=task, solver=O.ALS, k=k, max_iter=sweeps, enable_v=enable_v, l2_w0=0.1,
                      min_target=float(y.min()), max_target=float(y.max()), step_size=1, metric=O.LL if task == O.CLASSIFICATION else O.RMSE)
-    rw0, rw, rv, rt = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v, max_rec=20)
     # fields_odd has ~1.2 non-zeros per feature in its wide field: 1/(alpha*A) amplifies the summation-order noise
     t64 = 1e-6 if layout == "fields_odd" else 1e-8
     # fp32 handles: on fields_odd (features with one or two non-zeros: h = x q - x^2 v cancels to rounding noise and
     # 1/(alpha * sum h^2) blows it up) the engine runs the sweep in fp64 on a shadow model and hands the result back
-    # (train_als.cu: precision policy), so the fp32 handle meets the north star's 1e-4 on every layout
+    # (train_als.cu: precision policy), so the fp32 handle meets the north star's 1e-4 on every layout.  "Same inputs" for an
+    # fp32 handle means the initial parameters as that handle stores them: on such data the reference itself turns the 1e-8
+    # rounding of the initial V into O(1) differences, so the oracle is fed the fp32-rounded values.
     for prec, tol in ((L.F64, t64), (L.F32, 1e-4)):
+        if prec == L.F32:
+            w0, w, v = float(np.float32(w0)), w.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64)
+        rw0, rw, rv, rt = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v, max_rec=20)
         (gw0, gw, gv), gt, _ = gpu_als(gpu_ctx, prec, ds, y, task, L.ALS, k, w0, w, v, sweeps, enable_v, l2_w0=0.1, step_size=1,
                                        metric=L.LL if task == O.CLASSIFICATION else L.RMSE)
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol, (prec, relerr(gw0, rw0), relerr(gw, rw), relerr(gv, rv))
@@ -106,13 +110,15 @@ def test_mcmc_injected_streams_match_oracle(gpu_ctx, port, task, enable_v):
     rands = rng.integers(0, 2**31 - 1, 400000).astype(np.int32)
     cfg = O.make_cfg(task=task, solver=O.MCMC, k=k, max_iter=sweeps, enable_v=enable_v, l2_w0=0.1,
                      min_target=float(y.min()), max_target=float(y.max()))
-    port.set_streams(normals, gammas, rands)
-    rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v)
-    pos = port.stream_pos()
-    port.set_streams(None, None, None)
-    assert pos["overrun"] == 0
     # fp32 + classification runs in fp64 internally (the truncated-normal rejection loops are data-dependent): 1e-4 either way
     for prec, tol in ((L.F64, 1e-8), (L.F32, 1e-4)):
+        if prec == L.F32:                      # same inputs: the initial parameters as an fp32 handle stores them
+            w0, w, v = float(np.float32(w0)), w.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64)
+        port.set_streams(normals, gammas, rands)
+        rw0, rw, rv, _ = port.train(cfg, n, p, ds["rowptr"], ds["col"], ds["val"], y, w0, w, v)
+        pos = port.stream_pos()
+        port.set_streams(None, None, None)
+        assert pos["overrun"] == 0
         (gw0, gw, gv), _, _ = gpu_als(gpu_ctx, prec, ds, y, task, L.MCMC, k, w0, w, v, sweeps, enable_v, l2_w0=0.1,
                                       streams=(normals, gammas, rands))
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol, (prec, relerr(gw0, rw0), relerr(gw, rw), relerr(gv, rv))

@@ -121,7 +121,7 @@ def test_fm_train_predict_matches_oracle_end_to_end(port, solver):
     # fm.track replays the snapshots on (here) the training data: equals the train trace
     tk = A.fm_track(fit, data, normalize=False)
     assert relerr(tk["test"], fit["Trace"]["evaluation.train"]) < 1e-8
-    A.options(**{"FM.precision": "f32"})
+    A.options(**{"FM.precision": "auto"})
 
 
 @pytest.mark.gpu
@@ -147,7 +147,7 @@ def test_normalize_update_and_regression_clamp(port):
     assert np.abs(fit2["Model"]["w"] - fit["Model"]["w"]).max() > 0           # continued from the warm start
     with pytest.raises(ValueError, match="not the same"):
         A.fm_update(fit, A.fm_matrix(X, y, feature_names=["x%d" % i for i in range(p)]))
-    A.options(**{"FM.precision": "f32"})
+    A.options(**{"FM.precision": "auto"})
 
 
 @pytest.mark.gpu
@@ -172,4 +172,66 @@ def test_fm_update_with_kept_optimizer_state_equals_one_long_run():
         cold = A.fm_update(half, data)                           # the reference's fm.update: optimizer state restarts
         assert "State" not in cold and not np.array_equal(cold["Model"]["v"], long["Model"]["v"])
     finally:
-        A.options(**{"FM.precision": "f32", "FM.keep_state": False})
+        A.options(**{"FM.precision": "auto", "FM.keep_state": False})
+
+
+def test_default_precision_is_the_references_unless_throughput_mode_is_asked_for():
+    """ADVICE r1: a user who calls fm.train() with no options must get the reference's fp64 results (exact mode, every solver;
+    the reference's default solver is TDAP); fp32 is the throughput mode's default and otherwise an explicit opt-in"""
+    from fmwr_b200 import _lib as L
+    old = A.options()
+    try:
+        A.options(**{"FM.precision": "auto", "FM.mode": "exact"})
+        assert all(A._precision(s) == L.F64 for s in ("TDAP", "SGD", "FTRL", "ALS", "MCMC", None))
+        A.options(**{"FM.mode": "minibatch"})
+        assert A._precision("FTRL") == L.F32 and A._precision("ALS") == L.F64 and A._precision(None) == L.F64
+        A.options(**{"FM.precision": "f32", "FM.mode": "exact"})
+        assert A._precision("TDAP") == L.F32
+    finally:
+        A.options(**{"FM.precision": old["FM.precision"], "FM.mode": old["FM.mode"]})
+
+
+@pytest.mark.gpu
+def test_fm_matrix_is_uploaded_once_across_train_predict_update_track():
+    """the device copy of an fm.matrix is parked in a slot of that object (the R glue's external pointer), so
+    fm.train -> predict -> fm.update -> fm.track move the model and the labels but never X again; results equal the uncached calls"""
+    rng = np.random.default_rng(6)
+    n, p, k = 3000, 40, 4
+    X = rng.uniform(0.5, 1.5, (n, p)) * (rng.random((n, p)) < 0.25)
+    X[X.sum(1) == 0, 0] = 1.0
+    y01 = (rng.random(n) < 0.5).astype(float)
+    ctl = lambda: [A.model_control(factor_number=k, L2_w1=0.01), A.solver_control(max_iter=n - 1, solver=A.FTRL_solver()),
+                   A.track_control(step_size=1000)]
+    old = A.options()
+    try:
+        A.options(**{"FM.precision": "f64", "FM.seed": 2, "FM.mode": "exact", "FM.cache": False})
+        d0 = A.fm_matrix(X, y01)
+        f0 = A.fm_train(d0, normalize=True, control=ctl())
+        p0 = A.predict(f0, d0, normalize=True)
+        u0 = A.fm_update(f0, d0)
+        t0 = A.fm_track(u0, d0)
+        A.options(**{"FM.cache": True})
+        d1 = A.fm_matrix(X, y01)
+        ctx = A._ctx()
+        x_bytes = 12 * d1["features"]["size"] + 4 * n                 # value f64 + col i32 per entry, row_size i32 per row
+        model_bytes = 8 * (1 + p + p * k)
+        h0 = ctx.transfer_bytes()[0]
+        f1 = A.fm_train(d1, normalize=True, control=ctl())
+        h1 = ctx.transfer_bytes()[0]
+        assert h1 - h0 >= x_bytes                                       # the first call uploads X ...
+        p1 = A.predict(f1, d1, normalize=True)
+        u1 = A.fm_update(f1, d1)
+        h2 = ctx.transfer_bytes()[0]
+        assert h2 - h1 < x_bytes and h2 - h1 <= 4 * model_bytes + 8 * n + 4096      # ... the next ones only models (and re-coded labels)
+        # a call that does NOT normalize sees the values as uploaded again
+        p_raw = A.predict(f1, d1, normalize=False)
+        A.options(**{"FM.cache": False})
+        p_raw0 = A.predict(f0, A.fm_matrix(X), normalize=False)
+        assert np.array_equal(p_raw, p_raw0)
+        A.options(**{"FM.cache": True})
+        t1 = A.fm_track(u1, d1)
+        for a, b in ((f0, f1), (u0, u1)):
+            assert np.array_equal(a["Model"]["w"], b["Model"]["w"]) and np.array_equal(a["Model"]["v"], b["Model"]["v"]) and a["Model"]["w0"] == b["Model"]["w0"]
+        assert np.array_equal(p0, p1) and np.array_equal(t0["test"], t1["test"])
+    finally:
+        A.options(**{"FM.precision": old["FM.precision"], "FM.mode": old["FM.mode"], "FM.cache": old["FM.cache"], "FM.seed": old["FM.seed"]})

@@ -301,25 +301,34 @@ __device__ __forceinline__ void peer_wait(const PeerArgs& pa, int flag_base, int
 
 // Variants for a kernel that runs BOTH sides of a barrier itself (forward_stream.cuh fuses the partial pass and the owner's
 // reduction): the epoch to publish / wait for is passed in, because the local epoch word is bumped by this very kernel's last
-// CTA and a CTA that reads it "before or after?" would race.  `extra` runs once, in the last CTA, before the flags go out.
-template <class F>
-__device__ __forceinline__ void peer_signal_ep(const PeerArgs& pa, int flag_base, int epoch_word, int count_word, uint32_t ep, F&& extra)
+// CTA and a CTA that reads it "before or after?" would race.
+// peer_arrive_last: every thread of every CTA calls it at the end of a phase; returns true in ALL threads of the CTA that arrived
+// last (whose threads then see every other CTA's stores); peer_publish: that CTA's thread 0 sends the flags out.
+__device__ __forceinline__ bool peer_arrive_last(const PeerArgs& pa, int count_word)
+{
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
+    __threadfence_system();                                   // this CTA's (local and peer) stores before the count
+    const unsigned done = atomicAdd(ctl + count_word, 1u);
+    s_last = done == gridDim.x - 1;
+    if (s_last) { ctl[count_word] = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  return s_last != 0;
+}
+
+__device__ __forceinline__ void peer_publish(const PeerArgs& pa, int flag_base, int epoch_word, uint32_t ep)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
+    ctl[epoch_word] = ep;
     __threadfence_system();
-    const unsigned done = atomicAdd(ctl + count_word, 1u);
-    if (done == gridDim.x - 1) {
-      ctl[count_word] = 0u;
-      ctl[epoch_word] = ep;
-      __threadfence();                                        // the other CTAs' (local) stores before `extra` reads them
-      extra();
-      __threadfence_system();
 #pragma unroll
-      for (int h = 0; h < 8; ++h)
-        if (h < pa.world) st_release_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
-    }
+    for (int h = 0; h < 8; ++h)
+      if (h < pa.world) st_release_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
   }
 }
 
@@ -401,6 +410,8 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int64_t row_begin, int32_t n_fields, c
 void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);
 fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1);
 fmwr_data* data_concat_rows(fmwr_data* const* parts, int n_parts);
+fmwr_data* data_gather_rows(fmwr_data* src, const uint32_t* order_dev, int64_t m);
+std::vector<uint32_t> visit_order_host(const fmwr_data* d, const fmwr_solver_cfg* s);
 void link_table_eval(fmwr_ctx* ctx, int which, int64_t n, const double* x, double* out);
 
 }  // namespace fmwr

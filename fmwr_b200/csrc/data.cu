@@ -935,6 +935,49 @@ fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1)
   return d;
 }
 
+// ------------------------------------------------------------------------------------------ row gather
+__global__ void gather_row_sizes(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ order, int64_t m, uint32_t* __restrict__ cnt)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) { const uint32_t r = order[i]; cnt[i] = rowptr[r + 1] - rowptr[r]; }
+}
+__global__ void gather_row_entries(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ y,
+                                   const uint32_t* __restrict__ order, const uint32_t* __restrict__ new_rowptr, int64_t m,
+                                   uint32_t* __restrict__ ocol, float* __restrict__ oval, float* __restrict__ oy)
+{
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= m) return;
+  const uint32_t r = order[i], b = rowptr[r], cnt = rowptr[r + 1] - b, ob = new_rowptr[i];
+  for (uint32_t j = threadIdx.x & 31; j < cnt; j += 32) { ocol[ob + j] = col[b + j]; oval[ob + j] = val[b + j]; }
+  if (oy && (threadIdx.x & 31) == 0) oy[i] = y[r];
+}
+
+// rows order[0], order[1], ... of src (repeats allowed) as a dataset of its own: how the throughput mode follows a strided
+// visit sequence (random_step > 1) -- its batches are consecutive VISITS
+fmwr_data* data_gather_rows(fmwr_data* src, const uint32_t* order_dev, int64_t m)
+{
+  fmwr_ctx* ctx = src->ctx;
+  fmwr_data* d = new fmwr_data();
+  try {
+    d->ctx = ctx; d->n = m; d->p = src->p;
+    d->rowptr.alloc(m + 1);
+    DBuf<uint32_t> cnt;
+    cnt.alloc(m + 1);
+    FMWR_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * (m + 1), ctx->stream));
+    if (m > 0) FMWR_LAUNCH(ctx, gather_row_sizes, ceil_div(m, 256), 256, 0, src->rowptr.p, order_dev, m, cnt.p);
+    exclusive_scan_u32(ctx, cnt.p, d->rowptr.p, m + 1);
+    uint32_t total = 0;
+    FMWR_CUDA(cudaMemcpy(&total, d->rowptr.p + m, 4, cudaMemcpyDeviceToHost));
+    d->nnz = total;
+    d->col.alloc(total); d->val.alloc(total);
+    if (src->has_labels) { d->y.alloc(m); d->has_labels = true; d->min_y = src->min_y; d->max_y = src->max_y; }
+    if (m > 0) FMWR_LAUNCH(ctx, gather_row_entries, ceil_div(m * 32, 256), 256, 0, src->rowptr.p, src->col.p, src->val.p, src->has_labels ? src->y.p : nullptr,
+                           order_dev, d->rowptr.p, m, d->col.p, d->val.p, src->has_labels ? d->y.p : nullptr);
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) { delete d; throw; }
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------ row concatenation
 __global__ void add_offset_u32(const uint32_t* __restrict__ in, int64_t n, uint32_t off, uint32_t* __restrict__ out)
 {

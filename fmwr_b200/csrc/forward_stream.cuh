@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
     const PeerArgs& pa = a.pa;
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
     const uint32_t ep = ep_base + 1u;
-    peer_signal_ep(pa, PEER_FLAG1, PEER_EPOCH1, PEER_COUNT1, ep, [] {});
+    if (peer_arrive_last(pa, PEER_COUNT1)) peer_publish(pa, PEER_FLAG1, PEER_EPOCH1, ep);
     peer_wait_ep(pa, PEER_FLAG1, ep);
     const int rpo = pa.rows_per_owner;
     const int r_lo = pa.rank * rpo;
@@ -200,14 +200,22 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
       for (int i = 0; i < (int)(blockDim.x >> 5) * 4; ++i) t += s_msum[i];
       part[blockIdx.x] = t;
     }
-    const int nblk = gridDim.x;
-    peer_signal_ep(pa, PEER_FLAG2, PEER_EPOCH2, PEER_COUNT2, ep, [&] {
+    if (peer_arrive_last(pa, PEER_COUNT2)) {
+      // the CTA that arrived last adds the CTAs' partial sums in a fixed order (deterministic), all threads fetching in parallel
       double t = 0.0;
-      for (int i = 0; i < nblk; ++i) t += *reinterpret_cast<volatile double*>(part + i);
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(part + i);
+      __shared__ double s_fin[256];
+      s_fin[threadIdx.x] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) tot += s_fin[i];
 #pragma unroll
-      for (int h = 0; h < 8; ++h)
-        if (h < pa.world) reinterpret_cast<double*>(pa.base[h] + pa.off_msum)[pa.rank] = t;
-    });
+        for (int h = 0; h < 8; ++h)
+          if (h < pa.world) reinterpret_cast<double*>(pa.base[h] + pa.off_msum)[pa.rank] = tot;
+      }
+      peer_publish(pa, PEER_FLAG2, PEER_EPOCH2, ep);
+    }
     (void)ctl;
   }
 }

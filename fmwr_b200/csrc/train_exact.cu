@@ -574,6 +574,27 @@ int tracker_step_size(int step_size, int max_iter)
   return step_size;
 }
 
+// The sample visit sequence when it is not the plain scan: the caller's explicit list, or strides of 1 + floor(U * random_step)
+// drawn from glibc rand() like random_select (reference src/util/Random.h:126-132; scan loops SGD_Learner.h:84-88).  Empty result:
+// the plain scan i = 1 .. n-1 (F5).  Shared by the exact and the throughput mode.
+std::vector<uint32_t> visit_order_host(const fmwr_data* d, const fmwr_solver_cfg* s)
+{
+  std::vector<uint32_t> order_host;
+  const int64_t max_iter = s->max_iter;
+  if (s->visit_order && s->n_visit > 0) {
+    order_host.assign(s->visit_order, s->visit_order + s->n_visit);
+  } else if (s->random_step > 1) {
+    auto draw = [&]() -> uint32_t { return (uint32_t)((std::rand() / ((double)RAND_MAX + 1)) * s->random_step + 1); };
+    while ((int64_t)order_host.size() < max_iter) {
+      const size_t before = order_host.size();
+      for (uint32_t i = draw(); i < (uint32_t)d->n && (int64_t)order_host.size() < max_iter; i += draw()) order_host.push_back(i);
+      if (order_host.size() == before && d->n <= 1) break;
+    }
+  }
+  for (uint32_t r : order_host) FMWR_REQUIRE((int64_t)r < d->n, FMWR_ERR_ARG, "visit_order entry out of range");
+  return order_host;
+}
+
 template <class T>
 static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
 {
@@ -597,20 +618,9 @@ static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr
   // 1 + floor(U * random_step) from glibc rand() (reference src/util/Random.h:126-132); the caller may pass
   // the sequence explicitly (visit_order) so both sides of a comparison use the same one.
   DBuf<uint32_t> order_dev;
-  std::vector<uint32_t> order_host;
   const int64_t max_iter = s->max_iter;
-  if (s->visit_order && s->n_visit > 0) {
-    order_host.assign(s->visit_order, s->visit_order + s->n_visit);
-  } else if (s->random_step > 1) {
-    auto draw = [&]() -> uint32_t { return (uint32_t)((std::rand() / ((double)RAND_MAX + 1)) * s->random_step + 1); };
-    while ((int64_t)order_host.size() < max_iter) {
-      const size_t before = order_host.size();
-      for (uint32_t i = draw(); i < (uint32_t)d->n && (int64_t)order_host.size() < max_iter; i += draw()) order_host.push_back(i);
-      if (order_host.size() == before && d->n <= 1) break;
-    }
-  }
+  std::vector<uint32_t> order_host = visit_order_host(d, s);
   if (!order_host.empty()) {
-    for (uint32_t r : order_host) FMWR_REQUIRE((int64_t)r < d->n, FMWR_ERR_ARG, "visit_order entry out of range");
     order_dev.alloc(order_host.size());
     FMWR_CUDA(cudaMemcpyAsync(order_dev.p, order_host.data(), 4 * order_host.size(), cudaMemcpyHostToDevice, ctx->stream));
     a.order = order_dev.p; a.order_len = (int64_t)order_host.size();

@@ -177,6 +177,22 @@ mb_finalize_kernel(const float* __restrict__ y, const double* __restrict__ scal,
   }
 }
 
+// tracker on a feature-sharded model: summed partials -> score -> link -> prediction (one warp per row)
+template <class T>
+__global__ void __launch_bounds__(256)
+mb_score_kernel(const double* __restrict__ scal, int kp, int k0, int rows, const T* __restrict__ Scache, int s_stride, int link, double lo, double hi,
+                const double* __restrict__ pnY, double* __restrict__ out)
+{
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const T* row = Scache + (size_t)r * s_stride;
+  T acc = T(0);
+  for (int f = lane; f < kp; f += 32) { const T sv = row[f]; acc += T(0.5) * sv * sv; }
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = apply_link(link, (double)((k0 ? T(scal[0]) : T(0)) + row[kp] + acc), lo, hi, pnY);
+}
+
 // ---- K2: one lane group per (batch, feature) segment --------------------------------------------
 template <class T>
 struct MbUpdArgs {
@@ -754,12 +770,60 @@ static SolverParams<T> params_from(const SolverParams<double>& d)
 
 SolverParams<double> make_params_f64(const fmwr_model* m, const fmwr_solver_cfg* s);
 
+// Tracker on a feature-sharded model (reference: the full predict_batch + metric inside the epoch, src/solver/SGD_Learner.h:140-166).
+// Nothing is gathered: every rank forwards ITS column slice over all rows in chunks, the chunk's partials (S_f, additive scalar) are
+// summed over the ranks, and every rank finishes score -> link -> metric on the identical totals, so all ranks record the same value.
 template <class T>
-static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr)
+static double tracker_score_sharded(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s)
+{
+  const int64_t n = d->n;
+  const int s_stride = m->kp + 4;
+  const int64_t chunk = 65536;
+  DBuf<T> buf;
+  buf.alloc((size_t)chunk * s_stride);
+  buf.zero(ctx->stream);
+  d->pred64.ensure(n);
+  d->pred_prec = FMWR_F64;
+  const int link = m->cfg.task == FMWR_REGRESSION ? FMWR_LINK_CLAMP : FMWR_LINK_LOGISTIC;
+  MbLaunch<T> L;
+  memset(&L.ua, 0, sizeof L.ua);
+  memset(&L.pa, 0, sizeof L.pa);
+  L.ctx = ctx; L.m = m; L.d = d; L.s = s; L.mult = nullptr; L.Scache = buf.p; L.s_stride = s_stride; L.partial = 1; L.fused_exchange = false;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int rows = (int)std::min<int64_t>(chunk, n - r0);
+    L.row_begin = r0; L.rows = rows; L.phase = 0;
+    dispatch_layout<T>(m->kp, L);
+    comm_allreduce_sum(ctx, buf.p, (size_t)rows * s_stride, sizeof(T) == 8);
+    FMWR_LAUNCH(ctx, mb_score_kernel<T>, ceil_div(rows, 8), 256, 0, (const double*)m->scal.p, m->kp, m->cfg.keep_w0, rows, buf.p, s_stride, link,
+                (double)s->min_target, (double)s->max_target, ctx->pn_table.p, d->pred64.p + r0);
+  }
+  return evaluate_dev(ctx, d, m->cfg.task, s->metric);
+}
+
+template <class T>
+static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr_solver_cfg* s, fmwr_trace* tr, fmwr_data* eval_d = nullptr)
 {
   FMWR_REQUIRE(s->batch_size > 0, FMWR_ERR_ARG, "batch_size must be positive in minibatch mode");
-  FMWR_REQUIRE(s->random_step <= 1 && !s->visit_order, FMWR_ERR_UNSUPPORTED,
-               "minibatch mode scans rows in storage order (random_step must be 1)");
+  if (!eval_d) eval_d = d;
+  if (s->random_step > 1 || (s->visit_order && s->n_visit > 0)) {
+    // strided / explicit visit sequence (reference random_select, src/util/Random.h:126-132): the visited rows are gathered, in
+    // visit order, into a dataset of their own and the batches are consecutive visits; the tracker still scores the full data
+    FMWR_REQUIRE(!(ctx->nccl_comm && ctx->world > 1), FMWR_ERR_UNSUPPORTED, "random_step > 1 is not available on a feature-sharded model");
+    std::vector<uint32_t> order = visit_order_host(d, s);
+    if ((int64_t)order.size() > (int64_t)s->max_iter) order.resize(s->max_iter);
+    if (order.empty()) { if (tr) tr->iters_done = 0; return; }
+    DBuf<uint32_t> order_dev;
+    order_dev.alloc(order.size());
+    FMWR_CUDA(cudaMemcpyAsync(order_dev.p, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::unique_ptr<fmwr_data> visited(data_gather_rows(d, order_dev.p, (int64_t)order.size()));
+    fmwr_solver_cfg s2 = *s;
+    s2.random_step = 1; s2.visit_order = nullptr; s2.n_visit = 0;
+    s2.compat &= ~FMWR_COMPAT_SKIP_ROW0;                   // the sequence already says which rows are visited
+    s2.max_iter = (int32_t)order.size();
+    train_minibatch_t<T>(ctx, m, visited.get(), &s2, tr, eval_d);
+    return;
+  }
   const SolverParams<double> spd = make_params_f64(m, s);
   const bool kept_state = model_alloc_state(m, solver_state_count(spd), s->solver, s->warm_state != 0);
 
@@ -772,7 +836,6 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
 
   // single GPU: S cache rows are kp wide.  Feature-parallel: kp + 4 (S_f, the additive scalar, padding to keep 16-byte rows)
   const bool multi = ctx->nccl_comm != nullptr && ctx->world > 1;
-  FMWR_REQUIRE(!(multi && s->step_size > 0), FMWR_ERR_UNSUPPORTED, "the tracker is not available on a feature-sharded model (score the gathered model instead)");
   const int s_stride = multi ? m->kp + 4 : m->kp;
   // peer window open: the exchange runs inside our own kernels (NVLink stores + flags), no NCCL call per batch
   const bool peer = multi && ctx->peer.ready && getenv("FMWR_NO_PEER") == nullptr;
@@ -899,7 +962,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
       if (use_graph && ++captured >= GRAPH_CHUNK) flush_graph();
       if (step > 0 && (iter > next_track || iter >= max_iter)) {
         // tracker at batch granularity: one record per step_size samples crossed (and at the end)
-        const double score = tracker_score(ctx, m, d, s);
+        const double score = multi ? tracker_score_sharded<T>(ctx, m, eval_d, s) : tracker_score(ctx, m, eval_d, s);
         if (n_rec > 1 && std::fabs((score - old_score) / (old_score + 1e-30)) <= s->convergence) conv_times++;
         else conv_times = 0;
         old_score = score;

@@ -96,6 +96,36 @@ def main():
             moved = float(np.max(np.abs(sv - v2)))
             print("fused exchange (k=32, fp32) solver=%d world=%d max rel err vs single GPU = %.3e (params moved by %.3e)" % (solver, world, err, moved), flush=True)
             ok = ok and err < 2e-4 and moved > 1e-3
+    # tracker on the sharded model (step_size > 0): every rank scores its slice's partials through one all-reduce per chunk and
+    # records the same train metric the single-GPU run records (reference: SGD_Learner.h:140-166)
+    iters = 2 * (n - 1)
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l1_w1=1e-3, l2_w1=1e-3, l2_v=1e-3)
+    sc = L.SolverCfg(solver=L.FTRL, max_iter=iters, random_step=1, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0, min_target=-1.0, max_target=1.0,
+                     mode=L.MODE_MINIBATCH, batch_size=B, precision=L.F64, compat=L.COMPAT_SKIP_ROW0, step_size=5000, metric=L.LL, convergence=0.0)
+    full = L.Data.from_csr32(ctx, n, p, rowptr, col, val, y)
+    part = full.slice_columns(c0, c1)
+    full.close()
+    m = L.Model(ctx, mc, c1 - c0, L.F64)
+    m.set(w0, w[c0:c1], v[c0:c1])
+    trb = L.TraceBuf(20)
+    L.train_dev(ctx, m, part, sc, trb)
+    mine_tr = trb.result()
+    m.close(); part.close()
+    trs = [None] * world
+    dist.all_gather_object(trs, (mine_tr["eval_train"], mine_tr["rec_index"]))
+    if rank == 0:
+        solo = L.Context(local)
+        d1 = L.Data.from_csr32(solo, n, p, rowptr, col, val, y)
+        m1 = L.Model(solo, mc, p, L.F64)
+        m1.set(w0, w, v)
+        tr1 = L.TraceBuf(20)
+        L.train_dev(solo, m1, d1, sc, tr1)
+        r1 = tr1.result()
+        m1.close(); d1.close(); solo.close()
+        same_idx = all(np.array_equal(t[1], r1["rec_index"]) for t in trs)
+        terr = max(float(np.max(np.abs(t[0] - r1["eval_train"]) / np.maximum(1, np.abs(r1["eval_train"])))) for t in trs) if same_idx and len(r1["eval_train"]) else 1.0
+        print("sharded tracker: %d records, max rel err of the train metric vs single GPU = %.3e" % (len(r1["eval_train"]), terr), flush=True)
+        ok = ok and same_idx and len(r1["eval_train"]) >= 3 and terr < 1e-9
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     ctx.comm_destroy(); ctx.close()

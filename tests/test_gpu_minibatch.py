@@ -292,3 +292,43 @@ def test_minibatch_parity_in_the_benchmark_regime(gpu_ctx, port, solver):
     assert ll_r < 0.69
     assert abs(ll_g - ll_r) / ll_r < 0.03, (ll_g, ll_r)
     assert abs(auc_g - auc_r) < 0.02, (auc_g, auc_r)
+
+
+def test_throughput_mode_follows_a_strided_visit_sequence(gpu_ctx):
+    """random_step > 1 (reference random_select, src/util/Random.h:126-132; scan loops SGD_Learner.h:84-88): the throughput mode
+    batches consecutive VISITS.  With an explicit visit sequence and batch = 1 it equals the exact mode on the same sequence;
+    with the engine's own rand()-driven strides and a real batch it trains and reports the visits it made."""
+    rng = np.random.default_rng(21)
+    rowptr, col, val = synth.random_csr(500, 60, 7, seed=22)
+    n, p, k = 500, 60, 4
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k))
+    visit = []
+    while len(visit) < 1300:                                # three passes of strides 1..4, ascending inside a pass
+        i = int(rng.integers(1, 5))
+        while i < n and len(visit) < 1300:
+            visit.append(i); i += int(rng.integers(1, 5))
+    visit = np.array(visit, np.uint32)
+
+    def run(mode, batch, visit_order=None, random_step=1, max_iter=1300):
+        d = L.Data.from_csr32(gpu_ctx, n, p, rowptr, col, val, y)
+        m = L.Model(gpu_ctx, L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w1=0.01, l2_v=0.01), p, L.F64)
+        m.set(0.1, w, v)
+        sc = L.SolverCfg(solver=L.FTRL, max_iter=max_iter, random_step=random_step, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0, min_target=-1.0,
+                         max_target=1.0, mode=mode, batch_size=batch, precision=L.F64, compat=L.COMPAT_SKIP_ROW0, step_size=-1)
+        keep = None
+        if visit_order is not None:
+            keep = np.ascontiguousarray(visit_order, np.uint32)
+            sc.visit_order = L.ptr(keep); sc.n_visit = keep.size
+        tr = L.TraceBuf(4)
+        L.train_dev(gpu_ctx, m, d, sc, tr, keep=(keep,))
+        out = m.get()
+        m.close(); d.close()
+        return out, tr.result()
+
+    a, ta = run(L.MODE_MINIBATCH, 1, visit)
+    b, tb = run(L.MODE_EXACT, 1, visit)
+    assert ta["iters_done"] == tb["iters_done"] == 1300
+    assert relerr(a[0], b[0]) < 1e-10 and relerr(a[1], b[1]) < 1e-10 and relerr(a[2], b[2]) < 1e-10
+    c, tc = run(L.MODE_MINIBATCH, 64, None, random_step=3, max_iter=900)
+    assert tc["iters_done"] == 900 and np.isfinite(c[2]).all() and float(np.max(np.abs(c[2] - v))) > 1e-3

@@ -725,6 +725,38 @@ def multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, prec, solve
     return err
 
 
+def multi_parity_als(L, multi, dist, ctx, rank, world, local, solver, n_rows):
+    """row-sharded ALS / MCMC against one GPU: every rank must end the sweeps with the model the single-GPU run ends with
+    (MCMC: same seed -> same counter-based draws); returns max |a-b| / max(1,|b|) on rank 0"""
+    afields, k = [138493, 26744, 2048], 8
+    p = sum(afields)
+    a0, a1 = multi.row_partition(n_rows, world)[rank]
+    mc = L.ModelCfg(task=L.REGRESSION, keep_w0=1, keep_w1=1, k=k)
+    sc = L.SolverCfg(solver=solver, max_iter=2, random_step=1, min_target=0.5, max_target=5.0, mode=L.MODE_EXACT, precision=L.F64,
+                     compat=L.COMPAT_REFERENCE, enable_v=1, step_size=-1, seed=7)
+    d = L.Data.synth_rows(ctx, a0, a1 - a0, afields, [0, 1, 0], 0, 3, 0.3, 20240601)
+    m = L.Model(ctx, mc, p, L.F64)
+    m.init_random(0.0, 0.01, 20240603)
+    start = m.get()
+    L.train_dev(ctx, m, d, sc)
+    mine = m.get()
+    m.close(); d.close()
+    err = None
+    if rank == 0:
+        solo = L.Context(local)
+        d1 = L.Data.synth(solo, n_rows, afields, [0, 1, 0], 0, 3, 0.3, 20240601)
+        m1 = L.Model(solo, mc, p, L.F64)
+        m1.set(*start)
+        L.train_dev(solo, m1, d1, sc)
+        sw0, sw, sv = m1.get()
+        m1.close(); d1.close(); solo.close()
+        err = max(abs(mine[0] - sw0) / max(1.0, abs(sw0)), float(np.max(np.abs(mine[1] - sw) / np.maximum(1, np.abs(sw)))),
+                  float(np.max(np.abs(mine[2] - sv) / np.maximum(1, np.abs(sv)))))
+        if not float(np.max(np.abs(sv - start[2]))) > 1e-4:
+            err = float("inf")
+    return err
+
+
 def run_c5(L, multi, dist, ctx, args, rank, world, timed, peak):
     """BASELINE configs[4]: SGD / TDAP minibatch epochs + predict on 100M rows x 39 nnz, 50M features, k=32, sharded over the box.
     Training is feature-parallel (every rank: all rows, its fields' columns, generated in row chunks on the device);
@@ -886,12 +918,17 @@ def run_engine_multi(args, rank, world, local):
         e64 = multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, L.F64, L.FTRL, args.parity_rows, 8192)
         e32 = multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, L.F32, L.FTRL, args.parity_rows, 8192)
         es = multi_parity(L, multi, dist, ctx, rank, world, local, fields, k, L.F64, L.SGD, args.parity_rows, 8192)
+        ea = multi_parity_als(L, multi, dist, ctx, rank, world, local, L.ALS, args.parity_rows)
+        em = multi_parity_als(L, multi, dist, ctx, rank, world, local, L.MCMC, args.parity_rows)
         if rank == 0:
-            parity = {"multi_vs_single_max_rel_err": e64, "ftrl_f32": e32, "sgd_f64": es, "rows": args.parity_rows, "batch": 8192, "epochs": 2,
+            parity = {"multi_vs_single_max_rel_err": e64, "ftrl_f32": e32, "sgd_f64": es, "als_f64": ea, "mcmc_f64": em,
+                      "rows": args.parity_rows, "batch": 8192, "epochs": 2,
                       "what": "max |a-b|/max(1,|b|) over (w0, w, V): FTRL fp64 (headline key), FTRL fp32 (the benchmarked precision; the S_f sums are "
-                              "split by shard, so fp32 differs by rounding), SGD fp64 -- %d GPUs (in-kernel peer exchange) against one GPU" % world,
-                      "asserted": "fp64 < 1e-8, fp32 < 5e-3"}
-        ok = [parity is None or (parity["multi_vs_single_max_rel_err"] < 1e-8 and parity["sgd_f64"] < 1e-8 and parity["ftrl_f32"] < 5e-3)]
+                              "split by shard, so fp32 differs by rounding), SGD fp64 -- %d GPUs (in-kernel peer exchange) against one GPU; "
+                              "als_f64 / mcmc_f64: two sweeps (w and V blocks) row-sharded against one GPU on a MovieLens-shaped prefix" % world,
+                      "asserted": "fp64 < 1e-8 (ALS / MCMC < 1e-6: their statistics are summed in a different order), fp32 < 5e-3"}
+        ok = [parity is None or (parity["multi_vs_single_max_rel_err"] < 1e-8 and parity["sgd_f64"] < 1e-8 and parity["ftrl_f32"] < 5e-3
+                                 and parity["als_f64"] < 1e-6 and parity["mcmc_f64"] < 1e-6)]
         dist.broadcast_object_list(ok, src=0)
         if not ok[0]:
             if rank == 0:

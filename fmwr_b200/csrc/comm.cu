@@ -60,6 +60,13 @@ void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64)
   ctx->launches++;
 }
 
+void comm_allreduce_sum_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count)
+{
+  FMWR_REQUIRE(ctx->nccl_comm, FMWR_ERR_COMM, "no communicator");
+  nccl_check(g_nccl.all_reduce(buf, buf, count, 3 /*ncclUint32*/, 0 /*ncclSum*/, ctx->nccl_comm, ctx->stream), "ncclAllReduce");
+  ctx->launches++;
+}
+
 void comm_allreduce_max_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count)
 {
   FMWR_REQUIRE(ctx->nccl_comm, FMWR_ERR_COMM, "no communicator");

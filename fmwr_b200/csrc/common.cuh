@@ -221,6 +221,7 @@ namespace fmwr {
 // NCCL all-reduces on the context's stream (comm.cu)
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 void comm_allreduce_max_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count);
+void comm_allreduce_sum_u32(fmwr_ctx* ctx, uint32_t* buf, size_t count);
 void peer_check_error(fmwr_ctx* ctx);   // throws FMWR_ERR_COMM (and clears the flag) when an in-kernel peer barrier timed out
 
 // ---- device helpers ----------------------------------------------------------------------------
@@ -237,7 +238,7 @@ __device__ __forceinline__ T warp_sum(T v)
 // [FLAG1 + 32 r]  arrival of rank r at barrier 1 (partials stored)      -- written by rank r into EVERY rank's window
 // [FLAG2 + 32 r]  arrival of rank r at barrier 2 (row totals stored)
 // EPOCH1/2, COUNT1/2, ERR: local words of the owning rank.  Flags sit in separate 128-byte lines.
-enum { PEER_FLAG1 = 0, PEER_FLAG2 = 256, PEER_EPOCH1 = 512, PEER_EPOCH2 = 513, PEER_COUNT1 = 514, PEER_COUNT2 = 515, PEER_ERR = 516,
+enum { PEER_FLAG1 = 0, PEER_FLAG2 = 256, PEER_EPOCH1 = 512, PEER_EPOCH2 = 513, PEER_COUNT1 = 514, PEER_COUNT2 = 515, PEER_ERR = 516, PEER_DEBUG = 768 /* 4 x u64 */,
        PEER_CTL_BYTES = 4096 };
 
 struct PeerArgs {
@@ -338,10 +339,13 @@ __device__ __forceinline__ void peer_wait_ep(const PeerArgs& pa, int flag_base, 
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
     const uint32_t* f = ctl + flag_base + 32 * threadIdx.x;
     const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(f) - ep) < 0) {
+    // poll with plain (relaxed, L1-bypassing) loads and acquire ONCE when the flag is there: an acquire at system scope
+    // invalidates the SM's L1, and hundreds of CTAs polling that way slow down the CTAs that are still computing
+    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(f) - ep) < 0) {
       if (clock64() - t0 > 40000000000ll) { ctl[PEER_ERR] = 1u; break; }
-      __nanosleep(64);
+      __nanosleep(32);
     }
+    (void)ld_acquire_sys(f);
   }
   __syncthreads();
 }

@@ -23,6 +23,7 @@ namespace fmwr {
 #ifndef FMWR_SF_BLOCKS
 #define FMWR_SF_BLOCKS 3     // 78 registers, no spills; at 4 (64 registers) ptxas rematerialises every shared-memory address per step
 #endif
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 enum { SF_PREDICT = 0, SF_TRAIN = 1, SF_PARTIAL = 2, SF_PARTIAL_PEER = 3 };
 
 struct SfArgs {
@@ -32,6 +33,7 @@ struct SfArgs {
   float lo, hi;
   int64_t row_begin; int64_t rows;       // rows [row_begin, row_begin + rows) of the data handle
   int rpg;                                // rows per 8-lane group (stream_grid)
+  int debug;                              // SF_PARTIAL_PEER: accumulate the phase timers (FMWR_PEER_DEBUG)
   double* out;                            // SF_PREDICT: raw scores (the link runs as a second, elementwise pass)
   float* mult; float* Scache; int s_stride;   // SF_TRAIN / SF_PARTIAL*: per-row multiplier and S cache (row index relative to row_begin)
   PeerArgs pa;
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
   const int group = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + g;
   const int rpg = a.rpg;
   uint32_t ep_base = 0u;
+  unsigned long long t_start = 0;
+  if (MODE == SF_PARTIAL_PEER && a.debug && threadIdx.x == 0) t_start = globaltimer_ns();
   if (MODE == SF_PARTIAL_PEER)       // EPOCH2 is only bumped after every CTA of the previous launch passed its last barrier: stable here
     ep_base = *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(peer_base(a.pa, a.pa.rank)) + PEER_EPOCH2);
   int r = (int)min((int64_t)group * rpg, a.rows);         // current row (relative to row_begin)
@@ -159,8 +163,14 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
     const PeerArgs& pa = a.pa;
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
     const uint32_t ep = ep_base + 1u;
+    // FMWR_PEER_DEBUG: where a CTA's time goes (ns summed over CTAs and launches): [0] partial pass, [1] first barrier, [2] owner's
+    // reduction, [3] CTAs counted
+    unsigned long long* dbg = a.debug ? reinterpret_cast<unsigned long long*>(ctl + PEER_DEBUG) : nullptr;
+    unsigned long long t1 = 0, t2 = 0;
+    if (dbg && threadIdx.x == 0) { t1 = globaltimer_ns(); atomicAdd(dbg + 0, t1 - t_start); atomicAdd(dbg + 3, 1ull); }
     if (peer_arrive_last(pa, PEER_COUNT1)) peer_publish(pa, PEER_FLAG1, PEER_EPOCH1, ep);
     peer_wait_ep(pa, PEER_FLAG1, ep);
+    if (dbg && threadIdx.x == 0) { t2 = globaltimer_ns(); atomicAdd(dbg + 1, t2 - t1); }
     const int rpo = pa.rows_per_owner;
     const int r_lo = pa.rank * rpo;
     const int n_local = max(0, (int)min((int64_t)(r_lo + rpo), a.rows) - r_lo);
@@ -191,6 +201,7 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
       }
       msum += (double)m;
     }
+    if (dbg && threadIdx.x == 0) atomicAdd(dbg + 2, globaltimer_ns() - t2);
     __shared__ double s_msum[32];
     if (l == 0) s_msum[(threadIdx.x >> 5) * 4 + g] = msum;
     __syncthreads();
@@ -200,7 +211,9 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
       for (int i = 0; i < (int)(blockDim.x >> 5) * 4; ++i) t += s_msum[i];
       part[blockIdx.x] = t;
     }
-    if (peer_arrive_last(pa, PEER_COUNT2)) {
+    const bool last2 = peer_arrive_last(pa, PEER_COUNT2);
+    if (dbg && threadIdx.x == 0) atomicAdd(dbg + 4, globaltimer_ns() - t_start);      // [4] kernel start -> second arrival, per CTA
+    if (last2) {
       // the CTA that arrived last adds the CTAs' partial sums in a fixed order (deterministic), all threads fetching in parallel
       double t = 0.0;
       for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(part + i);
@@ -215,6 +228,7 @@ __global__ void __launch_bounds__(256, FMWR_SF_BLOCKS) forward_stream_kernel(SfA
           if (h < pa.world) reinterpret_cast<double*>(pa.base[h] + pa.off_msum)[pa.rank] = tot;
       }
       peer_publish(pa, PEER_FLAG2, PEER_EPOCH2, ep);
+      if (dbg && threadIdx.x == 0) { atomicAdd(dbg + 5, globaltimer_ns() - t_start); atomicAdd(dbg + 6, 1ull); }    // [5] start -> flags out (last CTA)
     }
     (void)ctl;
   }
@@ -245,10 +259,12 @@ inline int stream_grid(const fmwr_ctx* ctx, int64_t rows, int* rpg_out)
 }
 
 // the stream kernels serve fp32 models whose padded row is exactly 32 floats, on data with rows long enough to keep a ring busy
-inline bool stream_forward_ok(const fmwr_model* m, int64_t nnz, int64_t n)
+// (min_nnz_per_row: 8 for whole rows; the column slices of a feature-sharded model have 39/N non-zeros per row and still take the
+// stream kernel, which then also runs the exchange)
+inline bool stream_forward_ok(const fmwr_model* m, int64_t nnz, int64_t n, int min_nnz_per_row = 8)
 {
   const bool off = getenv("FMWR_NO_STREAM") != nullptr;     // read per call: tests flip it
-  return !off && m->prec == FMWR_F32 && m->kp == 32 && n > 0 && nnz >= 8 * n;
+  return !off && m->prec == FMWR_F32 && m->kp == 32 && n > 0 && nnz >= (int64_t)min_nnz_per_row * n;
 }
 
 }  // namespace fmwr

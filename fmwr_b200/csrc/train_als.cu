@@ -1553,24 +1553,16 @@ static bool has_thin_columns(fmwr_ctx* ctx, fmwr_data* d)
     cnt.zero(ctx->stream);
     FMWR_CUDA(cudaMemsetAsync(mn.p, 0xff, 4, ctx->stream));
     if (d->nnz > 0) FMWR_LAUNCH(ctx, col_count_kernel, ceil_div(d->nnz, 256), 256, 0, d->col.p, d->nnz, cnt.p);
+    // row shards: a column's count is the sum over the shards (a shard alone sees a fraction of every column and would call
+    // almost any data thin); every rank then derives the same answer
+    if (ctx->nccl_comm && ctx->world > 1 && d->p > 0) comm_allreduce_sum_u32(ctx, cnt.p, (size_t)d->p);
     if (d->p > 0) FMWR_LAUNCH(ctx, col_count_min_kernel, ceil_div(d->p, 256), 256, 0, cnt.p, d->p, mn.p);
     uint32_t h = 0;
     FMWR_CUDA(cudaMemcpyAsync(&h, mn.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
     d->min_col_nnz = h == 0xffffffffu ? (1ll << 40) : (int64_t)h;
   }
-  uint32_t flag = d->min_col_nnz <= 2 ? 1u : 0u;
-  if (ctx->nccl_comm && ctx->world > 1) {
-    // row shards: a shard sees only its part of a column, so "thin here" over-approximates "thin overall"; what matters is
-    // that every rank takes the same branch
-    DBuf<uint32_t> f;
-    f.alloc(1);
-    FMWR_CUDA(cudaMemcpyAsync(f.p, &flag, 4, cudaMemcpyHostToDevice, ctx->stream));
-    comm_allreduce_max_u32(ctx, f.p, 1);
-    FMWR_CUDA(cudaMemcpyAsync(&flag, f.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  return flag != 0u;
+  return d->min_col_nnz <= 2;
 }
 
 template <class A, class B>

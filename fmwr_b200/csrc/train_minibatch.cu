@@ -151,7 +151,10 @@ mb_exchange_kernel(const float* __restrict__ y, const double* __restrict__ scal,
         T* dst = reinterpret_cast<T*>(pa.base[h] + pa.off_S) + (size_t)r * s_stride;
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) reinterpret_cast<V16*>(dst)[ch * LPR + l] = arr_to_vec(S[ch]);
-        if (l == 0) *reinterpret_cast<V16*>(dst + kp) = arr_to_vec(tail);
+        if (l == 0) {
+          *reinterpret_cast<V16*>(dst + kp) = arr_to_vec(tail);
+          reinterpret_cast<T*>(pa.base[h] + pa.off_mult)[r] = m;     // compact copy: the intercept block of K2 sums these with unit stride
+        }
       }
     }
   }
@@ -208,6 +211,7 @@ struct MbUpdArgs {
   int mult_stride;                      // 1, or the S-cache row stride when the multiplier lives in the row's padding (peer mode)
   int peer;                             // peer-window exchange: wait for every rank's row totals first
   const double* msum; int msum_n;       // fused exchange: the ranks' sums of multipliers (else the intercept block sums a.mult itself)
+  const T* mult_compact;                // unfused peer exchange: the multipliers once more with unit stride (a.mult is strided there)
   PeerArgs pa;
 };
 
@@ -232,15 +236,17 @@ __device__ __forceinline__ void mb_intercept(const MbUpdArgs<T>& a)
     if (threadIdx.x == 0) for (int i = 0; i < a.msum_n; ++i) acc += a.msum[i];      // rank order: every rank forms the same sum
   } else {
     constexpr int UN = 16;
+    const T* mp = a.mult_compact ? a.mult_compact : a.mult;
+    const size_t ms = a.mult_compact ? 1 : (size_t)a.mult_stride;
     int r = threadIdx.x;
     for (; r + (UN - 1) * nt < a.rows; r += UN * nt) {
       T t[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) t[u] = a.mult[(size_t)(r + u * nt) * a.mult_stride];
+      for (int u = 0; u < UN; ++u) t[u] = mp[(size_t)(r + u * nt) * ms];
 #pragma unroll
       for (int u = 0; u < UN; ++u) acc += (double)t[u];
     }
-    for (; r < a.rows; r += nt) acc += (double)a.mult[(size_t)r * a.mult_stride];
+    for (; r < a.rows; r += nt) acc += (double)mp[(size_t)r * ms];
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -656,6 +662,7 @@ struct MbLaunch {
     a.scal = (const double*)m->scal.p; a.k0 = m->cfg.keep_w0; a.k1 = m->cfg.keep_w1; a.task = m->cfg.task;
     a.lo = (float)s->min_target; a.hi = (float)s->max_target; a.row_begin = row_begin; a.rows = rows;
     a.mult = (float*)mult; a.Scache = (float*)Scache; a.s_stride = s_stride; a.pa = pa;
+    a.debug = getenv("FMWR_PEER_DEBUG") != nullptr;
     const int grid = stream_grid(ctx, rows, &a.rpg);
     if (partial == 2) FMWR_LAUNCH(ctx, forward_stream_kernel<SF_PARTIAL_PEER>, grid, 256, 0, a);
     else if (partial == 1) FMWR_LAUNCH(ctx, forward_stream_kernel<SF_PARTIAL>, grid, 256, 0, a);
@@ -707,7 +714,7 @@ struct MbLaunch {
       FMWR_LAUNCH(ctx, (mb_exchange_kernel<TT, LPR, CH>), xgrid, 256, 0, d->y.p, (const double*)m->scal.p, m->kp, m->cfg.keep_w0,
                   m->cfg.task, TT(s->min_target), TT(s->max_target), row_begin, rows, s_stride, pa);
     } else if (phase == 0) {
-      if (sizeof(TT) == 4 && stream_forward_ok(m, d->nnz, d->n) && (partial != 2 || fused_exchange)) { k1_stream(); return; }
+      if (sizeof(TT) == 4 && (partial == 2 ? fused_exchange : stream_forward_ok(m, d->nnz, d->n, partial ? 2 : 8))) { k1_stream(); return; }
       const int tm = team_mode(d->nnz, d->n, LPR);
       if (tm == 1) k1<TT, LPR, CH, LPR>();
       else if (tm == 2) k1<TT, LPR, CH, (LPR <= 8 ? 16 : 32)>();
@@ -870,8 +877,9 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   ua.mult = mult_p; ua.Scache = sc_p;
   ua.peer = peer ? 1 : 0; ua.pa = pa; ua.mult_stride = peer ? s_stride : 1;
   // fp32 models with 32-float rows on long rows: the stream forward kernel runs the exchange itself
-  const bool fused_exchange = peer && sizeof(T) == 4 && stream_forward_ok(m, d->nnz, d->n) && getenv("FMWR_NO_FUSED_EXCHANGE") == nullptr;
+  const bool fused_exchange = peer && sizeof(T) == 4 && stream_forward_ok(m, d->nnz, d->n, 2) && getenv("FMWR_NO_FUSED_EXCHANGE") == nullptr;
   if (fused_exchange) { ua.msum = reinterpret_cast<const double*>(pa.base[pa.rank] + pa.off_msum); ua.msum_n = ctx->world; }
+  else if (peer) ua.mult_compact = reinterpret_cast<const T*>(pa.base[pa.rank] + pa.off_mult);
   L.fused_exchange = fused_exchange;
   ua.w = (T*)m->w.p; ua.v = (T*)m->v.p; ua.scal = (double*)m->scal.p;
   for (int i = 0; i < 4; ++i) { ua.sw[i] = (T*)m->sw[i].p; ua.sv[i] = (T*)m->sv[i].p; }
@@ -982,6 +990,16 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
   if (sgd_l1) { const double h[2] = {u_w, u_v}; FMWR_CUDA(cudaMemcpyAsync((double*)m->scal.p + 1, h, 16, cudaMemcpyHostToDevice, ctx->stream)); }
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   if (peer) peer_check_error(ctx);
+  if (peer && getenv("FMWR_PEER_DEBUG")) {
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* dp = reinterpret_cast<uint32_t*>(pa.base[pa.rank]) + PEER_DEBUG;
+    FMWR_CUDA(cudaMemcpy(h, dp, sizeof h, cudaMemcpyDeviceToHost));
+    FMWR_CUDA(cudaMemset(dp, 0, sizeof h));
+    if (h[3]) fprintf(stderr, "[fmwr peer] rank %d: per CTA and launch: partial pass %.1f us, first barrier %.1f us, owner reduction %.1f us (%llu CTA-launches)\n",
+                      ctx->rank, h[0] / 1e3 / h[3], h[1] / 1e3 / h[3], h[2] / 1e3 / h[3], h[3]);
+    if (h[3] && h[6]) fprintf(stderr, "[fmwr peer] rank %d: start -> second arrival %.1f us (avg CTA), start -> flags out %.1f us (last CTA)\n", ctx->rank,
+                              h[4] / 1e3 / h[3], h[5] / 1e3 / h[6]);
+  }
   if (tr) { tr->n_rec = std::min(n_rec, (int)tr->max_rec); tr->convergent = convergent; tr->iters_done = (int)iter; }
 }
 

@@ -5,6 +5,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <exception>
 #include <map>
 #include <mutex>
 
@@ -70,6 +71,9 @@ void* dev_alloc(size_t bytes)
 void dev_free(void* p, size_t bytes)
 {
   if (!p) return;
+  // Normal paths synchronise their stream before a buffer goes out of scope.  While an exception unwinds, kernels that
+  // reference the block may still be queued: wait for the device before the block can be handed to another stream / context.
+  if (std::uncaught_exceptions() > 0) { cudaDeviceSynchronize(); cudaGetLastError(); }
   int dev = 0;
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) dev = attr.device; else { cudaGetLastError(); cudaGetDevice(&dev); }

@@ -264,7 +264,7 @@ inline int stream_grid(const fmwr_ctx* ctx, int64_t rows, int* rpg_out)
 inline bool stream_forward_ok(const fmwr_model* m, int64_t nnz, int64_t n, int min_nnz_per_row = 8)
 {
   const bool off = getenv("FMWR_NO_STREAM") != nullptr;     // read per call: tests flip it
-  return !off && m->prec == FMWR_F32 && m->kp == 32 && n > 0 && nnz >= (int64_t)min_nnz_per_row * n;
+  return !off && m->prec == FMWR_F32 && m->kp == 32 && n > 0 && n < (1ll << 31) && nnz >= (int64_t)min_nnz_per_row * n;
 }
 
 }  // namespace fmwr

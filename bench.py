@@ -541,7 +541,10 @@ def run_e2e(L, lib, ctx, data, mcfg, sc, n, p, k, args):
     for a in (row_size, col_i, val64, y64, w, v):
         if lib.fmwr_host_pin(L.ptr(a), C.c_int64(a.nbytes)) == 0:
             pinned.append(a)
-    h2d = row_size.nbytes + col_i.nbytes + val64.nbytes + y64.nbytes + w.nbytes + v.nbytes + 8
+    # the library narrows the f64 values to f32 on the host (several threads, pinned staging) before they cross PCIe: 4 B per value
+    host_narrow = os.environ.get("FMWR_HOST_NARROW", "1") != "0"
+    val_bytes = val64.nbytes // 2 if host_narrow else val64.nbytes
+    h2d = row_size.nbytes + col_i.nbytes + val_bytes + y64.nbytes + w.nbytes + v.nbytes + 8
     d2h = w.nbytes + v.nbytes + 8
     steps = max(1, min(args.steps, args.e2e_steps))
 
@@ -592,9 +595,12 @@ def run_e2e(L, lib, ctx, data, mcfg, sc, n, p, k, args):
     lib.fmwr_host_unpin(L.ptr(out))
     return {"value": round((n - 1) * steps / dt, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": round(dt / steps * 1e3, 2), "call": "fmwr_train (host fm.matrix lists -> host model)",
+            "host_bytes_per_step": int(row_size.nbytes + col_i.nbytes + val64.nbytes + y64.nbytes + w.nbytes + v.nbytes + 8),
+            "note": "h2d_bytes_per_step = bytes that cross PCIe: the 8-byte values are narrowed to f32 on the host by the library (threads + pinned staging ring) "
+                    "while earlier chunks upload; host_bytes_per_step = the caller's buffers" if host_narrow else "values uploaded as f64 and narrowed on the device",
             "parked_matrix": resident,
             "predict": {"value": round(n * steps / dtp, 1), "unit": "rows/s", "ms_per_step": round(dtp / steps * 1e3, 2),
-                        "h2d_bytes_per_step": int(row_size.nbytes + col_i.nbytes + val64.nbytes + w.nbytes + v.nbytes),
+                        "h2d_bytes_per_step": int(row_size.nbytes + col_i.nbytes + val_bytes + w.nbytes + v.nbytes),
                         "d2h_bytes_per_step": int(out.nbytes), "call": "fmwr_predict"}}
 
 

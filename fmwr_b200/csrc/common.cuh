@@ -8,6 +8,8 @@
 #include <vector>
 #include <stdexcept>
 #include <memory>
+#include <atomic>
+#include <thread>
 
 #include "../../include/fmwr_b200.h"
 
@@ -140,6 +142,7 @@ struct fmwr_ctx {
   fmwr::DBuf<double> red_scratch;  // reductions
   fmwr::HBuf<double> h_scalar;
   fmwr::HBuf<uint32_t> h_u32;      // pinned landing zone for small device -> host reads (pageable targets serialise with in-flight uploads)
+  fmwr::HBuf<float> h_stage[2];    // pinned staging ring of the host-side f64 -> f32 narrowing (data.cu: value uploader); allocated once
 };
 
 struct fmwr_data {
@@ -176,6 +179,13 @@ struct fmwr_data {
   fmwr::DBuf<double> val_stage[2];
   fmwr::DBuf<double> val64;            // deferred upload: the raw f64 values; narrowed into `val` range by range on the compute stream
   bool val_all_narrowed = true;
+  // host-side narrowing (default): a background thread converts the caller's f64 values chunk by chunk into the context's pinned
+  // staging ring and uploads them as f32 -- half the PCIe bytes of the value stream; up_issued = chunks whose copy and event have
+  // been queued (an event must be recorded before anybody waits on it)
+  std::thread up_thread;
+  std::atomic<int64_t> up_issued{0};
+  int64_t up_chunks = 0;
+  bool upload_in_flight() const { return up_chunks > 0 && up_issued.load(std::memory_order_acquire) <= up_chunks; }
   // per-batch CSC built while the values were still in flight: ent_val / seg_rec.w of batch b are filled right before
   // batch b trains, as soon as the value chunks covering its rows have arrived (train_minibatch.cu)
   bool mb_vals_pending = false;
@@ -184,6 +194,7 @@ struct fmwr_data {
   std::vector<int64_t> mb_batch_ent;   // [n_batches+1] entries before batch b (== offsets into the sorted entry arrays)
   ~fmwr_data()
   {
+    if (up_thread.joinable()) up_thread.join();
     if (val_ready) { cudaEventSynchronize(val_ready); cudaEventDestroy(val_ready); }
     for (cudaEvent_t e : val_ev) cudaEventDestroy(e);
   }

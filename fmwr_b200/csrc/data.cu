@@ -192,10 +192,72 @@ void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi)
   FMWR_CUDA(cudaGetLastError());
 }
 
+// host wait until the uploader has QUEUED chunk ci (its copy and its event): only then may a stream wait on the event
+void data_wait_chunk_issued(fmwr_data* d, int64_t ci)
+{
+  while (d->up_chunks > 0 && d->up_issued.load(std::memory_order_acquire) <= ci) std::this_thread::yield();
+}
+
 void data_wait_values(fmwr_data* d)
 {
+  if (d->up_thread.joinable()) d->up_thread.join();
   if (d->val_ready) FMWR_CUDA(cudaStreamWaitEvent(d->ctx->stream, d->val_ready, 0));
   if (!d->val_all_narrowed) { data_narrow_values(d, 0, d->nnz); d->val_all_narrowed = true; }
+}
+
+// f64 -> f32 on the HOST, several threads, into pinned staging; then the f32 chunk crosses PCIe (half the bytes of the value
+// stream: at configs[1] 1.56 GB instead of 3.12 GB of a 5.06 GB upload).  Runs in a background thread so the caller can go on
+// queueing work (the per-batch CSC build needs only the column ids); chunk c's event is recorded right after its copy.
+static void narrow_slice(const double* in, float* out, int64_t n)
+{
+  for (int64_t i = 0; i < n; ++i) out[i] = (float)in[i];
+}
+
+static void start_value_upload(fmwr_data* d, const double* value, int64_t chunk)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t nnz = d->nnz;
+  const int64_t n_chunks = ceil_div64(nnz, chunk);
+  ctx->h_stage[0].ensure((size_t)std::min(chunk, nnz));
+  ctx->h_stage[1].ensure((size_t)std::min(chunk, nnz));
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    cudaEvent_t ce = nullptr;
+    FMWR_CUDA(cudaEventCreateWithFlags(&ce, cudaEventDisableTiming));
+    d->val_ev.push_back(ce);
+  }
+  FMWR_CUDA(cudaEventCreateWithFlags(&d->val_ready, cudaEventDisableTiming));
+  d->val_chunk = chunk;
+  d->up_chunks = n_chunks;
+  d->up_issued.store(0, std::memory_order_release);
+  static const int n_workers = [] {
+    int t = getenv("FMWR_HOST_THREADS") ? atoi(getenv("FMWR_HOST_THREADS")) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(t, 32));
+  }();
+  const int dev = ctx->device;
+  cudaStream_t vs = ctx->copy_stream;
+  float* stage[2] = {ctx->h_stage[0].p, ctx->h_stage[1].p};
+  d->up_thread = std::thread([d, value, chunk, nnz, n_chunks, dev, vs, stage] {
+    cudaSetDevice(dev);
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      const int64_t off = c * chunk, m = std::min(chunk, nnz - off);
+      float* buf = stage[c & 1];
+      if (c >= 2) cudaEventSynchronize(d->val_ev[c - 2]);            // the copy that last read this staging buffer
+      const int T = (int)std::min<int64_t>(n_workers, std::max<int64_t>(1, m / 65536));
+      std::vector<std::thread> pool;
+      const int64_t per = (m + T - 1) / T;
+      for (int t = 1; t < T; ++t) {
+        const int64_t lo = t * per, hi = std::min(m, lo + per);
+        if (lo < hi) pool.emplace_back(narrow_slice, value + off + lo, buf + lo, hi - lo);
+      }
+      narrow_slice(value + off, buf, std::min(m, per));
+      for (auto& th : pool) th.join();
+      cudaMemcpyAsync(d->val.p + off, buf, sizeof(float) * m, cudaMemcpyHostToDevice, vs);
+      cudaEventRecord(d->val_ev[c], vs);
+      d->up_issued.store(c + 1, std::memory_order_release);
+    }
+    cudaEventRecord(d->val_ready, vs);
+    d->up_issued.store(n_chunks + 1, std::memory_order_release);
+  });
 }
 
 fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, const int32_t* row_size,
@@ -229,7 +291,13 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
       // rowptr and col) while the 8-byte values are still crossing PCIe, and waits for val_ready before it reads them.
       static const int64_t chunk_env = getenv("FMWR_VAL_CHUNK") ? atoll(getenv("FMWR_VAL_CHUNK")) : 0;
       const int64_t chunk = chunk_env > 0 ? chunk_env : (16ll << 20);
-      if (defer_values) {
+      static const bool host_narrow = !(getenv("FMWR_HOST_NARROW") && atoi(getenv("FMWR_HOST_NARROW")) == 0);
+      if (host_narrow) {
+        FMWR_CUDA(cudaEventRecord(ctx->ev_copy[0], ctx->stream));        // the column ids go first: the key sort needs all of them
+        FMWR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
+        start_value_upload(d, value, chunk);
+        if (!defer_values) { data_wait_values(d); FMWR_CUDA(cudaStreamSynchronize(ctx->stream)); }
+      } else if (defer_values) {
         // the copy stream carries nothing but copies (a narrowing kernel between two chunks would stall the upload whenever it
         // has to wait for SM slots behind the compute stream's sort): raw f64 into a full-size staging buffer, one event per chunk;
         // the compute stream narrows exactly the range a batch needs once that batch's chunk has arrived
@@ -270,7 +338,7 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
       }
     }
     if (labels) set_labels_f64(d, labels);
-    ctx->h2d_bytes += 4 * n + 12 * nnz + (labels ? 8 * n : 0);
+    ctx->h2d_bytes += 4 * n + 4 * nnz + (d->up_chunks > 0 ? 4 : 8) * nnz + (labels ? 8 * n : 0);    // values cross as f32 when narrowed on the host
     finish_create(d);
   } catch (...) { delete d; throw; }
   return d;
@@ -577,7 +645,8 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   DBuf<K> keys_in, keys_out;
   DBuf<uint32_t> erow, idx_out, head, segid;
   // values still uploading (one-shot training path): build the structure from rowptr / col alone and keep the permutation
-  const bool deferred = d->val_ready != nullptr && !d->val_ev.empty() && cudaEventQuery(d->val_ready) != cudaSuccess;
+  const bool deferred = d->val_ready != nullptr && !d->val_ev.empty() &&
+                        (d->up_chunks > 0 ? d->upload_in_flight() || cudaEventQuery(d->val_ready) != cudaSuccess : cudaEventQuery(d->val_ready) != cudaSuccess);
   keys_in.alloc(m); keys_out.alloc(m); erow.alloc(m); head.alloc(m); segid.alloc(m);
   if (deferred) d->mb_perm.alloc(m); else idx_out.alloc(m);
   uint32_t* perm_p = deferred ? d->mb_perm.p : idx_out.p;

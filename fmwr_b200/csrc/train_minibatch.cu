@@ -29,6 +29,7 @@ int tracker_step_size(int step_size, int max_iter);
 void minibatch_fill_values(fmwr_data* d, uint32_t seg_lo, uint32_t seg_hi);
 void data_wait_values(fmwr_data* d);
 void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi);
+void data_wait_chunk_issued(fmwr_data* d, int64_t ci);
 void comm_allreduce_sum(fmwr_ctx* ctx, void* buf, size_t count, bool f64);
 
 // ---- K1: forward + multiplier + S cache --------------------------------------------------------
@@ -939,6 +940,7 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
         const int64_t last_entry = (int64_t)d->mb_e0 + d->mb_batch_ent[b + 1] - 1;
         if (last_entry >= 0 && d->val_chunk > 0) {
           const size_t ci = std::min<size_t>(d->val_ev.size() - 1, (size_t)(last_entry / d->val_chunk));
+          data_wait_chunk_issued(d, (int64_t)ci);          // host-narrowed upload: the event exists once the uploader queued the chunk
           FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->val_ev[ci], 0));
         }
         data_narrow_values(d, b == 0 ? 0 : (int64_t)d->mb_e0 + d->mb_batch_ent[b], (int64_t)d->mb_e0 + d->mb_batch_ent[b + 1]);

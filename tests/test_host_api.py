@@ -213,7 +213,7 @@ def test_fm_matrix_is_uploaded_once_across_train_predict_update_track():
         A.options(**{"FM.cache": True})
         d1 = A.fm_matrix(X, y01)
         ctx = A._ctx()
-        x_bytes = 12 * d1["features"]["size"] + 4 * n                 # value f64 + col i32 per entry, row_size i32 per row
+        x_bytes = 8 * d1["features"]["size"] + 4 * n                  # per entry col i32 + the value as f32 (narrowed on the host before the copy), row_size i32 per row
         model_bytes = 8 * (1 + p + p * k)
         h0 = ctx.transfer_bytes()[0]
         f1 = A.fm_train(d1, normalize=True, control=ctl())

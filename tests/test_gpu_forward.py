@@ -41,7 +41,7 @@ def test_forward_kat(gpu_ctx, port):
     assert abs(got[0] - 0.5398278371) < 1e-9 and abs(got[5] - 0.6255158326) < 1e-9
 
 
-@pytest.mark.parametrize("k", [0, 1, 2, 3, 8, 10, 32, 33, 64, 100, 128, 200])
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 8, 10, 29, 30, 32, 33, 64, 100, 128, 200])
 @pytest.mark.parametrize("prec", [L.F32, L.F64])
 def test_forward_random_ragged(gpu_ctx, port, k, prec):
     if prec == L.F64 and k > 128 * 2:

@@ -233,7 +233,7 @@ def test_minibatch_ragged_rows_with_empty_rows_and_wide_rows(gpu_ctx, solver):
 
 @pytest.mark.parametrize("solver,regs", [(O.FTRL, dict(l1_w=1e-3, l2_w=1e-3, l2_v=1e-3)), (O.SGD, dict(l2_w=1e-3, l2_v=1e-3)),
                                           (O.SGD, dict(l1_w=1e-3, l1_v=1e-3)), (O.TDAP, dict(l1_w=1e-3, l2_v=1e-3))])
-@pytest.mark.parametrize("k", [32, 8, 3])
+@pytest.mark.parametrize("k", [32, 30, 8, 3])
 def test_dense_update_kernel_equals_gather_kernel(gpu_ctx, solver, regs, k, monkeypatch):
     """mb_update_tma_kernel (parameter ranges staged by bulk copies, csrc/update_tma.cuh) against mb_update_kernel (per-segment
     gathers) on the same batches: same per-segment arithmetic and entry order, so the models agree to rounding of the

@@ -503,6 +503,31 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_kernel(ExactArgs<T> a)
   if (tid < 8) a.scal[tid] = sc[a.t_end & 1][tid];
 }
 
+}  // namespace fmwr
+#include "train_exact_pipe.cuh"
+namespace fmwr {
+
+template <class T, int SOLVER>
+struct ExactPipeLaunch {
+  fmwr_ctx* ctx; ExactArgs<T> args; double avg_nnz; bool launched; bool force;
+  template <class TT, int LPR, int CH>
+  void run()
+  {
+    constexpr int NS = SOLVER == FMWR_SGD ? 1 : (SOLVER == FMWR_FTRL ? 2 : 4);
+    const bool has_state = (SOLVER != FMWR_SGD) || args.sp.l1;
+    const XpPlan pl = xp_plan<TT>(LPR * CH, 32 / LPR, has_state, NS, avg_nnz);
+    launched = false;
+    if (pl.ecap < 32 / LPR) return;          // a factor row too wide to stage even one round: the CTA-wide kernel takes it
+    // fp64 FTRL / TDAP are bound by the IEEE sqrt / divide sequences of the 1248 coordinate steps of a sample, not by latency: one
+    // warp per sample loses to the CTA-wide kernel's 14 warps per sample there (7.8 vs 4.5 us per sample measured)
+    if (sizeof(TT) == 8 && SOLVER != FMWR_SGD && !force) return;
+    FMWR_CUDA(cudaFuncSetAttribute(exact_pipe_kernel<TT, LPR, CH, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+    FMWR_LAUNCH(ctx, (exact_pipe_kernel<TT, LPR, CH, SOLVER>), 1, (pl.teams + 3) * 32, pl.total, args, pl.teams, pl.ecap, pl.na,
+                (uint32_t)pl.off_stage, (uint32_t)pl.stage_bytes_per_team);
+    launched = true;
+  }
+};
+
 template <class T, int SOLVER>
 struct ExactLaunch {
   fmwr_ctx* ctx; ExactArgs<T> args;
@@ -613,6 +638,11 @@ static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr
   a.sp = make_params<T>(m, s);
   a.lo = s->min_target; a.hi = s->max_target;
   { const char* pf = std::getenv("FMWR_EXACT_PREFETCH"); a.prefetch = (pf && pf[0] == '0') ? 0 : 1; }
+  { const char* nh = std::getenv("FMWR_EXACT_NOHAZARD"); if (nh && nh[0] == '1') a.prefetch |= 2; }     // tests only: run the pipeline WITHOUT waiting for column hazards
+  bool pipelined = true;
+  bool force_pipe = false;
+  { const char* pp = std::getenv("FMWR_EXACT_PIPE"); if (pp && pp[0] == '0') pipelined = false; if (pp && pp[0] == '2') force_pipe = true; }
+  const double avg_nnz = d->n > 0 ? (double)d->nnz / (double)d->n : 0.0;
 
   // visit order.  random_step == 1: the reference scans i = 1 .. n-1 (F5).  random_step > 1: strides of
   // 1 + floor(U * random_step) from glibc rand() (reference src/util/Random.h:126-132); the caller may pass
@@ -643,7 +673,15 @@ static void train_exact_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const fmwr
       next = std::min<int64_t>(cand, max_iter);
     }
     a.t_begin = iter; a.t_end = next;
-    if (s->solver == FMWR_SGD) { ExactLaunch<T, FMWR_SGD> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
+    bool launched = false;
+    if (pipelined) {
+      // several samples in flight, serial semantics kept by column-hazard tracking (train_exact_pipe.cuh)
+      if (s->solver == FMWR_SGD) { ExactPipeLaunch<T, FMWR_SGD> L{ctx, a, avg_nnz, false, force_pipe}; dispatch_layout<T>(m->kp, L); launched = L.launched; }
+      else if (s->solver == FMWR_FTRL) { ExactPipeLaunch<T, FMWR_FTRL> L{ctx, a, avg_nnz, false, force_pipe}; dispatch_layout<T>(m->kp, L); launched = L.launched; }
+      else { ExactPipeLaunch<T, FMWR_TDAP> L{ctx, a, avg_nnz, false, force_pipe}; dispatch_layout<T>(m->kp, L); launched = L.launched; }
+    }
+    if (launched) {}
+    else if (s->solver == FMWR_SGD) { ExactLaunch<T, FMWR_SGD> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
     else if (s->solver == FMWR_FTRL) { ExactLaunch<T, FMWR_FTRL> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
     else { ExactLaunch<T, FMWR_TDAP> L{ctx, a}; dispatch_layout<T>(m->kp, L); }
     iter = next;

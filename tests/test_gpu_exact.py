@@ -224,3 +224,85 @@ def test_configs0_in_full_against_the_reference(gpu_ctx, ref):
         (gw0, gw, gv), tr = gpu_train(gpu_ctx, prec, ds, y, L.REGRESSION, L.SGD, k, w0, w, v, iters, regs)
         assert tr["iters_done"] == iters
         assert relerr(gw0, rw0) < tol and relerr(gw, rw) < tol and relerr(gv, rv) < tol
+
+
+# ---- the pipelined kernel (train_exact_pipe.cuh): several samples in flight, serial semantics through column-hazard tracking.
+# FMWR_EXACT_PIPE: 0 = CTA-wide kernel only, 2 = pipelined wherever it can run, unset = the engine's choice per solver / precision.
+HAZARD_SHAPES = [
+    # (n, p, max nnz, k): what the shape stresses
+    (3000, 40, 12, 8),        # every sample shares columns with its neighbours: the pipeline degrades to the serial order
+    (6000, 2500, 30, 32),     # dependencies at every distance inside the ring, many table sets holding two live columns
+    (1500, 6000, 150, 32),    # rows longer than the ring and the stage: chunked path, columns hashed from global memory
+    (4000, 300, 45, 4),       # 16 entries per round (k = 4): many lanes of a warp in the same table set
+]
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL, O.TDAP])
+@pytest.mark.parametrize("shape", HAZARD_SHAPES)
+def test_pipelined_exact_kernel_keeps_the_serial_order(gpu_ctx, port, monkeypatch, solver, shape):
+    """fp64, so a single stale read (a hazard the tracker missed) shows at 1e-3 while the two kernels' different summation
+    orders stay below 1e-9; then the oracle itself on the smaller shapes."""
+    n, p, max_nnz, k = shape
+    rng = np.random.default_rng(n + k)
+    rowptr, col, val = synth.random_csr(n, p, max_nnz, seed=n, empty_rows=True)
+    ds = dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k)); w0 = 0.1
+    regs = dict(l1_w=0.001, l2_w=0.001, l2_v=0.001)
+    iters = 2 * (n - 1) + 7
+    out = {}
+    for pipe in ("0", "2"):
+        monkeypatch.setenv("FMWR_EXACT_PIPE", pipe)
+        out[pipe], _ = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, SOLV[solver], k, w0, w, v, iters, regs=regs)
+    tol = 1e-9 if solver != O.TDAP else 1e-6        # TDAP amplifies rounding (DESIGN.md section 4)
+    assert abs(out["0"][0] - out["2"][0]) < tol * max(1.0, abs(out["0"][0]))
+    assert relerr(out["2"][1], out["0"][1]) < tol and relerr(out["2"][2], out["0"][2]) < tol
+    if n * max_nnz <= 200_000:
+        cfg = O.make_cfg(task=O.CLASSIFICATION, solver=solver, k=k, max_iter=iters, min_target=-1.0, max_target=1.0, **regs)
+        rw0, rw, rv = port.train(cfg, n, p, rowptr, col, val, y, w0, w, v)[:3]
+        assert abs(out["2"][0] - rw0) < 1e-8 * max(1.0, abs(rw0)) if solver != O.TDAP else True
+        assert relerr(out["2"][1], rw) < (1e-8 if solver != O.TDAP else 1e-5)
+        assert relerr(out["2"][2], rv) < (1e-8 if solver != O.TDAP else 1e-5)
+
+
+@pytest.mark.parametrize("solver", [O.SGD, O.FTRL])
+def test_pipelined_exact_kernel_fp32_and_visit_orders(gpu_ctx, monkeypatch, solver):
+    """fp32 instantiation, an explicit visit order with repeats (the same row twice in a row is the sharpest hazard), the
+    tracker's launch segmentation (step_size) and a launch shorter than the pipeline's depth."""
+    n, p, k = 2000, 900, 32
+    rng = np.random.default_rng(5)
+    rowptr, col, val = synth.random_csr(n, p, 40, seed=11, empty_rows=True)
+    ds = dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k)); w0 = 0.0
+    visit = rng.integers(0, n, 5000).astype(np.uint32)
+    visit[100:140] = 7                                  # forty visits of one row
+    visit[200:260:2] = 9                                # every other visit
+    for kw in (dict(visit=visit, max_iter=5000), dict(max_iter=3), dict(max_iter=2 * n, step_size=37)):
+        out = {}
+        for pipe in ("0", "2"):
+            monkeypatch.setenv("FMWR_EXACT_PIPE", pipe)
+            mi = kw["max_iter"]
+            out[pipe], tr = gpu_train(gpu_ctx, L.F32, ds, y, L.CLASSIFICATION, SOLV[solver], k, w0, w, v, mi, regs=dict(l2_w=0.001, l2_v=0.001),
+                                      visit=kw.get("visit"), step_size=kw.get("step_size", -1))
+        assert abs(out["0"][0] - out["2"][0]) < 2e-5
+        assert relerr(out["2"][1], out["0"][1]) < 2e-5 and relerr(out["2"][2], out["0"][2]) < 2e-5
+
+
+def test_hazard_tracking_is_what_keeps_the_order(gpu_ctx, monkeypatch):
+    """The same pipeline with the dependency waits switched off (FMWR_EXACT_NOHAZARD=1, a test-only switch) must NOT reproduce
+    the serial result on data whose neighbouring samples share columns: the stress tests above are sensitive to a missed hazard."""
+    n, p, max_nnz, k = HAZARD_SHAPES[0]
+    rng = np.random.default_rng(2)
+    rowptr, col, val = synth.random_csr(n, p, max_nnz, seed=n)
+    ds = dict(n=n, p=p, rowptr=rowptr, col=col, val=val)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    w = rng.normal(0, 0.1, p); v = rng.normal(0, 0.1, (p, k)); w0 = 0.1
+    out = {}
+    for name, env in (("serial", {"FMWR_EXACT_PIPE": "0"}), ("tracked", {"FMWR_EXACT_PIPE": "2"}), ("untracked", {"FMWR_EXACT_PIPE": "2", "FMWR_EXACT_NOHAZARD": "1"})):
+        monkeypatch.delenv("FMWR_EXACT_NOHAZARD", raising=False)
+        for kk, vv in env.items():
+            monkeypatch.setenv(kk, vv)
+        out[name], _ = gpu_train(gpu_ctx, L.F64, ds, y, L.CLASSIFICATION, L.SGD, k, w0, w, v, 2 * (n - 1), regs=dict(l2_w=0.001, l2_v=0.001), learn_rate=0.05)
+    assert relerr(out["tracked"][2], out["serial"][2]) < 1e-9
+    assert relerr(out["untracked"][2], out["serial"][2]) > 1e-6

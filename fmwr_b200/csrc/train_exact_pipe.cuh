@@ -33,10 +33,11 @@ constexpr int XP_R = 32;                   // ring slots (samples staged ahead b
 constexpr int XP_RN = 64;                  // ring entries per sample; longer rows read the rest from global memory
 constexpr int XP_G = 8;                    // samples per pipeline batch
 #ifndef XP_NAP
-#define XP_NAP 20        // ns between polls of a ring / done tag
+#define XP_NAP 0         // ns between polls of a ring / done tag.  0: plain spinning -- __nanosleep(20) wakes late enough to cost
+                         // 50 % on SGD and configs[0] (1.90 vs 1.28, 1.16 vs 0.73 us per sample); the pollers are single instructions
 #endif
 #ifndef XP_NAP_TOK
-#define XP_NAP_TOK 20    // ... of the scalar chain's token (latency-critical)
+#define XP_NAP_TOK 0     // ... of the scalar chain's token (latency-critical)
 #endif
 #ifndef XP_UNROLL_G
 #define XP_UNROLL_G 4
@@ -85,6 +86,7 @@ __device__ __forceinline__ uint32_t xp_lookup(const uint4 s, uint32_t c, uint32_
   else if (s.y == c) dh = xp_clip(xp_dist(q16, s.z >> 16));
   return dh | (xp_clip(xp_dist(q16, s.w & 0xffffu)) << 8);
 }
+#ifdef XP_OLD_INSERT
 __device__ __forceinline__ uint4 xp_insert(uint4 s, uint32_t c, uint32_t q16)
 {
   if (s.x == c) { s.z = (s.z & 0xffff0000u) | q16; return s; }
@@ -102,6 +104,17 @@ __device__ __forceinline__ bool xp_present(const uint4 s, uint32_t c, uint32_t q
 {
   return (s.x == c && (s.z & 0xffffu) == q16) || (s.y == c && (s.z >> 16) == q16);
 }
+#else
+// way 0 is the most recently entered column: a new column pushes way 0 to way 1 and what was there out of the set
+__device__ __forceinline__ uint4 xp_insert(uint4 s, uint32_t c, uint32_t q16)
+{
+  if (s.x == c) { s.z = (s.z & 0xffff0000u) | q16; return s; }
+  if (s.y != c) { const uint32_t old = s.z >> 16; if (xp_dist(q16, old) < xp_dist(q16, s.w & 0xffffu)) s.w = old; }     // the closest evicted sample is the one remembered
+  s.y = s.x; s.x = c; s.z = (s.z << 16) | q16;
+  return s;
+}
+__device__ __forceinline__ bool xp_present(const uint4 s, uint32_t c, uint32_t q16) { return s.x == c && (s.z & 0xffffu) == q16; }
+#endif
 
 // shared-memory plan (dynamic): fixed part, then the per-warp stages
 struct XpPlan {
@@ -111,7 +124,7 @@ struct XpPlan {
 
 struct XpFixed {
   uint32_t fetched[XP_R], loaded[XP_R], done[XP_R];       // tags: relative sample index + 1 (ring filled / hazards known / written back)
-  uint32_t mN[XP_R], mB[XP_R], mAll[XP_R];
+  uint32_t mN[XP_R], mB[XP_R], mAll[XP_R], mDep[XP_R];      // row length, first entry, flags, "some entry has a dependency in flight"
   float mY[XP_R];
   uint32_t rCol[XP_R][XP_RN];
   float rVal[XP_R][XP_RN];
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
           const uint32_t q = (it - 2) * XP_G + lane;
           if (q < total) {
             const int slot = q & (XP_R - 1);
-            if (q >= XP_R) { while (xp_ld(&F.done[slot]) < q - XP_R + 1u) { __nanosleep(XP_NAP); } }      // the slot's previous sample has finished
+            if (q >= XP_R) { while (xp_ld(&F.done[slot]) < q - XP_R + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }      // the slot's previous sample has finished
             const uint32_t nnz = eB - bB;
             F.mN[slot] = nnz; F.mB[slot] = bB; F.mY[slot] = yB; F.mAll[slot] = nnz > (uint32_t)ecap ? 1u : 0u;
           }
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       long long p0 = clock64();
 #endif
       const int slot = q & (XP_R - 1);
-      while (xp_ld(&F.fetched[slot]) != q + 1u) { __nanosleep(XP_NAP); }
+      while (xp_ld(&F.fetched[slot]) != q + 1u) { if (XP_NAP) __nanosleep(XP_NAP); }
       xp_order();
       PPROF(0)
       const uint32_t nnz = F.mN[slot], b = F.mB[slot];
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       for (uint32_t j = XP_RN + lane; j < nnz; j += 32) { const uint32_t c = a.col[b + j], h = xp_hash(c); F.hSet[h] = xp_insert(F.hSet[h], c, q16); }
       if (in0) F.rDep[slot][lane] = (uint16_t)dep0;
       if (in1) F.rDep[slot][lane + 32] = (uint16_t)dep1;
+      { const bool anyd = __any_sync(0xffffffffu, (dep0 | dep1) != 0u); if (lane == 0) F.mDep[slot] = anyd ? 1u : 0u; }
       if (f6) {
         max_nnz = max(max_nnz, nnz);
         bool write_low = (in0 && c0 < max_nnz) || (in1 && c1 < max_nnz);
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
         const int slot = q & (XP_R - 1);
         // a hint for a sample the workers already passed is useless: skip ahead instead of falling behind
         if (xp_ld(&F.done[slot]) >= q + 1u || xp_ld(&F.loaded[slot]) > q + 1u) continue;
-        while (xp_ld(&F.fetched[slot]) < q + 1u) { __nanosleep(XP_NAP); }
+        while (xp_ld(&F.fetched[slot]) < q + 1u) { if (XP_NAP) __nanosleep(XP_NAP); }
         __syncwarp();
         xp_order();
         if (xp_ld(&F.fetched[slot]) != q + 1u) continue;         // the slot moved on
@@ -367,7 +381,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       long long p0 = clock64();
 #endif
       const int slot = q & (XP_R - 1);
-      while (xp_ld(&F.loaded[slot]) != q + 1u) { __nanosleep(XP_NAP); }
+      while (xp_ld(&F.loaded[slot]) != q + 1u) { if (XP_NAP) __nanosleep(XP_NAP); }
       XPROF(0)
       __syncwarp();
       xp_order();
@@ -381,7 +395,11 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       auto open_dep = [&](uint32_t dist) -> bool { if (dist == 0u || dist > q) return false; const uint32_t d = q - dist; return xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u; };
       bool has_dep = false;
       if (wait_all) { if (lane >= 1 && lane < teams) has_dep = open_dep((uint32_t)lane); }
+#ifdef XP_NO_MDEP
       else {
+#else
+      else if (F.mDep[slot]) {
+#endif
         for (uint32_t j = lane; j < nnz; j += 32) {
           const uint32_t dd = F.rDep[slot][j];
           if (dd & 0x8000u) { for (uint32_t k2 = 1; k2 <= (dd & 0xffu); ++k2) has_dep |= open_dep(k2); }
@@ -399,17 +417,17 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       }
       if (!has_dep) {
       } else if (wait_all) {
-        if (lane >= 1 && lane < teams && q >= (uint32_t)lane) { const uint32_t d = q - lane; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { __nanosleep(XP_NAP); } }
+        if (lane >= 1 && lane < teams && q >= (uint32_t)lane) { const uint32_t d = q - lane; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
       } else {
         for (uint32_t j = lane; j < nnz; j += 32) {
           const uint32_t dd = F.rDep[slot][j];
           if (dd & 0x8000u) {
             // (F6) every sample since the farthest dependency
-            for (uint32_t k2 = 1; k2 <= (dd & 0xffu) && k2 <= q; ++k2) { const uint32_t d = q - k2; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { __nanosleep(XP_NAP); } }
+            for (uint32_t k2 = 1; k2 <= (dd & 0xffu) && k2 <= q; ++k2) { const uint32_t d = q - k2; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
           } else {
             const uint32_t d0 = dd & 0xffu, d1 = dd >> 8;
-            if (d0 && d0 <= q) { const uint32_t d = q - d0; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { __nanosleep(XP_NAP); } }
-            if (d1 && d1 <= q) { const uint32_t d = q - d1; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { __nanosleep(XP_NAP); } }
+            if (d0 && d0 <= q) { const uint32_t d = q - d0; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
+            if (d1 && d1 <= q) { const uint32_t d = q - d1; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
           }
         }
       }

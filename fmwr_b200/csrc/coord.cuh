@@ -35,9 +35,10 @@ __device__ __forceinline__ double fm_grad(double S, double v, double x) { return
 template <class T>
 __device__ __forceinline__ void sgd_apply_penalty(T& theta, T u, T& q)
 {
+  // both clips computed, one selected: the same values as the reference's if / else-if, without a divergent branch per element
   const T old = theta;
-  if (theta > T(0)) theta = fmax(T(0), old - (u + q));
-  else if (theta < T(0)) theta = fmin(T(0), old + (u - q));
+  const T pos = fmax(T(0), old - (u + q)), neg = fmin(T(0), old + (u - q));
+  theta = old > T(0) ? pos : (old < T(0) ? neg : old);
   q += theta - old;
 }
 

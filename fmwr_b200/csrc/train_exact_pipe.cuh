@@ -28,10 +28,19 @@
 
 namespace fmwr {
 
+#ifndef XP_RING
+#define XP_RING 64       // ring slots: 32 left the fetch warp waiting for free slots (8 samples being fetched, 8 in the hazard warp, 8 in work, 8 written back but unpublished)
+#endif
+#ifndef XP_RINGN
+#define XP_RINGN 48      // ring entries per sample
+#endif
 constexpr int XP_MAXT = 8;                 // worker warps = samples in flight
-constexpr int XP_R = 32;                   // ring slots (samples staged ahead by the pipeline warp)
-constexpr int XP_RN = 64;                  // ring entries per sample; longer rows read the rest from global memory
-constexpr int XP_G = 8;                    // samples per pipeline batch
+constexpr int XP_R = XP_RING;                   // ring slots (samples staged ahead by the pipeline warp)
+constexpr int XP_RN = XP_RINGN;                  // ring entries per sample; longer rows read the rest from global memory
+#ifndef XP_BATCH
+#define XP_BATCH 8
+#endif
+constexpr int XP_G = XP_BATCH;                    // samples per pipeline batch
 #ifndef XP_NAP
 #define XP_NAP 0         // ns between polls of a ring / done tag.  0: plain spinning -- __nanosleep(20) wakes late enough to cost
                          // 50 % on SGD and configs[0] (1.90 vs 1.28, 1.16 vs 0.73 us per sample); the pollers are single instructions

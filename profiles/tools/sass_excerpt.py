@@ -16,9 +16,10 @@ WANT = [("mb_update_tma_kernelIfLi8ELi1ELi500ELb0ELi32ELi3ELi3E", "mb_update_tma
         ("forward_kernelIfLi8ELi1ELi16E", "forward_kernel<float,8,1,16> -- team forward (short rows, other k)"),
         ("radix_pass_kernelIjjLb1E", "radix_pass_kernel<u32,u32,iota> -- the sorter's one-sweep pass"),
         ("fused_kernelIfLi4ELb1E", "fused_kernel<float,4,ones> -- ALS/MCMC fused coordinate pass"),
-        ("exact_kernelIfLi8ELi1ELi500E", "exact_kernel<float,8,1,FTRL> -- batch = 1, reference order")]
+        ("exact_pipe_kernelIfLi8ELi1ELi500E", "exact_pipe_kernel<float,8,1,FTRL> -- batch = 1, reference order, samples pipelined behind the hazard tracker"),
+        ("exact_kernelIfLi8ELi1ELi600E", "exact_kernel<float,8,1,TDAP> -- batch = 1, reference order, CTA-wide")]
 KEYS = ["UBLKCP", "UTMA", "SYNCS", "FENCE.VIEW.ASYNC", "LDGSTS", "LDGDEPBAR", "LDG.E.128", "LDG.E.CONSTANT", "LDG.E ", "STG.E.128", "STG.E ", "LDS", "STS", "RED.E", "REDG", "ATOMG", "ATOMS",
-        "SHFL", "MATCH", "MUFU", "FFMA", "DFMA", "BAR.SYNC", "STL", "LDL", "CCTL", "MEMBAR", "ST.E.STRONG.SYS", "LD.E.STRONG.SYS", "NANOSLEEP"]
+        "SHFL", "MATCH", "MUFU", "FFMA", "DFMA", "BAR.SYNC", "STL", "LDL", "CCTL", "MEMBAR", "LDS.128", "STS.128", "VOTE", "WARPSYNC", "ST.E.STRONG.SYS", "LD.E.STRONG.SYS", "NANOSLEEP"]
 
 
 def main():

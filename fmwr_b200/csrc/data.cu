@@ -603,6 +603,16 @@ __global__ void mb_batch_bounds(const K* __restrict__ keys, const uint32_t* __re
   (void)n_batches; (void)n_seg;
 }
 
+// batch_seg[b] = segment of the first sorted entry of batch b (n_seg past the end; an empty batch shares the next one's)
+__global__ void mb_batch_first_seg(const uint32_t* __restrict__ batch_ent, uint32_t e0, const uint32_t* __restrict__ segid, uint32_t m, uint32_t n_seg,
+                                   int64_t count, uint32_t* __restrict__ batch_seg)
+{
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= count) return;
+  const uint32_t i = batch_ent[b] - e0;
+  batch_seg[b] = i < m ? segid[i] : n_seg;
+}
+
 // Entries of rows [row0, n) regrouped by (batch, feature, row): the "sorted-key segmented
 // reduction" layout of the minibatch update kernels (one segment = one touched coordinate).
 template <class K>
@@ -621,10 +631,10 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, d->rowptr.p + row0, d->rowptr.p + d->n, hp);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   const uint32_t e0 = hp[0], e1 = hp[1];
+  DBuf<uint32_t> bp;
   {
     // entries before each batch (rows of a batch are consecutive, so this is also the batch's offset in the sorted arrays);
     // used by the deferred-value path of the one-shot trainer
-    DBuf<uint32_t> bp;
     bp.alloc(n_batches + 1);
     FMWR_LAUNCH(ctx, batch_row_ptr, ceil_div(n_batches + 1, 256), 256, 0, d->rowptr.p, row0, batch, d->n, n_batches + 1, bp.p);
     FMWR_LAUNCH(ctx, peek_u32, ceil_div(n_batches + 1, 256), 256, 0, bp.p, n_batches + 1, hp + 8);
@@ -668,9 +678,9 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   bseg.alloc(n_batches + 1);
   // default every batch offset to n_seg (covers trailing empty batches), then fill real starts.  (A kernel, not a host ->
   // device copy: a copy would queue behind every value chunk still waiting for the H2D engine.)
-  FMWR_LAUNCH(ctx, fill_u32, ceil_div(n_batches + 1, 256), 256, 0, bseg.p, n_batches + 1, n_seg);
-  FMWR_LAUNCH(ctx, mb_batch_bounds<K>, ceil_div(m, 256), 256, 0, keys_out.p, head.p, segid.p, m, colbits, n_batches, n_seg,
-              bseg.p);
+  // a batch's entries are as many in sorted order as in row order and come in batch order: its first segment is the one that holds
+  // its first entry (a walk over all m keys took 1.5 ms for the 153 answers)
+  FMWR_LAUNCH(ctx, mb_batch_first_seg, ceil_div(n_batches + 1, 256), 256, 0, bp.p, e0, segid.p, (uint32_t)m, n_seg, n_batches + 1, bseg.p);
   FMWR_LAUNCH(ctx, peek_u32, ceil_div(n_batches + 1, 256), 256, 0, bseg.p, n_batches + 1, hp);
   FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<uint32_t> hb(hp, hp + n_batches + 1);

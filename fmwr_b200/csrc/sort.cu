@@ -26,6 +26,9 @@ constexpr int RS_BINS = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MAX_PASSES = 8;
+#ifndef RS_NAP
+#define RS_NAP 20
+#endif
 
 template <class K> struct RsTile { enum { ITEMS = sizeof(K) == 4 ? 16 : 12, SIZE = RS_THREADS * ITEMS }; };
 
@@ -37,19 +40,43 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const K* __restrict__ k
   for (int i = threadIdx.x; i < passes * RS_BINS; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  // warp-uniform trip count (match_any needs the whole warp): iterate over warp-sized chunks
+  // Every lane takes HU consecutive keys per trip (one 16-byte load for 32-bit keys).  A digit that is the same across the warp's
+  // lanes (the high digits of sorted-ish keys: the batch number of consecutive rows) is counted by one lane; anything else goes
+  // to the shared-memory bins lane by lane -- low digits are near-random, 32 lanes into 256 bins rarely collide.
+  constexpr int HU = 16 / (int)sizeof(K);
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = warp_global * 32; base < n; base += n_warps * 32) {
-    const int64_t i = base + lane;
-    const bool ok = i < n;
-    const K key = ok ? keys[i] : K(0);
+  for (int64_t base = warp_global * 32 * HU; base < n; base += n_warps * 32 * HU) {
+    const int64_t i0 = base + (int64_t)lane * HU;
+    K key[HU];
+    bool ok[HU];
+    if (i0 + HU <= n && (reinterpret_cast<uintptr_t>(keys + i0) & 15) == 0) {
+      const uint4 q4 = *reinterpret_cast<const uint4*>(keys + i0);
+      if (sizeof(K) == 4) { key[0] = (K)q4.x; key[1 % HU] = (K)q4.y; key[2 % HU] = (K)q4.z; key[3 % HU] = (K)q4.w; }
+      else { key[0] = (K)(((uint64_t)q4.y << 32) | q4.x); key[1 % HU] = (K)(((uint64_t)q4.w << 32) | q4.z); }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) ok[u] = true;
+    } else {
+#pragma unroll
+      for (int u = 0; u < HU; ++u) { ok[u] = i0 + u < n; key[u] = ok[u] ? keys[i0 + u] : K(0); }
+    }
     for (int ps = 0; ps < passes; ++ps) {
       const int shift = ps * RS_BITS;
       const int nb = min(RS_BITS, bits - shift);
-      const uint32_t d = ok ? (uint32_t)((key >> shift) & (K)((1u << nb) - 1u)) : (uint32_t)RS_BINS;   // invalid lanes group apart
-      const unsigned m = __match_any_sync(0xffffffffu, d);
-      if (ok && lane == __ffs(m) - 1) atomicAdd(&sh[ps * RS_BINS + d], (uint32_t)__popc(m));
+      const K dm = (K)((1u << nb) - 1u);
+      uint32_t d[HU];
+#pragma unroll
+      for (int u = 0; u < HU; ++u) d[u] = ok[u] ? (uint32_t)((key[u] >> shift) & dm) : (uint32_t)RS_BINS;
+      bool same = true;
+#pragma unroll
+      for (int u = 1; u < HU; ++u) same &= d[u] == d[0];
+      const uint32_t d00 = __shfl_sync(0xffffffffu, d[0], 0);
+      if (__all_sync(0xffffffffu, same && d[0] == d00)) {
+        if (lane == 0 && d00 < (uint32_t)RS_BINS) atomicAdd(&sh[ps * RS_BINS + d00], 32u * HU);
+      } else {
+#pragma unroll
+        for (int u = 0; u < HU; ++u) if (ok[u]) atomicAdd(&sh[ps * RS_BINS + d[u]], 1u);
+      }
     }
   }
   __syncthreads();
@@ -180,7 +207,7 @@ radix_pass_kernel(const K* __restrict__ kin, K* __restrict__ kout, const uint32_
       W acc = 0;
       for (;;) {
         W s = vstate[(size_t)look * RS_BINS + tid];
-        while ((s & ~Lb<W>::MASK) == 0) { __nanosleep(20); s = vstate[(size_t)look * RS_BINS + tid]; }
+        while ((s & ~Lb<W>::MASK) == 0) { if (RS_NAP) __nanosleep(RS_NAP); s = vstate[(size_t)look * RS_BINS + tid]; }
         acc += s & Lb<W>::MASK;
         if (s & Lb<W>::INCL) break;
         --look;

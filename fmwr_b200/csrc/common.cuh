@@ -175,6 +175,14 @@ struct fmwr_data {
   // sorts the (batch, feature) keys; val_ready marks its end (data.cu: data_wait_values)
   cudaEvent_t val_ready = nullptr;
   std::vector<cudaEvent_t> val_ev;     // one per uploaded chunk of val_chunk entries (deferred upload only)
+  std::vector<char> val_dev;           // chunk c crossed PCIe as raw f64 into val64 and is narrowed on the device (mixed upload, data.cu)
+  int64_t val_waited = 0;              // chunks whose events the compute stream already waits for (train_minibatch.cu)
+  // one-shot training path: the column ids cross PCIe in chunks on the copy stream too (col_ev[c] = chunk c of col_chunk entries
+  // has arrived), so the per-batch CSC of the first row groups is built while the later ones are still uploading
+  // (data.cu: minibatch_build_grouped); everything else waits for all of them first (data_wait_cols)
+  std::vector<cudaEvent_t> col_ev;
+  int64_t col_chunk = 0;
+  bool cols_pending = false;           // uploads queued, CSR not validated yet
   int64_t val_chunk = 0;
   fmwr::DBuf<double> val_stage[2];
   fmwr::DBuf<double> val64;            // deferred upload: the raw f64 values; narrowed into `val` range by range on the compute stream
@@ -197,6 +205,7 @@ struct fmwr_data {
     if (up_thread.joinable()) up_thread.join();
     if (val_ready) { cudaEventSynchronize(val_ready); cudaEventDestroy(val_ready); }
     for (cudaEvent_t e : val_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : col_ev) cudaEventDestroy(e);
   }
   // ALS/MCMC layouts (phases, row-major / dense copies), built on first use, dropped when the values change
   std::shared_ptr<void> als_cache;
@@ -427,6 +436,7 @@ void data_synth(fmwr_ctx* ctx, int64_t n, int64_t row_begin, int32_t n_fields, c
                 int32_t value_mode, int32_t label_mode, double noise, uint64_t seed, fmwr_data** out);
 void model_init_random(fmwr_model* m, double mean, double sd, uint64_t seed);
 fmwr_data* data_slice_columns(fmwr_data* src, int64_t c0, int64_t c1);
+void data_wait_cols(fmwr_data* d);        // one-shot path: every column chunk uploaded and the CSR validated (data.cu)
 fmwr_data* data_concat_rows(fmwr_data* const* parts, int n_parts);
 fmwr_data* data_gather_rows(fmwr_data* src, const uint32_t* order_dev, int64_t m);
 std::vector<uint32_t> visit_order_host(const fmwr_data* d, const fmwr_solver_cfg* s);

@@ -187,15 +187,36 @@ static void set_labels_f64(fmwr_data* d, const double* labels)
 void data_narrow_values(fmwr_data* d, int64_t lo, int64_t hi)
 {
   if (!d->val64.p || hi <= lo) return;
-  f64_to_f32<<<ceil_div(hi - lo, 256), 256, 0, d->ctx->stream>>>(d->val64.p + lo, d->val.p + lo, hi - lo);
-  d->ctx->launches++;
-  FMWR_CUDA(cudaGetLastError());
+  if (d->val_dev.empty()) {
+    f64_to_f32<<<ceil_div(hi - lo, 256), 256, 0, d->ctx->stream>>>(d->val64.p + lo, d->val.p + lo, hi - lo);
+    d->ctx->launches++;
+    FMWR_CUDA(cudaGetLastError());
+    return;
+  }
+  // mixed upload: only the chunks that came up as raw f64 have anything to narrow
+  for (int64_t c = lo / d->val_chunk; c * d->val_chunk < hi && c < (int64_t)d->val_dev.size(); ++c) {
+    if (!d->val_dev[c]) continue;
+    const int64_t a = std::max(lo, c * d->val_chunk), b = std::min(hi, std::min(d->nnz, (c + 1) * d->val_chunk));
+    if (b <= a) continue;
+    f64_to_f32<<<ceil_div(b - a, 256), 256, 0, d->ctx->stream>>>(d->val64.p + a, d->val.p + a, b - a);
+    d->ctx->launches++;
+    FMWR_CUDA(cudaGetLastError());
+  }
 }
 
 // host wait until the uploader has QUEUED chunk ci (its copy and its event): only then may a stream wait on the event
 void data_wait_chunk_issued(fmwr_data* d, int64_t ci)
 {
   while (d->up_chunks > 0 && d->up_issued.load(std::memory_order_acquire) <= ci) std::this_thread::yield();
+}
+
+// every column chunk in, CSR validated: what any reader of `col` other than the grouped build calls first
+void data_wait_cols(fmwr_data* d)
+{
+  if (!d->cols_pending) return;
+  for (cudaEvent_t e : d->col_ev) FMWR_CUDA(cudaStreamWaitEvent(d->ctx->stream, e, 0));
+  d->cols_pending = false;
+  finish_create(d);
 }
 
 void data_wait_values(fmwr_data* d)
@@ -236,24 +257,71 @@ static void start_value_upload(fmwr_data* d, const double* value, int64_t chunk)
   const int dev = ctx->device;
   cudaStream_t vs = ctx->copy_stream;
   float* stage[2] = {ctx->h_stage[0].p, ctx->h_stage[1].p};
-  d->up_thread = std::thread([d, value, chunk, nnz, n_chunks, dev, vs, stage] {
+  // Mixed upload.  Narrowing on the host halves the PCIe bytes but is bound by the host's memory bandwidth (read 8 B, write 4 B per
+  // value: 57 ms for configs[1]'s 390M values on this box -- exactly what the raw f64 stream takes on PCIe).  The two resources
+  // are independent, so every third chunk goes up RAW (8 B per value, straight from the caller's pinned buffer, no host work)
+  // while the host narrows the two chunks before it: PCIe carries 2 x 4 + 8 bytes per three values in the time the host
+  // narrows two -- both ~4.7 ms per three 16M-value chunks.  Raw chunks are narrowed on the device by their first reader
+  // (data_narrow_values).  Only when the caller's buffer is pinned: a pageable source would be staged by the driver.
+  static const bool mix_env = !(getenv("FMWR_MIX_UPLOAD") && atoi(getenv("FMWR_MIX_UPLOAD")) == 0);
+  static const int period = std::max(2, std::min(8, getenv("FMWR_MIX_PERIOD") ? atoi(getenv("FMWR_MIX_PERIOD")) : 3));     // one raw chunk per `period`
+  bool mix = false;
+  if (mix_env && n_chunks >= 3) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, value) == cudaSuccess && at.type == cudaMemoryTypeHost) mix = true;
+    cudaGetLastError();
+  }
+  d->val_dev.assign(n_chunks, 0);
+  if (mix) {
+    for (int64_t c = period - 1; c < n_chunks; c += period) d->val_dev[c] = 1;
+    d->val64.alloc(nnz);
+    d->val_all_narrowed = false;
+  }
+  d->val_waited = 0;
+  const int P = period;
+  d->up_thread = std::thread([d, value, chunk, nnz, n_chunks, dev, vs, stage, P] {
     cudaSetDevice(dev);
-    for (int64_t c = 0; c < n_chunks; ++c) {
-      const int64_t off = c * chunk, m = std::min(chunk, nnz - off);
-      float* buf = stage[c & 1];
-      if (c >= 2) cudaEventSynchronize(d->val_ev[c - 2]);            // the copy that last read this staging buffer
-      const int T = (int)std::min<int64_t>(n_workers, std::max<int64_t>(1, m / 65536));
-      std::vector<std::thread> pool;
-      const int64_t per = (m + T - 1) / T;
-      for (int t = 1; t < T; ++t) {
-        const int64_t lo = t * per, hi = std::min(m, lo + per);
-        if (lo < hi) pool.emplace_back(narrow_slice, value + off + lo, buf + lo, hi - lo);
+    int64_t last_use[2] = {-1, -1};            // the chunk whose copy last read each staging buffer
+    int hcount = 0;
+    for (int64_t c0 = 0; c0 < n_chunks; c0 += P) {
+      // the raw chunk of the triple goes up in two halves, one behind each narrowed chunk's copy: while the host narrows the next
+      // chunk (2.4 ms) the link carries 1.15 ms of f32 and 1.15 ms of raw f64 -- neither side waits for the other
+      const int64_t cd = c0 + P - 1;
+      const bool has_d = cd < n_chunks && d->val_dev[cd];
+      const int64_t d_off = cd * chunk, d_m = has_d ? std::min(chunk, nnz - d_off) : 0;
+      const int parts = P - 1;                 // one part behind each narrowed chunk
+      int d_sent = 0;
+      auto send_raw = [&](bool all) {
+        if (!has_d || d_sent >= parts) return;
+        const int64_t from = d_m * d_sent / parts;
+        const int upto = all ? parts : d_sent + 1;
+        const int64_t to = d_m * upto / parts;
+        if (to > from) cudaMemcpyAsync(d->val64.p + d_off + from, value + d_off + from, sizeof(double) * (to - from), cudaMemcpyHostToDevice, vs);
+        d_sent = upto;
+        if (d_sent >= parts) cudaEventRecord(d->val_ev[cd], vs);
+      };
+      for (int64_t c = c0; c < std::min(n_chunks, c0 + P); ++c) {
+        if (d->val_dev[c]) continue;
+        const int64_t off = c * chunk, m = std::min(chunk, nnz - off);
+        const int sb = hcount++ & 1;
+        float* buf = stage[sb];
+        if (last_use[sb] >= 0) cudaEventSynchronize(d->val_ev[last_use[sb]]);
+        last_use[sb] = c;
+        const int T = (int)std::min<int64_t>(n_workers, std::max<int64_t>(1, m / 65536));
+        std::vector<std::thread> pool;
+        const int64_t per = (m + T - 1) / T;
+        for (int t = 1; t < T; ++t) {
+          const int64_t lo = t * per, hi = std::min(m, lo + per);
+          if (lo < hi) pool.emplace_back(narrow_slice, value + off + lo, buf + lo, hi - lo);
+        }
+        narrow_slice(value + off, buf, std::min(m, per));
+        for (auto& th : pool) th.join();
+        cudaMemcpyAsync(d->val.p + off, buf, sizeof(float) * m, cudaMemcpyHostToDevice, vs);
+        cudaEventRecord(d->val_ev[c], vs);
+        send_raw(false);
       }
-      narrow_slice(value + off, buf, std::min(m, per));
-      for (auto& th : pool) th.join();
-      cudaMemcpyAsync(d->val.p + off, buf, sizeof(float) * m, cudaMemcpyHostToDevice, vs);
-      cudaEventRecord(d->val_ev[c], vs);
-      d->up_issued.store(c + 1, std::memory_order_release);
+      send_raw(true);
+      d->up_issued.store(std::min(n_chunks, c0 + P), std::memory_order_release);     // the period's copies and events are queued
     }
     cudaEventRecord(d->val_ready, vs);
     d->up_issued.store(n_chunks + 1, std::memory_order_release);
@@ -284,12 +352,38 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
       FMWR_CUDA(cudaMemcpy(&total, d->rowptr.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost));
       FMWR_REQUIRE((int64_t)total == nnz, FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
     }
+    static const bool host_narrow0 = !(getenv("FMWR_HOST_NARROW") && atoi(getenv("FMWR_HOST_NARROW")) == 0);
+    static const bool col_chunks = !(getenv("FMWR_COL_CHUNKS") && atoi(getenv("FMWR_COL_CHUNKS")) == 0);
+    const bool stream_cols = nnz > 0 && defer_values && host_narrow0 && col_chunks;
+    bool labels_done = false;
+    if (stream_cols && labels) {
+      // the labels first: a copy queued behind the column chunks would sit on the copy engine (and the host in its sync) until
+      // all of them are through
+      set_labels_f64(d, labels);
+      labels_done = true;
+    }
+    if (stream_cols) {
+      // one-shot training: the column ids go up in chunks on the copy stream, one event each, and nobody waits here -- the
+      // per-batch CSC of a row group is built as soon as its chunks are in (minibatch_build_grouped)
+      const int64_t cchunk_env = getenv("FMWR_VAL_CHUNK") ? atoll(getenv("FMWR_VAL_CHUNK")) : 0;      // read per call: tests shrink it
+      const int64_t cchunk = cchunk_env > 0 ? cchunk_env : (16ll << 20);
+      for (int64_t off = 0; off < nnz; off += cchunk) {
+        const int64_t mm = std::min(cchunk, nnz - off);
+        FMWR_CUDA(cudaMemcpyAsync(d->col.p + off, col_idx + off, sizeof(int32_t) * mm, cudaMemcpyHostToDevice, ctx->copy_stream));
+        cudaEvent_t ce = nullptr;
+        FMWR_CUDA(cudaEventCreateWithFlags(&ce, cudaEventDisableTiming));
+        FMWR_CUDA(cudaEventRecord(ce, ctx->copy_stream));
+        d->col_ev.push_back(ce);
+      }
+      d->col_chunk = cchunk;
+      d->cols_pending = true;
+    }
     if (nnz > 0) {
-      FMWR_CUDA(cudaMemcpyAsync(d->col.p, col_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+      if (!stream_cols) FMWR_CUDA(cudaMemcpyAsync(d->col.p, col_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
       // f64 -> f32 narrowing on the device, chunked through two staging buffers.  defer_values: the chunks travel on the
       // copy stream and nobody waits here -- the one-shot training path sorts the (batch, feature) keys (which need only
       // rowptr and col) while the 8-byte values are still crossing PCIe, and waits for val_ready before it reads them.
-      static const int64_t chunk_env = getenv("FMWR_VAL_CHUNK") ? atoll(getenv("FMWR_VAL_CHUNK")) : 0;
+      const int64_t chunk_env = getenv("FMWR_VAL_CHUNK") ? atoll(getenv("FMWR_VAL_CHUNK")) : 0;
       const int64_t chunk = chunk_env > 0 ? chunk_env : (16ll << 20);
       static const bool host_narrow = !(getenv("FMWR_HOST_NARROW") && atoi(getenv("FMWR_HOST_NARROW")) == 0);
       if (host_narrow) {
@@ -337,9 +431,14 @@ fmwr_data* data_create_f64(fmwr_ctx* ctx, int64_t n, int64_t p, int64_t nnz, con
         d->val_stage[0].release(); d->val_stage[1].release();
       }
     }
-    if (labels) set_labels_f64(d, labels);
-    ctx->h2d_bytes += 4 * n + 4 * nnz + (d->up_chunks > 0 ? 4 : 8) * nnz + (labels ? 8 * n : 0);    // values cross as f32 when narrowed on the host
-    finish_create(d);
+    if (labels && !labels_done) set_labels_f64(d, labels);
+    {
+      int64_t vbytes = (d->up_chunks > 0 ? 4 : 8) * nnz;                  // values cross as f32 when narrowed on the host
+      for (size_t c = 0; c < d->val_dev.size(); ++c)                       // ... except the chunks of a mixed upload that go up raw
+        if (d->val_dev[c]) vbytes += 4 * std::min<int64_t>(d->val_chunk, nnz - (int64_t)c * d->val_chunk);
+      ctx->h2d_bytes += 4 * n + 4 * nnz + vbytes + (labels ? 8 * n : 0);
+    }
+    if (!d->cols_pending) finish_create(d);            // (chunked columns: validated group by group, or by data_wait_cols)
   } catch (...) { delete d; throw; }
   return d;
 }
@@ -693,9 +792,153 @@ static void minibatch_build_t(fmwr_data* d, int64_t row0, int64_t batch)
   if (deferred) { d->mb_e0 = e0; d->mb_vals_pending = true; }
 }
 
+// ---- the same structure built ROW GROUP BY ROW GROUP while the column ids are still uploading (one-shot training path).
+// A group is a run of whole batches (~32M entries); its entries are sorted on (batch inside the group, feature) -- fewer key bits,
+// one radix pass less than the whole-matrix sort -- and emitted into the global arrays at the group's entry / segment offsets.
+template <class K>
+__global__ void mbg_keys(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t r0, int64_t r1, int64_t row0,
+                         uint32_t batch, uint32_t b0, int colbits, uint32_t eg0, K* __restrict__ keys, uint32_t* __restrict__ erow)
+{
+  const int64_t row = r0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (row >= r1) return;
+  const uint32_t b = rowptr[row], e = rowptr[row + 1];
+  const uint64_t bid = (uint64_t)((row - row0) / batch) - b0;
+  for (uint32_t j = b + (threadIdx.x & 31); j < e; j += 32) {
+    keys[j - eg0] = (K)((bid << colbits) | (uint64_t)col[j]);
+    erow[j - eg0] = (uint32_t)row;
+  }
+}
+
+template <class K>
+__global__ void mbg_emit(const K* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ segid,
+                         const uint32_t* __restrict__ perm_local, const uint32_t* __restrict__ erow, int64_t mg, int colbits, uint32_t eoff,
+                         uint32_t seg_base, uint32_t n_seg_g, uint32_t* __restrict__ seg_ptr, uint4* __restrict__ seg_rec,
+                         uint32_t* __restrict__ ent_row, uint32_t* __restrict__ perm_global)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mg) return;
+  const uint32_t e = perm_local[i];
+  const uint32_t r = erow[e];
+  ent_row[eoff + i] = r;
+  perm_global[eoff + i] = e + eoff;                  // relative to the first entry of the whole structure, like the one-piece build
+  if (head[i]) {
+    const uint32_t s = seg_base + segid[i];
+    seg_ptr[s] = eoff + (uint32_t)i;
+    seg_rec[s] = make_uint4((uint32_t)((uint64_t)keys[i] & ((1ull << colbits) - 1ull)), 0u, r, 0u);      // value: mb_fill_values
+  }
+  if (i == mg - 1) seg_ptr[seg_base + n_seg_g] = eoff + (uint32_t)mg;
+}
+
+__global__ void mbg_batch_first_seg(const uint32_t* __restrict__ batch_ent, uint32_t eg0, const uint32_t* __restrict__ segid, uint32_t mg, uint32_t n_seg_g,
+                                    uint32_t seg_base, int64_t b0, int64_t count, uint32_t* __restrict__ host_dst)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const uint32_t i = batch_ent[b0 + k] - eg0;
+  host_dst[k] = seg_base + (i < mg ? segid[i] : n_seg_g);
+}
+
+template <class K>
+static void minibatch_build_grouped(fmwr_data* d, int64_t row0, int64_t batch, int64_t gb /* batches per group */, int gbits)
+{
+  fmwr_ctx* ctx = d->ctx;
+  const int64_t rows = d->n - row0;
+  const int64_t n_batches = ceil_div64(rows, batch);
+  d->mb_batch_seg.assign(n_batches + 1, 0);
+  ctx->h_u32.ensure(2 * (size_t)n_batches + 64);
+  uint32_t* hp = ctx->h_u32.p;
+  DBuf<uint32_t> bp;
+  bp.alloc(n_batches + 1);
+  FMWR_LAUNCH(ctx, batch_row_ptr, ceil_div(n_batches + 1, 256), 256, 0, d->rowptr.p, row0, batch, d->n, n_batches + 1, bp.p);
+  FMWR_LAUNCH(ctx, peek_u32, ceil_div(n_batches + 1, 256), 256, 0, bp.p, n_batches + 1, hp + 8);
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> ent(hp + 8, hp + 8 + n_batches + 1);       // absolute first entry of every batch
+  const uint32_t e0 = ent[0], e1 = ent[n_batches];
+  const int64_t m = (int64_t)e1 - e0;
+  d->mb_batch_ent.resize(n_batches + 1);
+  for (int64_t b = 0; b <= n_batches; ++b) d->mb_batch_ent[b] = (int64_t)ent[b] - (int64_t)e0;
+  const int colbits = bits_for((uint64_t)(d->p > 0 ? d->p - 1 : 0));
+  // segments: at most one per entry and at most one per (batch, feature)
+  const int64_t seg_cap = std::min<int64_t>(m, n_batches * d->p);
+  d->mb_ent_row.alloc(m + 8); d->mb_ent_val.alloc(m + 8); d->mb_perm.alloc(m);
+  d->mb_seg_ptr.alloc((size_t)seg_cap + 1 + 8); d->mb_seg_rec.alloc(seg_cap);
+  int64_t mg_max = 0;
+  for (int64_t b0 = 0; b0 < n_batches; b0 += gb) mg_max = std::max<int64_t>(mg_max, (int64_t)ent[std::min(n_batches, b0 + gb)] - ent[b0]);
+  DBuf<K> keys_in, keys_out;
+  DBuf<uint32_t> perm, erow, head, segid;
+  DBuf<int> flags;
+  keys_in.alloc(mg_max); keys_out.alloc(mg_max); perm.alloc(mg_max); erow.alloc(mg_max); head.alloc(mg_max); segid.alloc(mg_max);
+  flags.alloc(1); flags.zero(ctx->stream);
+  uint32_t seg_base = 0;
+  int64_t next_ev = 0;                                 // column chunks already waited for
+  for (int64_t b0 = 0; b0 < n_batches; b0 += gb) {
+    const int64_t b1 = std::min(n_batches, b0 + gb);
+    const int64_t r0 = row0 + b0 * batch, r1 = std::min(d->n, row0 + b1 * batch);
+    const uint32_t eg0 = ent[b0], eg1 = ent[b1];
+    const int64_t mg = (int64_t)eg1 - eg0;
+    // the chunks that hold this group's column ids
+    const int64_t need = mg > 0 ? ((int64_t)eg1 - 1) / d->col_chunk + 1 : next_ev;
+    for (; next_ev < need && next_ev < (int64_t)d->col_ev.size(); ++next_ev) FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->col_ev[next_ev], 0));
+    uint32_t n_seg_g = 0;
+    if (mg > 0) {
+      FMWR_LAUNCH(ctx, validate_csr, ceil_div(r1 - r0, 256), 256, 0, d->rowptr.p + r0, d->col.p, r1 - r0, (uint32_t)d->p, (uint32_t)d->nnz, flags.p);
+      FMWR_LAUNCH(ctx, mbg_keys<K>, ceil_div((r1 - r0) * 32, 256), 256, 0, d->rowptr.p, d->col.p, r0, r1, row0, (uint32_t)batch, (uint32_t)b0, colbits, eg0,
+                  keys_in.p, erow.p);
+      if (sizeof(K) == 4) sort_pairs_u32(ctx, (const uint32_t*)keys_in.p, (uint32_t*)keys_out.p, nullptr, perm.p, mg, colbits + gbits);
+      else sort_pairs_u64(ctx, (const uint64_t*)keys_in.p, (uint64_t*)keys_out.p, nullptr, perm.p, mg, colbits + gbits);
+      FMWR_LAUNCH(ctx, mb_heads<K>, ceil_div(mg, 256), 256, 0, keys_out.p, mg, head.p);
+      exclusive_scan_u32(ctx, head.p, segid.p, mg);
+      FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, segid.p + (mg - 1), head.p + (mg - 1), hp);
+    }
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mg > 0) n_seg_g = hp[0] + hp[1];
+    FMWR_REQUIRE((int64_t)seg_base + n_seg_g <= seg_cap, FMWR_ERR_SHAPE, "segment count exceeds its bound");
+    if (mg > 0) {
+      FMWR_LAUNCH(ctx, mbg_emit<K>, ceil_div(mg, 256), 256, 0, keys_out.p, head.p, segid.p, perm.p, erow.p, mg, colbits, eg0 - e0, seg_base, n_seg_g,
+                  d->mb_seg_ptr.p, d->mb_seg_rec.p, d->mb_ent_row.p, d->mb_perm.p);
+      FMWR_LAUNCH(ctx, mb_seg_len, ceil_div(n_seg_g, 256), 256, 0, d->mb_seg_ptr.p + seg_base, d->mb_seg_rec.p + seg_base, n_seg_g);
+    }
+    FMWR_LAUNCH(ctx, mbg_batch_first_seg, ceil_div(b1 - b0, 256), 256, 0, bp.p, eg0, segid.p, (uint32_t)mg, n_seg_g, seg_base, b0, b1 - b0, hp + 16);
+    FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t b = b0; b < b1; ++b) d->mb_batch_seg[b] = hp[16 + (b - b0)];
+    seg_base += n_seg_g;
+  }
+  const uint32_t n_seg = seg_base;
+  d->mb_batch_seg[n_batches] = n_seg;
+  for (int64_t b = n_batches - 1; b >= 0; --b) if (d->mb_batch_seg[b] > d->mb_batch_seg[b + 1]) d->mb_batch_seg[b] = d->mb_batch_seg[b + 1];
+  if (m == 0) FMWR_CUDA(cudaMemsetAsync(d->mb_seg_ptr.p, 0, 4, ctx->stream));
+  // rows before row0 (the skipped first row) were not part of any group: validate them with the rest of the checks
+  for (; next_ev < (int64_t)d->col_ev.size(); ++next_ev) FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->col_ev[next_ev], 0));
+  if (row0 > 0) FMWR_LAUNCH(ctx, validate_csr, ceil_div(row0, 256), 256, 0, d->rowptr.p, d->col.p, row0, (uint32_t)d->p, (uint32_t)d->nnz, flags.p);
+  int h = 0;
+  FMWR_CUDA(cudaMemcpyAsync(&h, flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+  d->cols_pending = false;
+  FMWR_REQUIRE(!(h & 4), FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
+  FMWR_REQUIRE(!(h & 1), FMWR_ERR_SHAPE, "col_idx out of range (>= number of features)");
+  FMWR_REQUIRE(!(h & 2), FMWR_ERR_SHAPE, "col_idx must be strictly ascending within each row");
+  d->mb_batch = batch; d->mb_row0 = row0;
+  d->mb_e0 = e0; d->mb_vals_pending = true;
+}
+
 void minibatch_build(fmwr_data* d, int64_t row0, int64_t batch)
 {
   if (d->mb_batch == batch && d->mb_row0 == row0) return;
+  if (d->cols_pending && batch > 0 && d->n - row0 > 0 && d->up_chunks > 0 && d->nnz > 0) {
+    // one-shot path, columns and values still crossing PCIe: build group by group behind the upload
+    const int64_t rows = d->n - row0;
+    const int64_t n_batches = ceil_div64(rows, batch);
+    const double per_batch = (double)d->nnz / (double)n_batches;
+    const double group_entries = getenv("FMWR_GROUP_ENTRIES") ? atof(getenv("FMWR_GROUP_ENTRIES")) : (double)(32ll << 20);
+    int64_t gb = (int64_t)std::max(1.0, std::floor(group_entries / std::max(1.0, per_batch)));
+    if (gb > n_batches) gb = n_batches;
+    const int gbits = bits_for((uint64_t)(gb > 0 ? gb - 1 : 0));
+    const int bits = bits_for((uint64_t)(d->p > 0 ? d->p - 1 : 0)) + gbits;
+    if (bits <= 32) minibatch_build_grouped<uint32_t>(d, row0, batch, gb, gbits);
+    else minibatch_build_grouped<uint64_t>(d, row0, batch, gb, gbits);
+    return;
+  }
+  data_wait_cols(d);
   FMWR_REQUIRE(batch > 0, FMWR_ERR_ARG, "batch_size must be positive");
   const int64_t rows = d->n - row0;
   const int64_t n_batches = rows > 0 ? ceil_div64(rows, batch) : 0;

@@ -941,7 +941,8 @@ static void train_minibatch_t(fmwr_ctx* ctx, fmwr_model* m, fmwr_data* d, const 
         if (last_entry >= 0 && d->val_chunk > 0) {
           const size_t ci = std::min<size_t>(d->val_ev.size() - 1, (size_t)(last_entry / d->val_chunk));
           data_wait_chunk_issued(d, (int64_t)ci);          // host-narrowed upload: the event exists once the uploader queued the chunk
-          FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->val_ev[ci], 0));
+          // every chunk up to ci (a mixed upload queues a raw chunk before the two narrowed ones in front of it)
+          for (; d->val_waited <= (int64_t)ci; ++d->val_waited) FMWR_CUDA(cudaStreamWaitEvent(ctx->stream, d->val_ev[d->val_waited], 0));
         }
         data_narrow_values(d, b == 0 ? 0 : (int64_t)d->mb_e0 + d->mb_batch_ent[b], (int64_t)d->mb_e0 + d->mb_batch_ent[b + 1]);
         minibatch_fill_values(d, (uint32_t)d->mb_batch_seg[b], (uint32_t)d->mb_batch_seg[b + 1]);

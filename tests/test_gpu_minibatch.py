@@ -164,14 +164,22 @@ def test_warm_state_continues_the_optimizer(gpu_ctx, solver, regs, mode):
     d.close()
 
 
+@pytest.mark.parametrize("group_entries,pinned", [(None, False), ("1000000", False), ("250000", False), ("1000000", True), (None, True)])
 @pytest.mark.parametrize("solver", [O.FTRL, O.SGD])
-def test_one_shot_train_equals_handle_path(gpu_ctx, solver):
+def test_one_shot_train_equals_handle_path(gpu_ctx, monkeypatch, solver, group_entries, pinned):
     """fmwr_train (host fm.matrix lists in, host model out; the values upload on the copy stream while the per-batch CSC is
     sorted, and every batch waits only for its own chunk) must give the parameters of the handle path bit for bit --
     also over two epochs, when the second pass finds every value in place."""
     import ctypes as C
     ctx = gpu_ctx
     lib = L.lib()
+    # the one-shot path builds the per-batch CSC row group by row group behind the column upload: one group, ~9 groups of
+    # several batches, and one batch per group (43 groups) must all give the one-piece structure
+    # pinned: with page-locked caller buffers every third value chunk goes up as raw f64 and is narrowed on the device by its
+    # first reader (mixed upload); the rounding is the same conversion either way, so the result stays bit-identical
+    monkeypatch.setenv("FMWR_VAL_CHUNK", "1500000")            # several column / value chunks (and group boundaries inside them)
+    if group_entries:
+        monkeypatch.setenv("FMWR_GROUP_ENTRIES", group_entries)
     n, fields, k = 700_000, [997] * 13, 8               # 9.1M entries: several upload chunks' worth is not needed for the check
     rowptr, col, val, p = synth.fields_csr(n, fields, None, 1, 21)
     score = synth.planted_scores_fast(rowptr, col, val, p, seed=22)
@@ -190,8 +198,16 @@ def test_one_shot_train_equals_handle_path(gpu_ctx, solver):
         rs = np.diff(rowptr.astype(np.int64)).astype(np.int32)
         ci = col.astype(np.int32); v64 = val.astype(np.float64); y64 = y.astype(np.float64)
         bw0 = C.c_double(w0); bw = w.copy(); bv = v.copy()
-        L.check(lib.fmwr_train(C.byref(mc), C.byref(sc), C.c_int64(n), C.c_int64(p), C.c_int64(ci.size), L.ptr(rs), L.ptr(ci), L.ptr(v64),
-                               L.ptr(y64), C.byref(bw0), L.ptr(bw), L.ptr(bv), None))
+        if pinned:
+            for arr in (ci, v64):
+                L.check(lib.fmwr_host_pin(L.ptr(arr), C.c_int64(arr.nbytes)))
+        try:
+            L.check(lib.fmwr_train(C.byref(mc), C.byref(sc), C.c_int64(n), C.c_int64(p), C.c_int64(ci.size), L.ptr(rs), L.ptr(ci), L.ptr(v64),
+                                   L.ptr(y64), C.byref(bw0), L.ptr(bw), L.ptr(bv), None))
+        finally:
+            if pinned:
+                for arr in (ci, v64):
+                    lib.fmwr_host_unpin(L.ptr(arr))
         assert a[0] == bw0.value and np.array_equal(a[1], bw) and np.array_equal(a[2], bv)
 
 

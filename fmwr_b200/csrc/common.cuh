@@ -279,6 +279,18 @@ __device__ __forceinline__ char* peer_base(const PeerArgs& pa, int i)
   return p;
 }
 
+// __threadfence_system() is fence.sc.sys (MEMBAR.SC.SYS); the release / acquire patterns here need no sequential consistency
+// between fences, and the acq_rel form is the cheaper instruction (the cta-scope pair measured 3000-6000 vs < 1000 cycles in the
+// exact pipeline, profiles/r02_summary.md).  FMWR_PEER_SC_FENCE=1 at build time restores the old form for A/B.
+#ifdef FMWR_PEER_SC_FENCE
+__device__ __forceinline__ void peer_fence_sys() { __threadfence_system(); }
+#else
+__device__ __forceinline__ void peer_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+#endif
+#ifndef FMWR_PEER_NAP
+#define FMWR_PEER_NAP 0          // ns between polls of a peer flag; 0 = plain spinning (__nanosleep wakes late)
+#endif
+__device__ __forceinline__ void peer_nap() { if (FMWR_PEER_NAP) __nanosleep(FMWR_PEER_NAP); }
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 // flag stores AFTER one __threadfence_system(): fence + relaxed stores is the release pattern, and it costs one system-scope
 // fence per publication instead of one per peer (st.release.sys in a loop over 8 ranks was 8 fences back to back)
@@ -292,13 +304,13 @@ __device__ __forceinline__ void peer_signal(const PeerArgs& pa, int flag_base, i
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
-    __threadfence_system();                                   // this CTA's (peer) stores before the count
+    peer_fence_sys();                                   // this CTA's (peer) stores before the count
     const unsigned done = atomicAdd(ctl + count_word, 1u);
     if (done == gridDim.x - 1) {
       ctl[count_word] = 0u;
       const uint32_t ep = ctl[epoch_word] + 1u;
       ctl[epoch_word] = ep;
-      __threadfence_system();
+      peer_fence_sys();
 #pragma unroll
       for (int h = 0; h < 8; ++h)
         if (h < pa.world) st_relaxed_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
@@ -317,7 +329,7 @@ __device__ __forceinline__ void peer_wait(const PeerArgs& pa, int flag_base, int
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(f) - ep) < 0) {
       if (clock64() - t0 > 40000000000ll) { ctl[PEER_ERR] = 1u; break; }   // ~20 s: a peer died; the host reports it
-      __nanosleep(64);
+      peer_nap();
     }
   }
   __syncthreads();
@@ -334,10 +346,10 @@ __device__ __forceinline__ bool peer_arrive_last(const PeerArgs& pa, int count_w
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
-    __threadfence_system();                                   // this CTA's (local and peer) stores before the count
+    peer_fence_sys();                                   // this CTA's (local and peer) stores before the count
     const unsigned done = atomicAdd(ctl + count_word, 1u);
     s_last = done == gridDim.x - 1;
-    if (s_last) { ctl[count_word] = 0u; __threadfence(); }
+    if (s_last) { ctl[count_word] = 0u; asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
   }
   __syncthreads();
   return s_last != 0;
@@ -349,7 +361,7 @@ __device__ __forceinline__ void peer_publish(const PeerArgs& pa, int flag_base, 
   if (threadIdx.x == 0) {
     uint32_t* ctl = reinterpret_cast<uint32_t*>(peer_base(pa, pa.rank));
     ctl[epoch_word] = ep;
-    __threadfence_system();
+    peer_fence_sys();
 #pragma unroll
     for (int h = 0; h < 8; ++h)
       if (h < pa.world) st_relaxed_sys(reinterpret_cast<uint32_t*>(pa.base[h]) + flag_base + 32 * pa.rank, ep);
@@ -366,7 +378,7 @@ __device__ __forceinline__ void peer_wait_ep(const PeerArgs& pa, int flag_base, 
     // invalidates the SM's L1, and hundreds of CTAs polling that way slow down the CTAs that are still computing
     while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(f) - ep) < 0) {
       if (clock64() - t0 > 40000000000ll) { ctl[PEER_ERR] = 1u; break; }
-      __nanosleep(32);
+      peer_nap();
     }
     (void)ld_acquire_sys(f);
   }

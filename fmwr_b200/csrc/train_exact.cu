@@ -520,7 +520,8 @@ struct ExactPipeLaunch {
     if (pl.ecap < 32 / LPR) return;          // a factor row too wide to stage even one round: the CTA-wide kernel takes it
     // fp64 FTRL / TDAP are bound by the IEEE sqrt / divide sequences of the 1248 coordinate steps of a sample, not by latency: one
     // warp per sample loses to the CTA-wide kernel's 14 warps per sample there (7.8 vs 4.5 us per sample measured)
-    // TDAP (five staged arrays: 4-5 samples in flight, and the longest coordinate step) also loses: 3.4 vs 1.9 us per sample in fp32
+    // TDAP (five staged arrays: only 4 samples in flight, and the longest coordinate step) is a tie in fp32 (1.84 vs 1.91 us per sample)
+    // and stays on the kernel whose speed does not depend on the data's column collisions
     if (((sizeof(TT) == 8 && SOLVER != FMWR_SGD) || SOLVER == FMWR_TDAP) && !force) return;
     FMWR_CUDA(cudaFuncSetAttribute(exact_pipe_kernel<TT, LPR, CH, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     FMWR_LAUNCH(ctx, (exact_pipe_kernel<TT, LPR, CH, SOLVER>), 1, (pl.teams + 3) * 32, pl.total, args, pl.teams, pl.ecap, pl.na,

@@ -141,6 +141,7 @@ struct XpFixed {
   uint32_t rCol[XP_R][XP_RN];
   float rVal[XP_R][XP_RN];
   uint16_t rDep[XP_R][XP_RN];              // per entry: distance to the sample that last held its column | distance to the set's evicted sample << 8 (0: none in flight)
+  uint16_t rDep2[XP_R][XP_RN];             // F6 only: the same two distances for the column the entry's POSITION names (read by the refresh)
   uint4 hSet[XP_H];                        // {column way 0, column way 1, last sample way 0 | way 1 << 16, latest evicted sample}
   uint32_t wCol[XP_MAXT][XP_RN];           // chunk columns / values of rows that do not fit the stage in one piece
   float wVal[XP_MAXT][XP_RN];
@@ -309,22 +310,23 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       if (in0) s0 = F.hSet[h0];
       if (in1) s1 = F.hSet[h1];
       if (f6) { if (in0) p0s = F.hSet[xp_hash(lane)]; if (in1) p1s = F.hSet[xp_hash(lane + 32u)]; }
-      uint32_t dep0 = in0 ? xp_lookup(s0, c0, q16) : 0u, dep1 = in1 ? xp_lookup(s1, c1, q16) : 0u;
+      uint32_t dep0 = in0 ? xp_lookup(s0, c0, q16) : 0u, dep1 = in1 ? xp_lookup(s1, c1, q16) : 0u, posdep0 = 0u, posdep1 = 0u;
       if (f6) {
         // the refresh READS the linear state of column j (= the position): wait for whoever wrote it last.  Reads are not
         // entered in the table (every sample reads positions 0 .. nnz-1; readers do not conflict with each other); a sample
-        // that WRITES such a column waits for every earlier sample instead (write_low below).  Two more samples do not fit
-        // the entry: all four fold into "everything since the farthest one".
-        const uint32_t d0 = in0 ? xp_lookup(p0s, lane, q16) : 0u, d1 = in1 ? xp_lookup(p1s, lane + 32u, q16) : 0u;
-        if (d0) dep0 = max(max(dep0 & 0xffu, d0 & 0xffu), max(dep0 >> 8, d0 >> 8)) | 0x8000u;
-        if (d1) dep1 = max(max(dep1 & 0xffu, d1 & 0xffu), max(dep1 >> 8, d1 >> 8)) | 0x8000u;
+        // that WRITES such a column waits for every earlier sample instead (write_low below).  (Folding these into "every
+        // sample since the farthest of the four" serialised 60 % of the samples: an old, finished sample named by a set's
+        // evicted field turned into a wait for the three samples in flight.)
+        posdep0 = in0 ? xp_lookup(p0s, lane, q16) : 0u; posdep1 = in1 ? xp_lookup(p1s, lane + 32u, q16) : 0u;
+        if (in0) F.rDep2[slot][lane] = (uint16_t)posdep0;
+        if (in1) F.rDep2[slot][lane + 32] = (uint16_t)posdep1;
       }
       if (in0) F.hSet[h0] = xp_insert(s0, c0, q16);
       if (in1) F.hSet[h1] = xp_insert(s1, c1, q16);
       for (uint32_t j = XP_RN + lane; j < nnz; j += 32) { const uint32_t c = a.col[b + j], h = xp_hash(c); F.hSet[h] = xp_insert(F.hSet[h], c, q16); }
       if (in0) F.rDep[slot][lane] = (uint16_t)dep0;
       if (in1) F.rDep[slot][lane + 32] = (uint16_t)dep1;
-      { const bool anyd = __any_sync(0xffffffffu, (dep0 | dep1) != 0u); if (lane == 0) F.mDep[slot] = anyd ? 1u : 0u; }
+      { const bool anyd = __any_sync(0xffffffffu, (dep0 | dep1 | posdep0 | posdep1) != 0u); if (lane == 0) F.mDep[slot] = anyd ? 1u : 0u; }
       if (f6) {
         max_nnz = max(max_nnz, nnz);
         bool write_low = (in0 && c0 < max_nnz) || (in1 && c1 < max_nnz);
@@ -416,9 +418,8 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       else if (F.mDep[slot]) {
 #endif
         for (uint32_t j = lane; j < nnz; j += 32) {
-          const uint32_t dd = F.rDep[slot][j];
-          if (dd & 0x8000u) { for (uint32_t k2 = 1; k2 <= (dd & 0xffu); ++k2) has_dep |= open_dep(k2); }
-          else if (dd) has_dep |= open_dep(dd & 0xffu) | open_dep(dd >> 8);
+          const uint32_t dd = F.rDep[slot][j] | (f6 ? (uint32_t)F.rDep2[slot][j] << 16 : 0u);
+          if (dd) has_dep |= open_dep(dd & 0xffu) | open_dep((dd >> 8) & 0xffu) | open_dep((dd >> 16) & 0xffu) | open_dep(dd >> 24);
         }
       }
       has_dep = __any_sync(0xffffffffu, has_dep) && !(a.prefetch & 2);      // bit 1: FMWR_EXACT_NOHAZARD=1, the tests' proof that the tracker matters
@@ -435,14 +436,11 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
         if (lane >= 1 && lane < teams && q >= (uint32_t)lane) { const uint32_t d = q - lane; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
       } else {
         for (uint32_t j = lane; j < nnz; j += 32) {
-          const uint32_t dd = F.rDep[slot][j];
-          if (dd & 0x8000u) {
-            // (F6) every sample since the farthest dependency
-            for (uint32_t k2 = 1; k2 <= (dd & 0xffu) && k2 <= q; ++k2) { const uint32_t d = q - k2; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
-          } else {
-            const uint32_t d0 = dd & 0xffu, d1 = dd >> 8;
-            if (d0 && d0 <= q) { const uint32_t d = q - d0; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
-            if (d1 && d1 <= q) { const uint32_t d = q - d1; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
+          const uint32_t dd = F.rDep[slot][j] | (f6 ? (uint32_t)F.rDep2[slot][j] << 16 : 0u);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const uint32_t dist = (dd >> (8 * k2)) & 0xffu;
+            if (dist && dist <= q) { const uint32_t d = q - dist; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
           }
         }
       }

@@ -62,7 +62,10 @@ constexpr int XP_G = XP_BATCH;                    // samples per pipeline batch
 #endif
 #define XP_PRAGMA(x) _Pragma(#x)
 #define XP_UNROLL(n) XP_PRAGMA(unroll n)
-constexpr int XP_LOGH = 12, XP_H = 1 << XP_LOGH;      // sets of the hazard table
+#ifndef XP_HASH_BITS
+#define XP_HASH_BITS 12
+#endif
+constexpr int XP_LOGH = XP_HASH_BITS, XP_H = 1 << XP_LOGH;      // sets of the hazard table
 
 __device__ __forceinline__ void xp_cp16(void* dst, const void* src)
 {

@@ -495,6 +495,14 @@ XP_UNROLL(XP_UNROLL_G)
       for (uint32_t e0 = 0; e0 < nnz; e0 += (uint32_t)ecap) {
         const uint32_t cnt = min((uint32_t)ecap, nnz - e0);
         gather(e0, cnt);
+        if (pending != 0xffffffffu) {
+          // the previous sample's done tag: its stores were issued a whole gather (a DRAM round trip) ago, so the fence finds
+          // them landed; publishing here rather than after the forward pass takes ~1500 cycles off what a dependent sample waits
+          xp_fence();
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&F.done[pending & (XP_R - 1)]) = pending + 1u;
+          pending = 0xffffffffu;
+        }
 XP_UNROLL(XP_UNROLL_F)
         for (uint32_t en = slotw; en < cnt; en += SPW) {
           const T x = T(cval[en]);
@@ -522,8 +530,8 @@ XP_UNROLL(XP_UNROLL_F)
           for (int i = 0; i < VN; ++i) acc += T(0.5) * S[ch][i] * S[ch][i];
       }
       const T rest = warp_sum(acc);
-      if (pending != 0xffffffffu) {
-        xp_fence();                          // the previous sample's stores were issued a whole forward pass ago
+      if (pending != 0xffffffffu) {            // a row without entries never entered the loop above
+        xp_fence();
         __syncwarp();
         if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&F.done[pending & (XP_R - 1)]) = pending + 1u;
         pending = 0xffffffffu;

@@ -80,6 +80,23 @@ __device__ __forceinline__ void xp_cp_commit() { asm volatile("cp.async.commit_g
 __device__ __forceinline__ void xp_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t xp_hash(uint32_t c) { return (c * 2654435761u) >> (32 - XP_LOGH); }
 __device__ __forceinline__ uint32_t xp_ld(const volatile uint32_t* p) { return *p; }
+// Watchdog of the pollers: every wait in this kernel is for a strictly EARLIER sample (or for the warp that feeds the ring), so
+// none can last; if one does (a bug), the kernel traps -- the host sees a CUDA error ("unspecified launch failure") instead of a
+// hung GPU.
+#ifndef XP_WATCHDOG_CYCLES
+#define XP_WATCHDOG_CYCLES 6000000000ll      // ~3 s at 2 GHz; a wait is microseconds
+#endif
+struct XpSpin {
+  uint32_t n = 0; long long t0 = 0;
+  __device__ __forceinline__ void tick(const char*, uint32_t)
+  {
+    if (XP_NAP) __nanosleep(XP_NAP);
+    if ((++n & 0xffffu) != 0u) return;
+    const long long now = clock64();
+    if (t0 == 0) { t0 = now; return; }
+    if (now - t0 > XP_WATCHDOG_CYCLES) __trap();       // (no printf: its stack frame cost the FTRL kernel 18 %)
+  }
+};
 // Every thread of this kernel is in ONE CTA, so CTA scope is the widest scope any synchronisation here needs.  __threadfence() /
 // __threadfence_block() are fence.sc (MEMBAR.SC.*: 3000-6000 cycles each where measured, profiles/r02_summary.md); the
 // acquire-release form orders the same accesses without the sequential-consistency round trip.
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
           const uint32_t q = (it - 2) * XP_G + lane;
           if (q < total) {
             const int slot = q & (XP_R - 1);
-            if (q >= XP_R) { while (xp_ld(&F.done[slot]) < q - XP_R + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }      // the slot's previous sample has finished
+            if (q >= XP_R) { XpSpin sp_; while (xp_ld(&F.done[slot]) < q - XP_R + 1u) sp_.tick("a free ring slot", q); }      // the slot's previous sample has finished
             const uint32_t nnz = eB - bB;
             F.mN[slot] = nnz; F.mB[slot] = bB; F.mY[slot] = yB; F.mAll[slot] = nnz > (uint32_t)ecap ? 1u : 0u;
           }
@@ -300,7 +317,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       long long p0 = clock64();
 #endif
       const int slot = q & (XP_R - 1);
-      while (xp_ld(&F.fetched[slot]) != q + 1u) { if (XP_NAP) __nanosleep(XP_NAP); }
+      { XpSpin sp_; while (xp_ld(&F.fetched[slot]) != q + 1u) sp_.tick("the fetch warp", q); }
       xp_order();
       PPROF(0)
       const uint32_t nnz = F.mN[slot], b = F.mB[slot];
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
         const int slot = q & (XP_R - 1);
         // a hint for a sample the workers already passed is useless: skip ahead instead of falling behind
         if (xp_ld(&F.done[slot]) >= q + 1u || xp_ld(&F.loaded[slot]) > q + 1u) continue;
-        while (xp_ld(&F.fetched[slot]) < q + 1u) { if (XP_NAP) __nanosleep(XP_NAP); }
+        { XpSpin sp_; while (xp_ld(&F.fetched[slot]) < q + 1u) sp_.tick("the fetch warp (hints)", q); }
         __syncwarp();
         xp_order();
         if (xp_ld(&F.fetched[slot]) != q + 1u) continue;         // the slot moved on
@@ -401,7 +418,7 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       long long p0 = clock64();
 #endif
       const int slot = q & (XP_R - 1);
-      while (xp_ld(&F.loaded[slot]) != q + 1u) { if (XP_NAP) __nanosleep(XP_NAP); }
+      { XpSpin sp_; while (xp_ld(&F.loaded[slot]) != q + 1u) sp_.tick("the hazard warp", q); }
       XPROF(0)
       __syncwarp();
       xp_order();
@@ -436,14 +453,14 @@ __global__ void __launch_bounds__((XP_MAXT + 3) * 32, 1) exact_pipe_kernel(Exact
       }
       if (!has_dep) {
       } else if (wait_all) {
-        if (lane >= 1 && lane < teams && q >= (uint32_t)lane) { const uint32_t d = q - lane; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
+        if (lane >= 1 && lane < teams && q >= (uint32_t)lane) { const uint32_t d = q - lane; XpSpin sp_; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) sp_.tick("all earlier samples", q); }
       } else {
         for (uint32_t j = lane; j < nnz; j += 32) {
           const uint32_t dd = F.rDep[slot][j] | (f6 ? (uint32_t)F.rDep2[slot][j] << 16 : 0u);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
             const uint32_t dist = (dd >> (8 * k2)) & 0xffu;
-            if (dist && dist <= q) { const uint32_t d = q - dist; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) { if (XP_NAP) __nanosleep(XP_NAP); } }
+            if (dist && dist <= q) { const uint32_t d = q - dist; XpSpin sp_; while (xp_ld(&F.done[d & (XP_R - 1)]) < d + 1u) sp_.tick("a dependency", q); }
           }
         }
       }
@@ -541,7 +558,7 @@ XP_UNROLL(XP_UNROLL_F)
       // ---- the scalar chain: w0, multiplier, w0's optimizer step, in sample order
       T mult = T(0), u_w = T(0), u_v = T(0);
       if (lane == 0) {
-        while (xp_ld(&F.tok) != q) { if (XP_NAP_TOK) __nanosleep(XP_NAP_TOK); }
+        { XpSpin sp_; while (xp_ld(&F.tok) != q) sp_.tick("the token", q); }
         XPROF(3)
         xp_order();
         volatile double* sc = F.sc;

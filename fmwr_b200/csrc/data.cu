@@ -903,8 +903,17 @@ static void minibatch_build_grouped(fmwr_data* d, int64_t row0, int64_t batch, i
       FMWR_LAUNCH(ctx, mb_heads<K>, ceil_div(mg, 256), 256, 0, keys_out.p, mg, head.p);
       exclusive_scan_u32(ctx, head.p, segid.p, mg);
       FMWR_LAUNCH(ctx, peek2_u32, 1, 32, 0, segid.p + (mg - 1), head.p + (mg - 1), hp);
+      FMWR_LAUNCH(ctx, peek_u32, 1, 32, 0, reinterpret_cast<const uint32_t*>(flags.p), (int64_t)1, hp + 4);
     }
     FMWR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mg > 0) {
+      // a bad group stops the build here, with the reference's message, before its keys are taken for segments
+      const uint32_t hf = hp[4];
+      if (hf) d->cols_pending = false;
+      FMWR_REQUIRE(!(hf & 4), FMWR_ERR_SHAPE, "the length of input's row_size is not correct...");
+      FMWR_REQUIRE(!(hf & 1), FMWR_ERR_SHAPE, "col_idx out of range (>= number of features)");
+      FMWR_REQUIRE(!(hf & 2), FMWR_ERR_SHAPE, "col_idx must be strictly ascending within each row");
+    }
     if (mg > 0) n_seg_g = hp[0] + hp[1];
     FMWR_REQUIRE((int64_t)seg_base + n_seg_g <= seg_cap, FMWR_ERR_SHAPE, "segment count exceeds its bound");
     if (mg > 0) {

@@ -348,3 +348,38 @@ def test_throughput_mode_follows_a_strided_visit_sequence(gpu_ctx):
     assert relerr(a[0], b[0]) < 1e-10 and relerr(a[1], b[1]) < 1e-10 and relerr(a[2], b[2]) < 1e-10
     c, tc = run(L.MODE_MINIBATCH, 64, None, random_step=3, max_iter=900)
     assert tc["iters_done"] == 900 and np.isfinite(c[2]).all() and float(np.max(np.abs(c[2] - v))) > 1e-3
+
+
+@pytest.mark.parametrize("bad", ["range", "order"])
+def test_one_shot_train_rejects_a_bad_matrix(gpu_ctx, bad):
+    """The one-shot path uploads the column ids in chunks and validates them group by group while it builds the per-batch CSC
+    (data.cu: minibatch_build_grouped): a column out of range or a row that is not ascending must still come back as the
+    reference's shape error (src/util/Smatrix.h:52 family), not as a crash in the kernels that follow."""
+    import ctypes as C
+    lib = L.lib()
+    n, fields, k = 60_000, [97] * 7, 4
+    rowptr, col, val, p = synth.fields_csr(n, fields, None, 1, 5)
+    col = col.copy()
+    if bad == "range":
+        col[rowptr[41_000] + 3] = p + 5
+    else:
+        j = rowptr[17_000]
+        col[j], col[j + 1] = col[j + 1], col[j]
+    y = np.where(np.arange(n) % 2 == 0, 1.0, -1.0)
+    mc = L.ModelCfg(task=L.CLASSIFICATION, keep_w0=1, keep_w1=1, k=k, l2_w1=1e-3, l2_v=1e-3)
+    sc = L.SolverCfg(solver=L.FTRL, max_iter=n - 1, random_step=1, alpha_w=0.1, alpha_v=0.1, beta_w=1.0, beta_v=1.0, min_target=-1.0, max_target=1.0,
+                     mode=L.MODE_MINIBATCH, batch_size=4096, precision=L.F32, compat=L.COMPAT_REFERENCE, step_size=-1)
+    rs = np.diff(rowptr.astype(np.int64)).astype(np.int32)
+    ci = col.astype(np.int32); v64 = val.astype(np.float64)
+    w0 = C.c_double(0.0); w = np.zeros(p); v = np.zeros((p, k))
+    rc = lib.fmwr_train(C.byref(mc), C.byref(sc), C.c_int64(n), C.c_int64(p), C.c_int64(ci.size), L.ptr(rs), L.ptr(ci), L.ptr(v64), L.ptr(y),
+                        C.byref(w0), L.ptr(w), L.ptr(v), None)
+    assert rc == L.ERR_SHAPE if hasattr(L, "ERR_SHAPE") else rc != 0
+    msg = lib.fmwr_last_error().decode()
+    assert ("out of range" in msg) if bad == "range" else ("ascending" in msg)
+    # and the library is still usable afterwards
+    col2 = synth.fields_csr(n, fields, None, 1, 5)[1]
+    ci2 = col2.astype(np.int32)
+    L.check(lib.fmwr_train(C.byref(mc), C.byref(sc), C.c_int64(n), C.c_int64(p), C.c_int64(ci2.size), L.ptr(rs), L.ptr(ci2), L.ptr(v64), L.ptr(y),
+                           C.byref(w0), L.ptr(w), L.ptr(v), None))
+    assert np.isfinite(w).all() and np.abs(w).sum() > 0      # (V starts at zero and an all-zero V has a zero gradient)
